@@ -1,0 +1,189 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the REFERENCE'S OWN code on seeded inputs.
+
+Run in the build container only (needs /root/reference, read-only).  The reference scripts
+cannot be imported (they create private directories and import missing packages at import
+time), so the hot-path classes/functions are lifted out of their source files by ``ast`` and
+``exec``-ed unchanged in a namespace that supplies torch / numpy / scipy.  Nothing from the
+reference is written into this repository except the numerical outputs.
+
+    python oracle/make_golden.py            # rewrites tests/golden/
+"""
+from __future__ import annotations
+
+import ast
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import unet_oracle as O          # noqa: E402  (only for synth inputs / weights)
+
+REF = "/root/reference"
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def lift(relpath: str, names):
+    src = open(os.path.join(REF, relpath)).read()
+    tree = ast.parse(src)
+    ns = {"torch": torch, "nn": nn, "np": np, "F": torch.nn.functional}
+    from scipy.ndimage import distance_transform_edt
+    ns["distance_transform_edt"] = distance_transform_edt
+    got = []
+    for node in tree.body:
+        if isinstance(node, (ast.ClassDef, ast.FunctionDef)) and node.name in names:
+            code = compile(ast.Module(body=[node], type_ignores=[]), relpath, "exec")
+            exec(code, ns)
+            got.append(node.name)
+    missing = set(names) - set(got)
+    assert not missing, f"{relpath}: missing {missing}"
+    return ns
+
+
+def edge_masks(H, W, seed=0):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    yy, xx = np.mgrid[0:H, 0:W]
+    ms = {}
+    ms["all0"] = np.zeros((H, W), bool)
+    ms["all1"] = np.ones((H, W), bool)
+    m = np.zeros((H, W), bool); m[H // 3, W // 2] = True
+    ms["single_fg"] = m
+    ms["single_bg"] = ~m
+    m = np.zeros((H, W), bool); m[H // 4, :] = True; m[(3 * H) // 4, :] = True   # abl.py:232-234 style
+    ms["hlines"] = m
+    m = np.zeros((H, W), bool); m[:, W // 5] = True
+    ms["vline"] = m
+    ms["checker"] = ((yy + xx) % 2).astype(bool)
+    ms["bernoulli"] = rng.random((H, W)) < 0.5
+    ms["sparse"] = rng.random((H, W)) < 0.01
+    ms["disc"] = (yy - H * 0.55) ** 2 + (xx - W * 0.4) ** 2 <= (min(H, W) / 3.1) ** 2
+    m = np.zeros((H, W), bool); m[0, 0] = True; m[H - 1, W - 1] = True
+    ms["corners"] = m
+    m = np.zeros((H, W), bool); m[2:H - 2, 2:W - 2] = True; m[H // 2 - 2:H // 2 + 2, W // 2 - 3:W // 2 + 3] = False
+    ms["box_with_hole"] = m
+    return ms
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+
+    # ---------------- EDT / SDF -------------------------------------------------------
+    bl = lift("src/train_with_boundary_loss.py",
+              ["signed_distance_map_np", "batch_sdf_from_masks", "SymmetricBoundaryLoss",
+               "CompositeSegLoss", "BCEDiceLoss"])
+    sdf = {}
+    for (H, W) in ((32, 48), (17, 5), (64, 64)):
+        for name, m in edge_masks(H, W, seed=H * 1000 + W).items():
+            t = torch.from_numpy(m.astype(np.float32))[None, None]
+            sdf[f"{name}_{H}x{W}_mask"] = np.packbits(m)
+            sdf[f"{name}_{H}x{W}_raw"] = bl["signed_distance_map_np"](m.astype(np.uint8))
+            sdf[f"{name}_{H}x{W}_norm"] = bl["batch_sdf_from_masks"](t)[0, 0].numpy()
+    _, m224 = O.synth_batch(2, 224, 224, seed=7)
+    sdf["disc_224x224_mask"] = np.packbits(m224[0, 0].numpy().astype(bool))
+    sdf["disc_224x224_norm"] = bl["batch_sdf_from_masks"](m224[:1])[0, 0].numpy()
+    np.savez_compressed(os.path.join(OUT, "sdf.npz"), **sdf)
+
+    # ---------------- losses & metrics --------------------------------------------------
+    tb = lift("train_bce_dice.py", ["BCEDiceLoss", "dice_metric", "iou_metric"])
+    fd = lift("src/train_with_focalDice.py", ["FocalLoss", "FocalDiceLoss", "precision_recall_f1"])
+    fp = lift("src/finetune_pseudo.py", ["BCEDiceLoss", "dice_metric", "iou_metric"])
+    f224 = lift("src/finetune_for_224.py", ["BCEDiceLossPerSample", "dice_iou_at_t"])
+
+    B, H, W = 3, 40, 56
+    rng = np.random.Generator(np.random.PCG64(11))
+    _, targets = O.synth_batch(B, H, W, seed=3)
+    logits = torch.from_numpy((rng.standard_normal((B, 1, H, W)) * 2.5).astype(np.float32))
+    logits = logits + 3.0 * (targets - 0.4)          # correlated with the mask, like a trained net
+    logits[0, 0, 0, :8] = torch.tensor([0.0, 1e-8, -1e-8, 6e-8, 1.2e-7, -1.2e-7, 30.0, -30.0])
+    losses = {"logits": logits.numpy(), "targets": np.packbits(targets.numpy().astype(bool)),
+              "shape": np.array([B, 1, H, W])}
+
+    def run(name, crit):
+        x = logits.clone().requires_grad_(True)
+        out = crit(x, targets)
+        if out.dim():
+            losses[name + "_value"] = out.detach().numpy()
+            out = out.sum()
+        else:
+            losses[name + "_value"] = np.float64(out.item())
+        out.backward()
+        losses[name + "_grad"] = x.grad.numpy()
+
+    run("bce_dice", tb["BCEDiceLoss"](bce_weight=0.5, smooth=1.0))
+    run("bce_dice_w03_s2", tb["BCEDiceLoss"](bce_weight=0.3, smooth=2.0))
+    run("bce_dice_dims123", fp["BCEDiceLoss"](bce_weight=0.5, smooth=1.0))
+    run("bce_dice_per_sample", f224["BCEDiceLossPerSample"]())
+    run("focal_a025", fd["FocalLoss"](alpha=0.25, gamma=2.0, reduction="mean"))
+    run("focal_sum_g15", fd["FocalLoss"](alpha=0.6, gamma=1.5, reduction="sum"))
+    run("focal_dice", fd["FocalDiceLoss"](alpha=0.5, gamma=2.0, smooth=1.0, w_focal=0.7))
+    run("boundary", bl["SymmetricBoundaryLoss"]())
+    run("boundary_noabs", bl["SymmetricBoundaryLoss"](t=0.4, w_gt=0.8, w_pred=0.3, use_abs=False, scale=2.0))
+    run("composite", bl["CompositeSegLoss"](bce_weight=0.5, boundary_weight=0.3))
+
+    losses["soft_dice"] = np.float64(tb["dice_metric"](logits, targets))
+    for t in (0.2, 0.5, 0.65, 0.8):
+        tag = f"t{int(round(t * 100)):02d}"
+        losses["iou_" + tag] = np.float64(tb["iou_metric"](logits, targets, t=t))
+        losses["hard_dice_" + tag] = np.float64(fp["dice_metric"](logits, targets, t=t))
+        losses["prf_" + tag] = np.array(fd["precision_recall_f1"](logits, targets, t=t))
+        losses["dice_iou_at_" + tag] = np.array(f224["dice_iou_at_t"](logits, targets, t=t))
+        losses["mask_gt_" + tag] = np.packbits((torch.sigmoid(logits) > t).numpy())
+        losses["mask_ge_" + tag] = np.packbits((torch.sigmoid(logits) >= t).numpy())
+    ths = np.linspace(0.2, 0.8, 13)
+    sw = []
+    for t in ths:                                         # train_bce_dice.py:223-227
+        preds = (torch.sigmoid(logits) > t).float()
+        inter = (preds * targets).sum((2, 3)); denom = preds.sum((2, 3)) + targets.sum((2, 3))
+        sw.append(((2 * inter + 1.0) / (denom + 1.0)).mean().item())
+    losses["sweep13"] = np.array(sw)
+    np.savez_compressed(os.path.join(OUT, "losses.npz"), **losses)
+
+    # ---------------- model -------------------------------------------------------------
+    ct = lift("src/create_testset.py", ["DoubleConv", "UNet"])
+    model = {}
+    for tag, (B, H, W) in {"a": (2, 32, 32), "b": (1, 48, 16)}.items():
+        net = ct["UNet"](in_channels=3, out_channels=1)
+        sd = O.synth_state_dict(seed=1)
+        net.load_state_dict(sd, strict=True)
+        keys = list(net.state_dict().keys())
+        assert keys == [k for k, _ in O.state_dict_spec()], "state-dict key order drifted"
+        x, tgt = O.synth_batch(B, H, W, seed=5)
+
+        def logits_of(n, inp):                        # forward minus the trailing sigmoid (:83)
+            acts = {}
+            hnd = n.final_conv.register_forward_hook(lambda m, i, o: acts.__setitem__("z", o))
+            n(inp)
+            hnd.remove()
+            return acts["z"]
+
+        net.eval()
+        with torch.no_grad():
+            model[f"{tag}_eval_logits"] = logits_of(net, x).numpy()
+        net.train()
+        z = logits_of(net, x)
+        model[f"{tag}_train_logits"] = z.detach().numpy()
+        loss = tb["BCEDiceLoss"]()(z, tgt)
+        loss.backward()
+        model[f"{tag}_train_loss"] = np.float64(loss.item())
+        for k, p in net.named_parameters():
+            g = p.grad.detach().double()
+            model[f"{tag}_gnorm/{k}"] = np.float64(g.norm().item())
+            model[f"{tag}_ghead/{k}"] = p.grad.detach().flatten()[:8].numpy()
+        for k, b in net.named_buffers():
+            if k.endswith("running_mean") or k.endswith("running_var"):
+                model[f"{tag}_buf/{k}"] = b.detach().flatten()[:8].numpy()
+        model[f"{tag}_shape"] = np.array([B, 3, H, W])
+    model["n_params"] = np.int64(sum(p.numel() for p in net.parameters()))
+    np.savez_compressed(os.path.join(OUT, "model.npz"), **model)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()
