@@ -1,0 +1,540 @@
+// Bandwidth-bound kernels around the convolutions: weight (un)packing, input im2col, batch-norm
+// finalize / apply / backward, ReLU, 2x2 max-pool (+ its backward routing), the 1x1 head.
+// All of them are single coalesced passes with 16-byte vectors (8 bf16 channels per thread).
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace cs {
+
+static inline int grid_for(long long work, int block, int cap = 148 * 16) {
+  long long g = (work + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (int)g;
+}
+
+struct alignas(16) Vec8 { uint32_t w[4]; };
+CS_DEVINL void unpack8(const Vec8& v, float* f) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { f[2 * i] = bf16_lo(v.w[i]); f[2 * i + 1] = bf16_hi(v.w[i]); }
+}
+CS_DEVINL Vec8 pack8(const float* f) {
+  Vec8 v;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v.w[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+CS_DEVINL Vec8 ld8(const bf16* p) { return *reinterpret_cast<const Vec8*>(p); }
+CS_DEVINL void st8(bf16* p, const Vec8& v) { *reinterpret_cast<Vec8*>(p) = v; }
+
+// ============================================================================ weight packing
+// Tile of 32 (a) x 32 (b) pairs, T taps each; reads are contiguous in (b, t), the two outputs are
+// written contiguous in b (out_ab) and in a (out_ba) through a shared-memory transpose.
+__global__ void pack_pairs_kernel(const float* __restrict__ in, int Na, int Nb, int T, bf16* __restrict__ out_ab,
+                                  TapMap map_ab, bf16* __restrict__ out_ba, TapMap map_ba) {
+  __shared__ float tile[9][32][33];
+  const int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
+  const int nb = min(32, Nb - b0), na = min(32, Na - a0);
+  for (int ai = threadIdx.y; ai < na; ai += blockDim.y) {
+    const float* src = in + ((size_t)(a0 + ai) * Nb + b0) * T;
+    for (int i = threadIdx.x; i < nb * T; i += 32) tile[i % T][ai][i / T] = src[i];
+  }
+  __syncthreads();
+  for (int t = 0; t < T; ++t) {
+    if (out_ab) {
+      for (int ai = threadIdx.y; ai < na; ai += blockDim.y)
+        if ((int)threadIdx.x < nb)
+          out_ab[((size_t)map_ab.v[t] * Na + a0 + ai) * Nb + b0 + threadIdx.x] = __float2bfloat16(tile[t][ai][threadIdx.x]);
+    }
+    if (out_ba) {
+      for (int bi = threadIdx.y; bi < nb; bi += blockDim.y)
+        if ((int)threadIdx.x < na)
+          out_ba[((size_t)map_ba.v[t] * Nb + b0 + bi) * Na + a0 + threadIdx.x] = __float2bfloat16(tile[t][threadIdx.x][bi]);
+    }
+  }
+}
+cudaError_t launch_pack_pairs(const float* in, int Na, int Nb, int T, bf16* out_ab, TapMap map_ab, bf16* out_ba,
+                              TapMap map_ba, cudaStream_t s) {
+  dim3 grid((Nb + 31) / 32, (Na + 31) / 32), block(32, 8);
+  pack_pairs_kernel<<<grid, block, 0, s>>>(in, Na, Nb, T, out_ab, map_ab, out_ba, map_ba);
+  return cudaGetLastError();
+}
+
+__global__ void pack_first_kernel(const float* __restrict__ in, int Cout, int Cin, bf16* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Cout * 64) return;
+  const int co = i >> 6, k = i & 63;
+  float v = 0.f;
+  if (k < 9 * Cin) {
+    const int tap = k / Cin, c = k - tap * Cin;
+    v = in[((size_t)co * Cin + c) * 9 + tap];
+  }
+  out[i] = __float2bfloat16(v);
+}
+cudaError_t launch_pack_first(const float* in, int Cout, int Cin, bf16* out, cudaStream_t s) {
+  pack_first_kernel<<<(Cout * 64 + 255) / 256, 256, 0, s>>>(in, Cout, Cin, out);
+  return cudaGetLastError();
+}
+
+__global__ void unpack_pairs_kernel(const float* __restrict__ dwp, int Na, int Nb, int T, TapMap map,
+                                    float* __restrict__ grad) {
+  const size_t pairs = (size_t)Na * Nb;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < pairs; i += (size_t)gridDim.x * blockDim.x) {
+    for (int t = 0; t < T; ++t) grad[i * T + map.v[t]] = dwp[(size_t)t * pairs + i];
+  }
+}
+cudaError_t launch_unpack_pairs(const float* dwp, int Na, int Nb, int T, TapMap map, float* grad, cudaStream_t s) {
+  unpack_pairs_kernel<<<grid_for((long long)Na * Nb, 256), 256, 0, s>>>(dwp, Na, Nb, T, map, grad);
+  return cudaGetLastError();
+}
+
+__global__ void unpack_first_kernel(const float* __restrict__ dwp, int Cout, int Cin, float* __restrict__ grad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Cout * Cin * 9) return;
+  const int co = i / (Cin * 9), rem = i - co * Cin * 9;
+  const int c = rem / 9, tap = rem - c * 9;
+  grad[i] = dwp[co * 64 + tap * Cin + c];
+}
+cudaError_t launch_unpack_first(const float* dwp, int Cout, int Cin, float* grad, cudaStream_t s) {
+  unpack_first_kernel<<<(Cout * Cin * 9 + 255) / 256, 256, 0, s>>>(dwp, Cout, Cin, grad);
+  return cudaGetLastError();
+}
+
+// ============================================================================ input im2col
+__global__ void im2col_first_kernel(const float* __restrict__ x, int B, int Cin, int H, int W, bf16* __restrict__ col) {
+  // one thread per (pixel, 8-wide k group): 8 groups cover the 64-wide padded K
+  const long long total = (long long)B * H * W * 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int kg = (int)(i & 7);
+    const long long p = i >> 3;
+    const int w = (int)(p % W);
+    const int h = (int)((p / W) % H);
+    const int b = (int)(p / ((long long)W * H));
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = kg * 8 + j;
+      float v = 0.f;
+      if (k < 9 * Cin) {
+        const int tap = k / Cin, c = k - tap * Cin;
+        const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(&x[(((size_t)b * Cin + c) * H + hh) * W + ww]);
+      }
+      f[j] = v;
+    }
+    st8(col + p * 64 + kg * 8, pack8(f));
+  }
+}
+cudaError_t launch_im2col_first(const float* x, int B, int Cin, int H, int W, bf16* col, cudaStream_t s) {
+  if (9 * Cin > 64) return cudaErrorInvalidValue;
+  im2col_first_kernel<<<grid_for((long long)B * H * W * 8, 256), 256, 0, s>>>(x, B, Cin, H, W, col);
+  return cudaGetLastError();
+}
+
+// ============================================================================ batch norm: statistics -> affine
+__global__ void bn_finalize_train_kernel(BnFinalizeArgs a) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && a.num_batches_tracked) *a.num_batches_tracked += 1;
+  if (c >= a.C) return;
+  const double mean = a.sum[c] / a.count;
+  double var = a.sq[c] / a.count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const double invstd = rsqrt(var + (double)a.eps);
+  const float sc = (float)((double)a.gamma[c] * invstd);
+  a.scale[c] = sc;
+  a.shift[c] = (float)((double)a.beta[c] - mean * (double)a.gamma[c] * invstd);
+  a.mean[c] = (float)mean;
+  a.invstd[c] = (float)invstd;
+  if (a.running_mean) {
+    // The conv bias is never added to the activations (train-mode BN subtracts it again); it only
+    // shows up in the running mean.
+    const double bias = a.conv_bias ? (double)a.conv_bias[c] : 0.0;
+    const double m = (double)a.momentum;
+    a.running_mean[c] = (float)((1.0 - m) * (double)a.running_mean[c] + m * (mean + bias));
+    const double unbiased = a.count > 1.0 ? var * a.count / (a.count - 1.0) : var;
+    a.running_var[c] = (float)((1.0 - m) * (double)a.running_var[c] + m * unbiased);
+  }
+}
+cudaError_t launch_bn_finalize_train(const BnFinalizeArgs& a, cudaStream_t s) {
+  bn_finalize_train_kernel<<<(a.C + 127) / 128, 128, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+__global__ void bn_fold_eval_kernel(const float* gamma, const float* beta, const float* conv_bias, const float* rm,
+                                    const float* rv, float eps, float* scale, float* shift, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float invstd = 1.0f / sqrtf(rv[c] + eps);
+  const float sc = gamma[c] * invstd;
+  scale[c] = sc;
+  shift[c] = beta[c] + ((conv_bias ? conv_bias[c] : 0.f) - rm[c]) * sc;
+}
+cudaError_t launch_bn_fold_eval(const float* gamma, const float* beta, const float* conv_bias, const float* rm,
+                                const float* rv, float eps, float* scale, float* shift, int C, cudaStream_t s) {
+  bn_fold_eval_kernel<<<(C + 127) / 128, 128, 0, s>>>(gamma, beta, conv_bias, rm, rv, eps, scale, shift, C);
+  return cudaGetLastError();
+}
+
+// ============================================================================ BN apply + ReLU (+ 2x2 max-pool)
+template <bool POOL>
+__global__ void bn_relu_kernel(const bf16* __restrict__ y, int B, int H, int W, int C, const float* __restrict__ scale,
+                               const float* __restrict__ shift, bf16* __restrict__ out, int out_pitch, int out_c0,
+                               bf16* __restrict__ pooled) {
+  const int cg = C >> 3;
+  if (!POOL) {
+    const long long total = (long long)B * H * W * cg;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+      const int g = (int)(i % cg);
+      const long long p = i / cg;
+      float f[8], sc[8], sh[8];
+      unpack8(ld8(y + p * C + g * 8), f);
+      *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(scale + g * 8));
+      *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(scale + g * 8 + 4));
+      *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(shift + g * 8));
+      *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(shift + g * 8 + 4));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+      st8(out + p * out_pitch + out_c0 + g * 8, pack8(f));
+    }
+  } else {
+    const int H2 = H >> 1, W2 = W >> 1;
+    const long long total = (long long)B * H2 * W2 * cg;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+      const int g = (int)(i % cg);
+      const long long q = i / cg;                      // pooled pixel index
+      const int w2 = (int)(q % W2);
+      const int h2 = (int)((q / W2) % H2);
+      const int b = (int)(q / ((long long)W2 * H2));
+      float sc[8], sh[8], mx[8];
+      *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(scale + g * 8));
+      *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(scale + g * 8 + 4));
+      *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(shift + g * 8));
+      *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(shift + g * 8 + 4));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mx[j] = 0.f;          // post-ReLU values are >= 0
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const long long p = ((long long)b * H + 2 * h2 + (d >> 1)) * W + 2 * w2 + (d & 1);
+        float f[8];
+        unpack8(ld8(y + p * C + g * 8), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+        const Vec8 v = pack8(f);
+        st8(out + p * out_pitch + out_c0 + g * 8, v);
+        float r[8];
+        unpack8(v, r);                                  // pool the values as stored (bf16-rounded)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mx[j] = fmaxf(mx[j], r[j]);
+      }
+      st8(pooled + q * C + g * 8, pack8(mx));
+    }
+  }
+}
+cudaError_t launch_bn_relu(const bf16* y, int B, int H, int W, int C, const float* scale, const float* shift,
+                           bf16* out, int out_pitch, int out_c0, bf16* pooled, cudaStream_t s) {
+  if (pooled) {
+    bn_relu_kernel<true><<<grid_for((long long)B * (H / 2) * (W / 2) * (C / 8), 256), 256, 0, s>>>(
+        y, B, H, W, C, scale, shift, out, out_pitch, out_c0, pooled);
+  } else {
+    bn_relu_kernel<false><<<grid_for((long long)B * H * W * (C / 8), 256), 256, 0, s>>>(y, B, H, W, C, scale, shift,
+                                                                                         out, out_pitch, out_c0, pooled);
+  }
+  return cudaGetLastError();
+}
+
+__global__ void maxpool_kernel(const bf16* __restrict__ in, int in_pitch, int in_c0, int B, int H, int W, int C,
+                               bf16* __restrict__ pooled) {
+  const int cg = C >> 3, H2 = H >> 1, W2 = W >> 1;
+  const long long total = (long long)B * H2 * W2 * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    const long long q = i / cg;
+    const int w2 = (int)(q % W2);
+    const int h2 = (int)((q / W2) % H2);
+    const int b = (int)(q / ((long long)W2 * H2));
+    float mx[8];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      const long long p = ((long long)b * H + 2 * h2 + (d >> 1)) * W + 2 * w2 + (d & 1);
+      float f[8];
+      unpack8(ld8(in + p * in_pitch + in_c0 + g * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mx[j] = d == 0 ? f[j] : fmaxf(mx[j], f[j]);
+    }
+    st8(pooled + q * C + g * 8, pack8(mx));
+  }
+}
+cudaError_t launch_maxpool(const bf16* in, int in_pitch, int in_c0, int B, int H, int W, int C, bf16* pooled,
+                           cudaStream_t s) {
+  maxpool_kernel<<<grid_for((long long)B * (H / 2) * (W / 2) * (C / 8), 256), 256, 0, s>>>(in, in_pitch, in_c0, B, H, W,
+                                                                                           C, pooled);
+  return cudaGetLastError();
+}
+
+// ============================================================================ BN + ReLU (+ pool/skip) backward
+// g_total(pixel) = g[pixel] (+ g_pool[window] if the pixel is the first maximum of its 2x2 window).
+// mask = (y*scale + shift > 0), evaluated on the bf16-rounded activation exactly as the forward stored it.
+struct BnCoef { float sc[8], sh[8], mu[8], is[8]; };
+CS_DEVINL void load_coef(const BnBwdArgs& a, int g, BnCoef& k) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    *reinterpret_cast<float4*>(k.sc + 4 * h) = __ldg(reinterpret_cast<const float4*>(a.scale + g * 8 + 4 * h));
+    *reinterpret_cast<float4*>(k.sh + 4 * h) = __ldg(reinterpret_cast<const float4*>(a.shift + g * 8 + 4 * h));
+    *reinterpret_cast<float4*>(k.mu + 4 * h) = __ldg(reinterpret_cast<const float4*>(a.mean + g * 8 + 4 * h));
+    *reinterpret_cast<float4*>(k.is + 4 * h) = __ldg(reinterpret_cast<const float4*>(a.invstd + g * 8 + 4 * h));
+  }
+}
+// Computes, for one pixel (no pool) or one 2x2 window (pool), the masked gradient gm[d][8] and xhat[d][8].
+template <bool POOL>
+CS_DEVINL void masked_grad(const BnBwdArgs& a, const BnCoef& k, int g, long long unit, float gm[][8], float xh[][8],
+                           long long pix[]) {
+  constexpr int ND = POOL ? 4 : 1;
+  float act[ND][8];
+  if (POOL) {
+    const int H2 = a.H >> 1, W2 = a.W >> 1;
+    const int w2 = (int)(unit % W2);
+    const int h2 = (int)((unit / W2) % H2);
+    const int b = (int)(unit / ((long long)W2 * H2));
+#pragma unroll
+    for (int d = 0; d < ND; ++d) pix[d] = ((long long)b * a.H + 2 * h2 + (d >> 1)) * a.W + 2 * w2 + (d & 1);
+  } else {
+    pix[0] = unit;
+  }
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    float yv[8], gv[8];
+    unpack8(ld8(a.y + pix[d] * a.C + g * 8), yv);
+    unpack8(ld8(a.g + pix[d] * a.g_pitch + a.g_c0 + g * 8), gv);
+    float t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = fmaxf(fmaf(yv[j], k.sc[j], k.sh[j]), 0.f);
+    unpack8(pack8(t), act[d]);                          // bf16-rounded, as stored by the forward
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      gm[d][j] = gv[j];
+      xh[d][j] = (yv[j] - k.mu[j]) * k.is[j];
+    }
+  }
+  if (POOL) {
+    float gp[8];
+    unpack8(ld8(a.g_pool + unit * a.C + g * 8), gp);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int best = 0;
+      float bv = act[0][j];
+#pragma unroll
+      for (int d = 1; d < ND; ++d)
+        if (act[d][j] > bv) { bv = act[d][j]; best = d; }
+#pragma unroll
+      for (int d = 0; d < ND; ++d)
+        if (d == best) gm[d][j] += gp[j];
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < ND; ++d)
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (!(act[d][j] > 0.f)) gm[d][j] = 0.f;
+}
+
+template <bool POOL>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdArgs a) {
+  constexpr int ND = POOL ? 4 : 1;
+  extern __shared__ float sacc[];                       // [2][C]
+  const int cg = a.C >> 3;
+  for (int i = threadIdx.x; i < 2 * a.C; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int g = threadIdx.x % cg;
+  const int ri = threadIdx.x / cg;
+  const int rpb = blockDim.x / cg;
+  const long long units = POOL ? (long long)a.B * (a.H >> 1) * (a.W >> 1) : (long long)a.B * a.H * a.W;
+  BnCoef k;
+  load_coef(a, g, k);
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  if (ri < rpb) {
+    for (long long u = (long long)blockIdx.x * rpb + ri; u < units; u += (long long)gridDim.x * rpb) {
+      float gm[ND][8], xh[ND][8];
+      long long pix[ND];
+      masked_grad<POOL>(a, k, g, u, gm, xh, pix);
+#pragma unroll
+      for (int d = 0; d < ND; ++d)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s1[j] += gm[d][j]; s2[j] += gm[d][j] * xh[d][j]; }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sacc[g * 8 + j], s1[j]);
+      atomicAdd(&sacc[a.C + g * 8 + j], s2[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < a.C; i += blockDim.x) {
+    atomicAdd(&a.s1[i], (double)sacc[i]);
+    atomicAdd(&a.s2[i], (double)sacc[a.C + i]);
+  }
+}
+cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t s) {
+  const int cg = a.C / 8;
+  if (cg > 256) return cudaErrorInvalidValue;
+  const int rpb = 256 / cg;
+  const long long units = a.g_pool ? (long long)a.B * (a.H / 2) * (a.W / 2) : (long long)a.B * a.H * a.W;
+  const int grid = grid_for(units, rpb * 4, 148 * 4);
+  const size_t smem = 2 * a.C * sizeof(float);
+  if (a.g_pool) bn_bwd_reduce_kernel<true><<<grid, 256, smem, s>>>(a);
+  else bn_bwd_reduce_kernel<false><<<grid, 256, smem, s>>>(a);
+  return cudaGetLastError();
+}
+
+template <bool POOL>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwdArgs a) {
+  constexpr int ND = POOL ? 4 : 1;
+  const int cg = a.C >> 3;
+  const long long units = POOL ? (long long)a.B * (a.H >> 1) * (a.W >> 1) : (long long)a.B * a.H * a.W;
+  const double inv_n = 1.0 / ((double)a.B * a.H * a.W);
+  if (blockIdx.x == 0) {                                 // parameter gradients of the BN affine
+    for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+      if (a.grad_gamma) a.grad_gamma[c] = (float)a.s2[c];
+      if (a.grad_beta) a.grad_beta[c] = (float)a.s1[c];
+      if (a.grad_conv_bias) a.grad_conv_bias[c] = 0.f;   // exactly zero: BN removes the bias again
+    }
+  }
+  const long long total = units * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    const long long u = i / cg;
+    BnCoef k;
+    load_coef(a, g, k);
+    float c1[8], c2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      c1[j] = (float)(a.s1[g * 8 + j] * inv_n);
+      c2[j] = (float)(a.s2[g * 8 + j] * inv_n);
+    }
+    float gm[ND][8], xh[ND][8];
+    long long pix[ND];
+    masked_grad<POOL>(a, k, g, u, gm, xh, pix);
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = k.sc[j] * (gm[d][j] - c1[j] - xh[d][j] * c2[j]);
+      st8(a.dy + pix[d] * a.C + g * 8, pack8(o));
+    }
+  }
+}
+cudaError_t launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t s) {
+  const long long units = a.g_pool ? (long long)a.B * (a.H / 2) * (a.W / 2) : (long long)a.B * a.H * a.W;
+  const int grid = grid_for(units * (a.C / 8), 256);
+  if (a.g_pool) bn_bwd_apply_kernel<true><<<grid, 256, 0, s>>>(a);
+  else bn_bwd_apply_kernel<false><<<grid, 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+// ============================================================================ 1x1 head (C -> 1)
+__global__ void head_fwd_kernel(const bf16* __restrict__ act, long long P, int C, const float* __restrict__ w,
+                                const float* __restrict__ b, float* __restrict__ logits) {
+  // 8 lanes per pixel, each lane strides over the channel groups
+  const int cg = C >> 3;
+  const int sub = threadIdx.x & 7;
+  const long long stride = (long long)gridDim.x * (blockDim.x >> 3);
+  const float bias = b ? __ldg(b) : 0.f;
+  for (long long p = blockIdx.x * (long long)(blockDim.x >> 3) + (threadIdx.x >> 3); p < P; p += stride) {
+    float acc = 0.f;
+    for (int g = sub; g < cg; g += 8) {
+      float f[8];
+      unpack8(ld8(act + p * C + g * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc = fmaf(f[j], __ldg(w + g * 8 + j), acc);
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (sub == 0) logits[p] = acc + bias;
+  }
+}
+cudaError_t launch_head_fwd(const bf16* act, long long P, int C, const float* w, const float* b, float* logits,
+                            cudaStream_t s) {
+  // P is always a multiple of 32 here (H, W multiples of 16), so every warp iterates uniformly
+  head_fwd_kernel<<<grid_for(P * 8, 256), 256, 0, s>>>(act, P, C, w, b, logits);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) head_bwd_kernel(const bf16* __restrict__ act, const float* __restrict__ dlogits,
+                                                      long long P, int C, const float* __restrict__ w,
+                                                      bf16* __restrict__ g_act, float* __restrict__ grad_w,
+                                                      float* __restrict__ grad_b) {
+  extern __shared__ float sacc[];                       // [C + 1]
+  for (int i = threadIdx.x; i <= C; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int cg = C >> 3;
+  const int g = threadIdx.x % cg, ri = threadIdx.x / cg, rpb = blockDim.x / cg;
+  float wv[8], acc[8], accb = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { wv[j] = __ldg(w + g * 8 + j); acc[j] = 0.f; }
+  if (ri < rpb) {
+    for (long long p = (long long)blockIdx.x * rpb + ri; p < P; p += (long long)gridDim.x * rpb) {
+      const float d = __ldg(dlogits + p);
+      float f[8], o[8];
+      unpack8(ld8(act + p * C + g * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { acc[j] = fmaf(d, f[j], acc[j]); o[j] = d * wv[j]; }
+      st8(g_act + p * C + g * 8, pack8(o));
+      if (g == 0) accb += d;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&sacc[g * 8 + j], acc[j]);
+    if (g == 0) atomicAdd(&sacc[C], accb);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&grad_w[i], sacc[i]);
+  if (threadIdx.x == 0 && grad_b) atomicAdd(grad_b, sacc[C]);
+}
+cudaError_t launch_head_bwd(const bf16* act, const float* dlogits, long long P, int C, const float* w, bf16* g_act,
+                            float* grad_w, float* grad_b, cudaStream_t s) {
+  const int rpb = 256 / (C / 8);
+  cudaError_t e = cudaMemsetAsync(grad_w, 0, C * sizeof(float), s);
+  if (e != cudaSuccess) return e;
+  if (grad_b) { e = cudaMemsetAsync(grad_b, 0, sizeof(float), s); if (e != cudaSuccess) return e; }
+  head_bwd_kernel<<<grid_for(P, rpb * 8, 148 * 4), 256, (C + 1) * sizeof(float), s>>>(act, dlogits, P, C, w, g_act,
+                                                                                     grad_w, grad_b);
+  return cudaGetLastError();
+}
+
+// ============================================================================ per-channel sum (convT bias grad)
+__global__ void __launch_bounds__(256) channel_sum_kernel(const bf16* __restrict__ gsrc, int pitch, int c0, long long P,
+                                                         int C, float* __restrict__ out) {
+  extern __shared__ float sacc[];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int cg = C >> 3;
+  const int g = threadIdx.x % cg, ri = threadIdx.x / cg, rpb = blockDim.x / cg;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (ri < rpb) {
+    for (long long p = (long long)blockIdx.x * rpb + ri; p < P; p += (long long)gridDim.x * rpb) {
+      float f[8];
+      unpack8(ld8(gsrc + p * pitch + c0 + g * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&sacc[g * 8 + j], acc[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&out[i], sacc[i]);
+}
+cudaError_t launch_channel_sum(const bf16* g, int pitch, int c0, long long P, int C, float* out, cudaStream_t s) {
+  if (C / 8 > 256) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(out, 0, C * sizeof(float), s);
+  if (e != cudaSuccess) return e;
+  const int rpb = 256 / (C / 8);
+  channel_sum_kernel<<<grid_for(P, rpb * 8, 148 * 4), 256, C * sizeof(float), s>>>(g, pitch, c0, P, C, out);
+  return cudaGetLastError();
+}
+
+}  // namespace cs

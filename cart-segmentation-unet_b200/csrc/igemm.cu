@@ -1,0 +1,517 @@
+// tcgen05 / TMA implicit-GEMM kernels for sm_100a (see igemm.cuh for the operand model).
+//
+// Warp roles (192 threads, one CTA per SM):
+//   warp 0      TMA producer   (lane 0 issues; whole warp walks the pipeline)
+//   warp 1      MMA issuer     (lane 0 issues tcgen05.mma / tcgen05.commit)
+//   warps 2..5  epilogue       (TMEM -> registers -> swizzled smem -> TMA store / red.global)
+// Pipelines: smem full/empty mbarriers (TMA <-> MMA), TMEM full/empty mbarriers (MMA <-> epilogue,
+// double-buffered accumulators), persistent static tile schedule.
+#include "igemm.cuh"
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace cs {
+
+static constexpr int kThreads = 192;
+static constexpr int kAtomBytes = 1024;            // 8 rows x 128 B: one 128B-swizzle atom
+static constexpr int kASlotBytes = 18 * kAtomBytes; // (16 + 2 halo) image rows of 8 pixels x 64 ch
+static constexpr int kStageBytes = 128 * 128;      // epilogue staging: 128 pixels x 64 ch bf16
+
+CS_DEVINL void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// =============================================================================================
+//                                   pixel-major GEMM
+// =============================================================================================
+template <int BLOCK_N, int SA, int SB>
+struct PixLayout {
+  static constexpr int kBSlot = BLOCK_N * 128;
+  static constexpr int kA = 0;
+  static constexpr int kB = kA + SA * kASlotBytes;
+  static constexpr int kStage = kB + SB * kBSlot;
+  static constexpr int kVec = kStage + 2 * kStageBytes;      // 2 x 1024 floats
+  static constexpr int kRed = kVec + 2 * 1024 * 4;           // 4 x 64 x 2 floats
+  static constexpr int kBar = kRed + 4 * 64 * 2 * 4;
+  static constexpr int kNumBar = 2 * SA + 2 * SB + 4;
+  static constexpr int kTmemPtr = kBar + kNumBar * 8;
+  static constexpr int kTotal = kTmemPtr + 16;
+  static constexpr int kDyn = kTotal + 1024;                 // slack for manual 1024-B alignment
+  static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+};
+
+template <int BLOCK_N, int SA, int SB>
+__global__ void __launch_bounds__(kThreads, 1) pix_gemm_kernel(const __grid_constant__ PixGemmParams p) {
+  using L = PixLayout<BLOCK_N, SA, SB>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBar);
+  uint64_t* fullA = bars;
+  uint64_t* emptyA = fullA + SA;
+  uint64_t* fullB = emptyA + SA;
+  uint64_t* emptyB = fullB + SB;
+  uint64_t* tmem_full = emptyB + SB;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtr);
+  float* vec = reinterpret_cast<float*>(smem + L::kVec);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = p.tiles_w * p.tiles_h * p.batch;
+  const int num_tiles = m_tiles * p.n_blocks;
+  const bool want_stats = p.stat_sum != nullptr;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < SA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
+    for (int i = 0; i < SB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    fence_barrier_init();
+    for (int g = 0; g < p.G; ++g) tma_prefetch_desc(&p.tmapA[p.a_map[g]]);
+    tma_prefetch_desc(&p.tmapB);
+    tma_prefetch_desc(&p.tmapO[0]);
+  }
+  if (warp == 2) tmem_alloc<L::kTmemCols>(tmem_ptr);
+  {
+    const int nvec = p.o_blocks_per_map * BLOCK_N;           // <= 1024
+    for (int i = threadIdx.x; i < 1024; i += kThreads) {
+      float a = 0.f, b = 0.f;
+      if (!want_stats && i < nvec) {
+        a = p.scale ? p.scale[i] : 1.f;
+        b = p.shift ? p.shift[i] : 0.f;
+      }
+      vec[i] = a;
+      vec[1024 + i] = b;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int per_img = p.tiles_w * p.tiles_h;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    int sa = 0, pa = 0, sb = 0, pb = 0;
+    const uint32_t a_bytes = (16 + p.R - 1) * kAtomBytes;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_blocks, nb = tile - m_tile * p.n_blocks;
+      const int b = m_tile / per_img, rem = m_tile - b * per_img;
+      const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
+      const int w0 = tw * 8, h0 = th * 16, n0 = nb * BLOCK_N;
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        for (int g = 0; g < p.G; ++g) {
+          mbar_wait(&emptyA[sa], pa ^ 1);
+          if (lane == 0) {
+            mbar_arrive_expect_tx(&fullA[sa], a_bytes);
+            tma_load_4d(smem + L::kA + sa * kASlotBytes, &p.tmapA[p.a_map[g]], &fullA[sa], p.a_chan0 + kc * 64,
+                        w0 + p.a_dw[g], h0 + p.a_dh[g], b);
+          }
+          if (++sa == SA) { sa = 0; pa ^= 1; }
+          for (int r = 0; r < p.R; ++r) {
+            mbar_wait(&emptyB[sb], pb ^ 1);
+            if (lane == 0) {
+              mbar_arrive_expect_tx(&fullB[sb], L::kBSlot);
+              tma_load_2d(smem + L::kB + sb * L::kBSlot, &p.tmapB, &fullB[sb], kc * 64,
+                          (g * p.R + r) * p.Ntot + n0);
+            }
+            if (++sb == SB) { sb = 0; pb ^= 1; }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = make_idesc(128, BLOCK_N, 0, 0);
+    int sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      uint32_t accumulate = 0;
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        for (int g = 0; g < p.G; ++g) {
+          mbar_wait(&fullA[sa], pa);
+          for (int r = 0; r < p.R; ++r) {
+            mbar_wait(&fullB[sb], pb);
+            tc_fence_after();
+            if (lane == 0) {
+              const uint32_t a_addr = smem_u32(smem + L::kA + sa * kASlotBytes) + r * kAtomBytes;
+              const uint32_t b_addr = smem_u32(smem + L::kB + sb * L::kBSlot);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_bf16(d_tmem, make_smem_desc(a_addr + k * 32, 0, kAtomBytes),
+                          make_smem_desc(b_addr + k * 32, 0, kAtomBytes), idesc, accumulate);
+                accumulate = 1;
+              }
+              umma_commit(&emptyB[sb]);
+            }
+            __syncwarp();
+            if (++sb == SB) { sb = 0; pb ^= 1; }
+          }
+          if (lane == 0) umma_commit(&emptyA[sa]);
+          __syncwarp();
+          if (++sa == SA) { sa = 0; pa ^= 1; }
+        }
+      }
+      if (lane == 0) umma_commit(&tmem_full[acc]);
+      __syncwarp();
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (128 threads)
+    const int et = threadIdx.x - 64;
+    const int sub = warp & 3;                  // TMEM sub-partition this warp may read
+    const int ewarp = warp - 2;
+    const int row = sub * 32 + lane;           // pixel row of the tile held by this thread
+    float* red = reinterpret_cast<float*>(smem + L::kRed);
+    int acc = 0, acc_phase = 0;
+    uint32_t buf_ctr = 0;
+    const bool affine = !want_stats && (p.scale != nullptr || p.shift != nullptr || p.relu);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_blocks, nb = tile - m_tile * p.n_blocks;
+      const int b = m_tile / per_img, rem = m_tile - b * per_img;
+      const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
+      const int w0 = tw * 8, h0 = th * 16;
+      const int omap = nb / p.o_blocks_per_map;
+      const int n_in_map0 = (nb - omap * p.o_blocks_per_map) * BLOCK_N;
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int cb = 0; cb < BLOCK_N / 64; ++cb) {
+        uint8_t* sbuf = smem + L::kStage + (buf_ctr & 1) * kStageBytes;
+        ++buf_ctr;
+        if (et == 0) tma_store_wait_read<1>();           // the store issued 2 blocks ago has drained
+        bar_sync(1, 128);
+        uint32_t v[64];
+        tmem_ld32(taddr + cb * 64, v);
+        tmem_ld32(taddr + cb * 64 + 32, v + 32);
+        tmem_ld_wait();
+        if (cb == BLOCK_N / 64 - 1) {                    // accumulator fully read: hand it back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        uint32_t packed[32];
+        if (affine) {
+          const float* sc = vec + n_in_map0 + cb * 64;
+          const float* sh = vec + 1024 + n_in_map0 + cb * 64;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float a = __uint_as_float(v[2 * i]) * sc[2 * i] + sh[2 * i];
+            float c = __uint_as_float(v[2 * i + 1]) * sc[2 * i + 1] + sh[2 * i + 1];
+            if (p.relu) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
+            packed[i] = pack_bf16x2(a, c);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) packed[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+        }
+        {
+          uint8_t* rowp = sbuf + row * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint4 q = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+            *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = q;
+          }
+        }
+        fence_proxy_async();
+        bar_sync(2, 128);
+        if (et == 0) {
+          tma_store_4d(&p.tmapO[omap], sbuf, p.o_chan0 + n_in_map0 + cb * 64, w0, h0, b);
+          tma_store_commit();
+        }
+        if (want_stats) {
+          // Column sums over the staged bf16 tile: this warp covers rows [32*sub, 32*sub+32), lane
+          // covers the channel pair (2*lane, 2*lane+1); rows the image does not have are exact zeros.
+          const uint32_t* s32 = reinterpret_cast<const uint32_t*>(sbuf);
+          const int chunk = lane >> 2, word = lane & 3;
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {
+            const int r2 = sub * 32 + rr;
+            const uint32_t w = s32[r2 * 32 + (((chunk ^ (r2 & 7)) << 2) | word)];
+            const float f0 = bf16_lo(w), f1 = bf16_hi(w);
+            s0 += f0; q0 += f0 * f0; s1 += f1; q1 += f1 * f1;
+          }
+          float* rw = red + (ewarp * 64 + 2 * lane) * 2;
+          rw[0] = s0; rw[1] = q0; rw[2] = s1; rw[3] = q1;
+          bar_sync(3, 128);
+          const int c = et & 63, which = et >> 6;
+          float tot = 0.f;
+#pragma unroll
+          for (int w4 = 0; w4 < 4; ++w4) tot += red[(w4 * 64 + c) * 2 + which];
+          vec[which * 1024 + n_in_map0 + cb * 64 + c] += tot;
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (et == 0) tma_store_wait_all<0>();
+    if (want_stats) {
+      bar_sync(1, 128);
+      const int nvec = p.o_blocks_per_map * BLOCK_N;
+      for (int i = et; i < nvec; i += 128) {
+        const float s = vec[i], q = vec[1024 + i];
+        if (q != 0.f) {
+          atomicAdd(&p.stat_sum[i], (double)s);
+          atomicAdd(&p.stat_sq[i], (double)q);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<L::kTmemCols>(tmem_base);
+  }
+}
+
+template <int BLOCK_N, int SA, int SB>
+static cudaError_t launch_pix(const PixGemmParams& p, int num_sms, cudaStream_t stream) {
+  using L = PixLayout<BLOCK_N, SA, SB>;
+  static_assert(L::kDyn <= 232448, "shared memory budget exceeded");
+  auto kern = pix_gemm_kernel<BLOCK_N, SA, SB>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDyn);
+  });
+  if (attr_err != cudaSuccess) return attr_err;
+  const int num_tiles = p.tiles_w * p.tiles_h * p.batch * p.n_blocks;
+  const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  if (grid <= 0) return cudaSuccess;
+  kern<<<grid, kThreads, L::kDyn, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pix_gemm(const PixGemmParams& p, int block_n, int num_sms, cudaStream_t stream) {
+  switch (block_n) {
+    case 64: return launch_pix<64, 6, 8>(p, num_sms, stream);
+    case 128: return launch_pix<128, 3, 7>(p, num_sms, stream);
+    case 256: return launch_pix<256, 3, 4>(p, num_sms, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// =============================================================================================
+//                                   weight-gradient GEMM
+// =============================================================================================
+template <int BLOCK_N, int STAGES>
+struct WgLayout {
+  static constexpr int kDY = 2 * 16 * kAtomBytes;                 // two 64-channel blocks of 128 pixels
+  static constexpr int kX = (BLOCK_N / 64) * kASlotBytes;         // BLOCK_N/64 blocks of (16+2) rows
+  static constexpr int kStageSz = kDY + kX;
+  static constexpr int kBar = STAGES * kStageSz;
+  static constexpr int kNumBar = 2 * STAGES + 1;
+  static constexpr int kTmemPtr = kBar + kNumBar * 8;
+  static constexpr int kTotal = kTmemPtr + 16;
+  static constexpr int kDyn = kTotal + 1024;
+  static constexpr int kTmemCols = 3 * BLOCK_N <= 128 ? 128 : (3 * BLOCK_N <= 256 ? 256 : 512);
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1) wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
+  using L = WgLayout<BLOCK_N, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kBar);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtr);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // work item: blockIdx = ((split * G + g) * n_blocks + nb) * m_blocks + mb
+  int id = blockIdx.x;
+  const int mb = id % p.m_blocks; id /= p.m_blocks;
+  const int nb = id % p.n_blocks; id /= p.n_blocks;
+  const int g = id % p.G;
+  const int split = id / p.G;
+  const int total_tiles = p.tiles_w * p.tiles_h * p.batch;
+  const int t_begin = (int)(((long long)total_tiles * split) / p.splits);
+  const int t_end = (int)(((long long)total_tiles * (split + 1)) / p.splits);
+  const int per_img = p.tiles_w * p.tiles_h;
+  const int m_valid = (p.Mtot - mb * 128) < 128 ? (p.Mtot - mb * 128) : 128;   // 64 or 128
+  const int dy_blocks = m_valid > 64 ? 2 : 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&p.tmapDY[p.dy_map[g]]);
+    tma_prefetch_desc(&p.tmapX[p.x_map[g]]);
+  }
+  if (warp == 2) tmem_alloc<L::kTmemCols>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    int s = 0, ph = 0;
+    const uint32_t x_rows_bytes = (16 + p.R - 1) * kAtomBytes;
+    const uint32_t bytes = dy_blocks * 16 * kAtomBytes + (BLOCK_N / 64) * x_rows_bytes;
+    for (int t = t_begin; t < t_end; ++t) {
+      const int b = t / per_img, rem = t - b * per_img;
+      const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
+      const int w0 = tw * 8, h0 = th * 16;
+      mbar_wait(&empty[s], ph ^ 1);
+      if (lane == 0) {
+        uint8_t* st = smem + s * L::kStageSz;
+        mbar_arrive_expect_tx(&full[s], bytes);
+        for (int j = 0; j < dy_blocks; ++j)
+          tma_load_4d(st + j * 16 * kAtomBytes, &p.tmapDY[p.dy_map[g]], &full[s], p.dy_chan0 + mb * 128 + j * 64, w0,
+                      h0, b);
+        for (int j = 0; j < BLOCK_N / 64; ++j)
+          tma_load_4d(st + L::kDY + j * kASlotBytes, &p.tmapX[p.x_map[g]], &full[s],
+                      p.x_chan0 + nb * BLOCK_N + j * 64, w0 + p.x_dw[g], h0 + p.x_dh[g], b);
+      }
+      __syncwarp();
+      if (++s == STAGES) { s = 0; ph ^= 1; }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc(128, BLOCK_N, 1, 1);
+    int s = 0, ph = 0;
+    uint32_t accumulate = 0;
+    // With a single 64-channel block of dY (Cout == 64) both halves of the M=128 operand alias the
+    // same block (LBO = 0); rows 64..127 of the accumulator are duplicates and never stored.
+    const uint32_t a_lbo = dy_blocks == 2 ? 16 * kAtomBytes : 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t dy_addr = smem_u32(smem + s * L::kStageSz);
+        const uint32_t x_addr = dy_addr + L::kDY;
+        for (int r = 0; r < p.R; ++r) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            umma_bf16(tmem_base + r * BLOCK_N, make_smem_desc(dy_addr + k * 2 * kAtomBytes, a_lbo, kAtomBytes),
+                      make_smem_desc(x_addr + (r + 2 * k) * kAtomBytes, kASlotBytes, kAtomBytes), idesc,
+                      accumulate | (uint32_t)(k > 0));
+          }
+        }
+        accumulate = 1;
+        umma_commit(&empty[s]);
+      }
+      __syncwarp();
+      if (++s == STAGES) { s = 0; ph ^= 1; }
+    }
+    if (lane == 0) umma_commit(tmem_full);
+    __syncwarp();
+  } else {
+    const int sub = warp & 3;
+    const int row = sub * 32 + lane;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    if (t_end > t_begin) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16);
+      for (int r = 0; r < p.R; ++r) {
+        float* dst_row = p.dw + ((size_t)((g * p.R + r) * p.Mtot + mb * 128 + row)) * p.Ntot + nb * BLOCK_N;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + r * BLOCK_N + c0, v);
+          tmem_ld_wait();
+          if (row < m_valid) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst_row + c0 + 4 * j),
+                           "f"(__uint_as_float(v[4 * j])), "f"(__uint_as_float(v[4 * j + 1])),
+                           "f"(__uint_as_float(v[4 * j + 2])), "f"(__uint_as_float(v[4 * j + 3]))
+                           : "memory");
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<L::kTmemCols>(tmem_base);
+  }
+}
+
+template <int BLOCK_N, int STAGES>
+static cudaError_t launch_wg(const WgradParams& p, cudaStream_t stream) {
+  using L = WgLayout<BLOCK_N, STAGES>;
+  static_assert(L::kDyn <= 232448, "shared memory budget exceeded");
+  auto kern = wgrad_gemm_kernel<BLOCK_N, STAGES>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDyn);
+  });
+  if (attr_err != cudaSuccess) return attr_err;
+  const int grid = p.m_blocks * p.n_blocks * p.G * p.splits;
+  if (grid <= 0) return cudaSuccess;
+  kern<<<grid, kThreads, L::kDyn, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_wgrad_gemm(const WgradParams& p, int block_n, cudaStream_t stream) {
+  switch (block_n) {
+    case 64: return launch_wg<64, 4>(p, stream);
+    case 128: return launch_wg<128, 3>(p, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// =============================================================================================
+//                                   tensor-map encoding
+// =============================================================================================
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+int make_tmap_4d(CUtensorMap* out, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                 const uint32_t box[4]) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -1;
+  cuuint64_t d[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t s[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+  cuuint32_t b[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t e[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), d, s, b, e,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
+}
+
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
+                 uint32_t box_inner, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -1;
+  cuuint64_t d[2] = {inner, rows};
+  cuuint64_t s[1] = {row_stride_bytes};
+  cuuint32_t b[2] = {box_inner, box_rows};
+  cuuint32_t e[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), d, s, b, e,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
+}
+
+}  // namespace cs

@@ -1,0 +1,71 @@
+// Parameter blocks and host-side launch declarations for the two tcgen05 implicit-GEMM kernels.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cs {
+
+// ---------------------------------------------------------------------------------------------
+// "Pixel-major" implicit GEMM:  D[128 pixels, BLOCK_N] += A[pixels, K] * B[K, N]
+//   A : NHWC bf16 activations, read as 8(w) x 16(h) pixel patches through 4-D TMA maps
+//       (channels, W, H, batch) — out-of-image coordinates are zero-filled by TMA, which is the
+//       convolution padding.  One A load per (64-channel chunk, group g) brings a patch that is
+//       (R-1) rows taller than the tile; the R vertical taps of the group are 1024-byte-aligned
+//       sub-views of it (one 8-pixel image row == one 128B-swizzle atom).
+//   B : packed weights [G*R taps][Ntot][K] bf16, K-major, one 2-D TMA map.
+//   Used for: conv3x3 fprop and dgrad (G=3 horizontal shifts, R=3), ConvTranspose2d(2,2) fprop
+//   (G=1,R=1, N = 4*Cout scattered through 4 strided output maps), its dgrad (G=4 strided input
+//   maps, R=1) and the im2col'd first conv (G=1,R=1).
+struct PixGemmParams {
+  CUtensorMap tmapA[4];
+  CUtensorMap tmapB;
+  CUtensorMap tmapO[4];
+  int G, R;
+  int a_map[4], a_dw[4], a_dh[4];
+  int a_chan0;          // first input channel (coordinate offset inside the A maps)
+  int kchunks;          // K / 64 per tap
+  int Ntot;             // rows per tap in B
+  int n_blocks;         // Ntot / BLOCK_N
+  int tiles_w, tiles_h, batch;
+  int o_blocks_per_map; // n-blocks written through one output map
+  int o_chan0;          // first output channel (coordinate offset inside the O maps)
+  const float* scale;   // per output channel (index inside its map), may be null
+  const float* shift;   // per output channel, may be null
+  int relu;
+  double* stat_sum;     // per output channel sum / sum of squares of the stored bf16 values
+  double* stat_sq;      //   (both null when no statistics are wanted)
+};
+
+cudaError_t launch_pix_gemm(const PixGemmParams& p, int block_n, int num_sms, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------
+// "Channel-major" implicit GEMM (weight gradients):
+//   dW[tap][co, ci] += sum over pixels  dY[pixel, co] * X[pixel + shift(tap), ci]
+//   Both operands are NHWC tiles, i.e. MN-major for the MMA (pixels are the K dimension).
+//   One CTA owns (128 output channels) x (BLOCK_N input channels) x (R taps of one group g) and a
+//   contiguous range of pixel tiles (split-K); partial sums are reduced with red.global.add.f32
+//   into a zero-initialised fp32 buffer laid out [G*R][Mtot][Ntot].
+struct WgradParams {
+  CUtensorMap tmapDY[4];   // indexed by dy_map[g]
+  CUtensorMap tmapX[4];    // indexed by x_map[g]
+  int G, R;
+  int dy_map[4], x_map[4], x_dw[4], x_dh[4];
+  int dy_chan0, x_chan0;
+  int Mtot, Ntot;          // Cout-like, Cin-like extents of dW
+  int m_blocks, n_blocks;  // ceil(Mtot/128), Ntot/BLOCK_N
+  int tiles_w, tiles_h, batch;
+  int splits;              // split-K factor over pixel tiles
+  float* dw;               // [G*R][Mtot][Ntot] fp32, accumulated atomically
+};
+
+cudaError_t launch_wgrad_gemm(const WgradParams& p, int block_n, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------------
+// Host helpers (tensor-map encoding through the driver entry point; no libcuda link dependency).
+int make_tmap_4d(CUtensorMap* out, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                 const uint32_t box[4]);
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
+                 uint32_t box_inner, uint32_t box_rows);
+
+}  // namespace cs

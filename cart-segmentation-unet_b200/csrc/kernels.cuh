@@ -1,0 +1,105 @@
+// Launchers for the bandwidth-bound (SIMT) kernels of the U-Net hot path.  All activations are NHWC
+// bf16 ("pixel rows" of C channels, optionally embedded in a wider row: pitch + channel offset);
+// logits / targets / SDFs are fp32 [B, H*W] exactly as the reference API supplies them.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cs {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- weights -------------------------------------------------------------------------------
+// in[(a*Nb + b)*T + t] (fp32)  ->  out_ab[map_ab[t]][a][b]  and  out_ba[map_ba[t]][b][a]  (bf16)
+struct TapMap { int v[9]; };
+cudaError_t launch_pack_pairs(const float* in, int Na, int Nb, int T, bf16* out_ab, TapMap map_ab, bf16* out_ba,
+                              TapMap map_ba, cudaStream_t s);
+// conv1.0: W[64][Cin<=7][3][3] -> [64][64] with k = (r*3+s)*Cin + c, zero padded
+cudaError_t launch_pack_first(const float* in, int Cout, int Cin, bf16* out, cudaStream_t s);
+// dWp[t][a][b] (fp32) -> grad[(a*Nb+b)*T + map[t]]
+cudaError_t launch_unpack_pairs(const float* dwp, int Na, int Nb, int T, TapMap map, float* grad, cudaStream_t s);
+cudaError_t launch_unpack_first(const float* dwp, int Cout, int Cin, float* grad, cudaStream_t s);
+
+// ---- input ---------------------------------------------------------------------------------
+// x fp32 NCHW [B,Cin,H,W] -> col bf16 [B*H*W][64], col[p][(r*3+s)*Cin + c] = x[b,c,h+r-1,w+s-1]
+cudaError_t launch_im2col_first(const float* x, int B, int Cin, int H, int W, bf16* col, cudaStream_t s);
+
+// ---- batch norm ----------------------------------------------------------------------------
+struct BnFinalizeArgs {
+  const double* sum; const double* sq; double count;
+  const float* gamma; const float* beta; const float* conv_bias;
+  float* running_mean; float* running_var; long long* num_batches_tracked;
+  float momentum, eps;
+  float* scale; float* shift; float* mean; float* invstd;
+  int C;
+};
+cudaError_t launch_bn_finalize_train(const BnFinalizeArgs& a, cudaStream_t s);
+cudaError_t launch_bn_fold_eval(const float* gamma, const float* beta, const float* conv_bias, const float* rm,
+                                const float* rv, float eps, float* scale, float* shift, int C, cudaStream_t s);
+// out[p][out_c0 + c] = relu(y[p][c]*scale[c] + shift[c]); optional 2x2 max-pooled copy (pitch C)
+cudaError_t launch_bn_relu(const bf16* y, int B, int H, int W, int C, const float* scale, const float* shift,
+                           bf16* out, int out_pitch, int out_c0, bf16* pooled, cudaStream_t s);
+// relu/bn already applied (eval path): plain 2x2 max-pool of in[p][c0 + c] (pitch in_pitch) -> pooled (pitch C)
+cudaError_t launch_maxpool(const bf16* in, int in_pitch, int in_c0, int B, int H, int W, int C, bf16* pooled,
+                           cudaStream_t s);
+
+struct BnBwdArgs {
+  const bf16* g; int g_pitch, g_c0;        // gradient w.r.t. the post-ReLU activation
+  const bf16* g_pool;                      // optional: gradient w.r.t. the 2x2-pooled activation (pitch C)
+  const bf16* y;                           // raw conv output (pitch C)
+  const float* scale; const float* shift; const float* mean; const float* invstd;
+  double* s1; double* s2;                  // per-channel sum(g*mask), sum(g*mask*xhat)
+  bf16* dy;                                // gradient w.r.t. the raw conv output (pitch C)
+  float* grad_gamma; float* grad_beta; float* grad_conv_bias;
+  int B, H, W, C;
+};
+cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t s);
+cudaError_t launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t s);   // also writes grad_gamma/beta/bias
+
+// ---- 1x1 head ------------------------------------------------------------------------------
+cudaError_t launch_head_fwd(const bf16* act, long long P, int C, const float* w, const float* b, float* logits,
+                            cudaStream_t s);
+// g_act[p][c] = dlogits[p]*w[c];  grad_w[c] += sum_p dlogits[p]*act[p][c];  grad_b += sum_p dlogits[p]
+cudaError_t launch_head_bwd(const bf16* act, const float* dlogits, long long P, int C, const float* w, bf16* g_act,
+                            float* grad_w, float* grad_b, cudaStream_t s);
+
+// ---- conv-transpose bias gradient -------------------------------------------------------------
+// grad_b[c] = sum_p g[p][c0 + c]
+cudaError_t launch_channel_sum(const bf16* g, int pitch, int c0, long long P, int C, float* out, cudaStream_t s);
+
+// ---- exact EDT / signed distance map --------------------------------------------------------
+// fg(pixel) = ge ? (src >= thr) : (src > thr);  sdf = (+dist to nearest fg | -dist to nearest bg) / norm,
+// all-fg / all-bg images give 0.  scratch: B*H*W*4 bytes + B*8 bytes.
+size_t sdf_scratch_bytes(int B, int H, int W);
+cudaError_t launch_sdf(const float* src, float thr, int ge, int B, int H, int W, float norm, float* sdf,
+                       void* scratch, cudaStream_t s);
+
+// ---- fused segmentation losses ---------------------------------------------------------------
+struct LossArgs {
+  const float* logits; const float* targets;     // [rows][n]
+  const float* sdf_gt; const float* sdf_pred;    // optional, [rows][n]
+  int rows; long long n;                         // rows = samples (Dice is per row)
+  float w_elem;       // weight of the element-wise term  alpha*(1-p_t)^gamma * BCE
+  float alpha, gamma; // alpha=1,gamma=0 -> plain BCE
+  int elem_sum;       // 1: sum over elements instead of mean
+  float w_dice, smooth;
+  float w_bgt, w_bpred; int use_abs;
+  int per_row;        // 1: loss_out is [rows] (per-sample loss, finetune_for_224.py:208-221)
+  double* stats;      // [rows][8] scratch + 1 counter (zeroed by the launcher)
+  float* loss_out;
+  const float* grad_out; // device scalar (or [rows] if per_row)
+  float* dlogits;
+};
+size_t loss_scratch_bytes(int rows);
+cudaError_t launch_loss_forward(const LossArgs& a, cudaStream_t s);
+cudaError_t launch_loss_backward(const LossArgs& a, cudaStream_t s);
+
+// ---- threshold / metrics ---------------------------------------------------------------------
+// For each row and threshold k (given as logit-space bounds xs[k], pred = x >= xs[k]):
+//   counts[row][k] = {sum pred, sum pred*t};  soft[row] = {sum p, sum t, sum p*t}
+cudaError_t launch_threshold_stats(const float* logits, const float* targets, int rows, long long n, const float* xs,
+                                   int K, double* counts, double* soft, cudaStream_t s);
+cudaError_t launch_threshold_mask(const float* logits, long long n, float xstar, uint8_t* mask, cudaStream_t s);
+
+}  // namespace cs

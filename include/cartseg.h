@@ -1,0 +1,153 @@
+/* cartseg.h — C ABI of the B200-native U-Net hot path (libcartseg.so).
+ *
+ * The reference (endressa/cart-segmentation-unet) has no FFI for this path: the boundary is the
+ * Python object protocol `model(x)` / `criterion(logits, targets)` (train_bce_dice.py:308-309,
+ * 331-334).  Its only native boundary, pybind `lsr_cpp.lsr_forward/lsr_backward`
+ * (src/training/abl_training/losses/lsr_cpp/csrc/lsr_kernel.cu:296-322), sets the conventions kept
+ * here: CUDA-only (hard error otherwise, :300-302), work is enqueued on the caller's stream (:220),
+ * no host synchronisation.  Each entry point below names the reference code it replaces; the
+ * Python host (cartseg/ops.py) binds them with ctypes and exposes them as torch.library ops.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless stated otherwise;
+ *   - the caller owns every buffer (including workspaces, sized by the *_bytes queries);
+ *   - nothing here allocates device memory, frees it, or synchronises; all work goes to `stream`;
+ *   - return value 0 = success, negative = failure; cs_last_error() gives a thread-local message;
+ *   - image tensors are fp32 NCHW exactly as the reference's DataLoader yields them; logits,
+ *     targets, SDFs and dlogits are fp32 [B,1,H,W]; H and W must be multiples of 16.
+ */
+#ifndef CARTSEG_H_
+#define CARTSEG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* cs_stream_t; /* cudaStream_t */
+
+const char* cs_last_error(void);
+int cs_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * U-Net  (replaces DoubleConv / UNet, src/create_testset.py:40-83; logits = final_conv output,
+ * the trailing sigmoid of :83 is NOT applied — every reference loss takes logits).
+ * Parameter order = the 82 trainable tensors in state_dict order (conv1.conv.0.weight, ...
+ * final_conv.bias), fp32, reference shapes (OIHW conv, IOHW conv-transpose).
+ * BN buffers: 18 layers in state_dict order; running_mean / running_var fp32 [C],
+ * num_batches_tracked int64 scalar.
+ * ---------------------------------------------------------------------------------------------- */
+#define CS_UNET_NUM_PARAMS 82
+#define CS_UNET_NUM_BN 18
+#define CS_UNET_NUM_BWD_STAGES 23 /* head, then 18 convs and 4 up-convs in reverse execution order */
+
+typedef struct cs_unet_plan cs_unet_plan;
+
+typedef struct cs_unet_tensors {
+  const float* param[CS_UNET_NUM_PARAMS];
+  float* grad[CS_UNET_NUM_PARAMS];          /* written by cs_unet_backward; may be NULL for forward */
+  float* running_mean[CS_UNET_NUM_BN];
+  float* running_var[CS_UNET_NUM_BN];
+  long long* num_batches_tracked[CS_UNET_NUM_BN];
+} cs_unet_tensors;
+
+/* Host-side: lay out activations / packed weights / gradients for one (batch, H, W). */
+int cs_unet_plan_create(cs_unet_plan** plan, int batch, int in_channels, int height, int width);
+void cs_unet_plan_destroy(cs_unet_plan* plan);
+size_t cs_unet_plan_workspace_bytes(const cs_unet_plan* plan);
+/* Attach a caller-owned device workspace (>= workspace_bytes, 1024-byte aligned) and encode the
+ * TMA descriptors that point into it. */
+int cs_unet_plan_bind(cs_unet_plan* plan, void* workspace, size_t bytes);
+/* fp32 reference-layout weights -> bf16 tap-major packs (fprop + dgrad).  Call after every
+ * optimizer step (the Python module tracks parameter versions). */
+int cs_unet_pack_weights(cs_unet_plan* plan, const cs_unet_tensors* t, cs_stream_t stream);
+/* x fp32 [B,Cin,H,W] -> logits fp32 [B,1,H,W].  training != 0: batch statistics, running buffers
+ * updated (momentum 0.1, eps 1e-5), activations kept for backward.  training == 0: running
+ * statistics folded into the convolution epilogues. */
+int cs_unet_forward(cs_unet_plan* plan, const cs_unet_tensors* t, const float* x, int training, float* logits,
+                    cs_stream_t stream);
+/* Backward of the last training forward.  Stages [stage_begin, stage_end) in reverse execution
+ * order; gradients of the parameters owned by those stages are final when the call's work
+ * completes, so a data-parallel caller can all-reduce them while later stages run.
+ * need_input_grads_from: index of the first encoder conv (0..9) whose parameters need gradients —
+ * 0 trains everything, 10 freezes the whole encoder (src/train_with_focalDice.py:384-391). */
+int cs_unet_backward(cs_unet_plan* plan, const cs_unet_tensors* t, const float* dlogits, int stage_begin,
+                     int stage_end, int frozen_encoder_convs, cs_stream_t stream);
+/* Which parameter indices (into param[]/grad[]) a backward stage finalises; returns the count. */
+int cs_unet_stage_params(int stage, int* out_indices, int capacity);
+
+/* ------------------------------------------------------------------------------------------------
+ * Signed distance maps (replaces signed_distance_map_np / batch_sdf_from_masks,
+ * src/train_with_boundary_loss.py:191-217: exact EDT, sdf = dist_out - dist_in, zeros for
+ * all-fg / all-bg, fp32 divide by `norm`).  fg = ge ? src >= thr : src > thr.
+ * ---------------------------------------------------------------------------------------------- */
+size_t cs_sdf_scratch_bytes(int batch, int height, int width);
+int cs_sdf(const float* src, float thr, int ge, int batch, int height, int width, float norm, float* sdf,
+           void* scratch, cs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused losses.  One descriptor covers
+ *   BCEDiceLoss            train_bce_dice.py:186-199          (alpha=1, gamma=0)
+ *   FocalLoss/FocalDiceLoss src/train_with_focalDice.py:195-235
+ *   SymmetricBoundaryLoss / CompositeSegLoss  src/train_with_boundary_loss.py:242-282
+ *   BCEDiceLossPerSample   src/finetune_for_224.py:208-221    (per_row = 1)
+ * loss = w_elem * mean|sum(alpha (1-p_t)^gamma BCE) + w_dice * (1 - mean_rows dice)
+ *        + w_bgt * mean|p*sdf_gt| + w_bpred * mean|(1-p)*(-sdf_pred)|
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cs_loss_desc {
+  int rows;            /* Dice rows (= B*C for dims (2,3), B for dims (1,2,3)) */
+  long long n;         /* elements per row, multiple of 4 */
+  float w_elem, alpha, gamma;
+  int elem_sum;
+  float w_dice, smooth;
+  float w_bgt, w_bpred;
+  int use_abs;
+  int per_row;
+} cs_loss_desc;
+
+size_t cs_loss_scratch_bytes(int rows);
+/* loss_out: 1 float (or rows floats if per_row).  scratch is re-read by cs_loss_backward. */
+int cs_loss_forward(const cs_loss_desc* d, const float* logits, const float* targets, const float* sdf_gt,
+                    const float* sdf_pred, void* scratch, float* loss_out, cs_stream_t stream);
+/* grad_out: device scalar (or [rows] if per_row), may be NULL (= 1). */
+int cs_loss_backward(const cs_loss_desc* d, const float* logits, const float* targets, const float* sdf_gt,
+                     const float* sdf_pred, const void* scratch, const float* grad_out, float* dlogits,
+                     cs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Thresholding / metrics (replaces dice_metric, iou_metric, find_best_threshold
+ * train_bce_dice.py:201-232; precision_recall_f1 src/train_with_focalDice.py:266-284; the
+ * pseudo-label threshold create_pseudo_labels_gpu.py:294).  Thresholds are given as logit-space
+ * bounds xs[k]: pred = (x >= xs[k]); the host derives xs[k] so that the result is bit-identical to
+ * sigmoid(x) > t (or >= t).
+ *   counts[row][k] = {sum pred, sum pred*target}   soft[row] = {sum p, sum t, sum p*t}
+ * ---------------------------------------------------------------------------------------------- */
+int cs_threshold_stats(const float* logits, const float* targets, int rows, long long n, const float* xs, int K,
+                       double* counts, double* soft, cs_stream_t stream);
+int cs_threshold_mask(const float* logits, long long n, float xstar, uint8_t* mask, cs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Single-layer entry points (unit tests / micro-benchmarks of the tcgen05 kernels).  Activations
+ * are NHWC bf16; weights fp32 in the reference layout; `scratch` must hold the packed copies
+ * (cs_layer_scratch_bytes).  dw is fp32 in the reference layout.
+ * ---------------------------------------------------------------------------------------------- */
+size_t cs_layer_scratch_bytes(int cin, int cout);
+int cs_conv3x3_fprop(const void* x_nhwc, int batch, int height, int width, int cin, const float* w_oihw, int cout,
+                     void* y_nhwc, double* stat_sum, double* stat_sq, void* scratch, cs_stream_t stream);
+int cs_conv3x3_dgrad(const void* dy_nhwc, int batch, int height, int width, int cin, const float* w_oihw, int cout,
+                     void* dx_nhwc, void* scratch, cs_stream_t stream);
+int cs_conv3x3_wgrad(const void* x_nhwc, const void* dy_nhwc, int batch, int height, int width, int cin, int cout,
+                     float* dw_oihw, void* scratch, cs_stream_t stream);
+int cs_convT2x2_fprop(const void* x_nhwc, int batch, int height, int width, int cin, const float* w_iohw,
+                      const float* bias, int cout, void* y_nhwc, int y_pitch, void* scratch, cs_stream_t stream);
+int cs_convT2x2_dgrad(const void* dy_nhwc, int dy_pitch, int batch, int height, int width, int cin,
+                      const float* w_iohw, int cout, void* dx_nhwc, void* scratch, cs_stream_t stream);
+int cs_convT2x2_wgrad(const void* x_nhwc, const void* dy_nhwc, int dy_pitch, int batch, int height, int width,
+                      int cin, int cout, float* dw_iohw, void* scratch, cs_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CARTSEG_H_ */
