@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""Headline benchmark: U-Net training throughput (images/s) on B200, reference CPU step beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload k2|k3|k4]
+
+Workloads (BASELINE.json configs / SURVEY.md §8):
+  k2 (default)  U-Net, B=64 per GPU, 3x224x224, bf16 tensor-core compute, focal-Dice loss
+  k3            B=32 per GPU, 3x512x512, focal-Dice, three LR groups (train_with_focalDice_unfrozen.py:388-392)
+  k4            B=64 per GPU, 3x224x224, Composite(BCE-Dice + symmetric boundary) with on-GPU exact EDT
+A "step" = forward + loss + backward (dgrad + wgrad of every layer) + AdamW update + bf16 weight re-pack,
+exactly the loop body of train_bce_dice.py:328-338.  N>1: one process per GPU (torchrun), batch sharded
+(weak scaling), gradients all-reduced over NCCL overlapped with backward.
+
+One JSON line on stdout (rank 0).  `value` = images/s with inputs resident in HBM; `e2e` = the same step
+through the public nn.Module API with pinned-host inputs copied H2D and the loss read back every step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "cart-segmentation-unet_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+# Algorithmic FLOPs (2*MACs of conv / conv-transpose only), SURVEY.md §8d, measured on the reference class
+GFLOP_TRAIN = {224: 221.095, 512: 1155.11}      # fprop + dgrad + wgrad per image
+GFLOP_FWD = {224: 73.756, 512: 385.339}
+
+WORKLOADS = {
+    "k2": dict(batch=64, size=224, loss="focal_dice", desc="U-Net B=64/GPU 3x224x224 bf16 focal-Dice fwd+bwd+AdamW"),
+    "k3": dict(batch=32, size=512, loss="focal_dice", desc="U-Net B=32/GPU 3x512x512 bf16 focal-Dice 3 LR groups"),
+    "k4": dict(batch=64, size=224, loss="composite", desc="U-Net B=64/GPU 3x224x224 bf16 BCE-Dice+boundary(EDT)"),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [v.strip() for v in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step_rate(loss_name: str, size: int, steps: int, warmup: int, batch: int = 4):
+    """The reference's CPU path (the oracle port of its UNet + loss classes, torch CPU fp32, all host threads)
+    on a bounded sample of the workload: `batch` images per step."""
+    import torch
+    from oracle import unet_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    x, tgt = O.synth_batch(batch, size, size, seed=0)
+    sd = O.synth_state_dict(seed=0)
+    keys = O.param_keys(sd)
+    for k in keys:
+        sd[k].requires_grad_(True)
+    fn = {"focal_dice": lambda z, t: O.focal_dice_loss(z, t, 0.5, 2.0, 1.0, 0.7),
+          "composite": lambda z, t: O.composite_seg_loss(z, t, 0.5, 0.3),
+          "bce_dice": lambda z, t: O.bce_dice_loss(z, t)}[loss_name]
+    times = []
+    for i in range(warmup + steps):
+        for k in keys:
+            sd[k].grad = None
+        t0 = time.perf_counter()
+        loss = fn(O.unet_logits(x, sd, training=True), tgt)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return dict(value=batch * len(times) / total, ms_per_step=1e3 * total / len(times), cores=torch.get_num_threads(),
+                sample=f"{len(times)} fwd+bwd steps of {batch}x3x{size}x{size} fp32, {loss_name}, torch CPU "
+                       f"({warmup} warm-up)")
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 6))
+    r = cpu_reference_step_rate(wl["loss"], wl["size"], steps, max(1, min(args.warmup, 2)))
+    line = {
+        "impl": "reference", "metric": "train_images_per_sec", "value": r["value"], "unit": "img/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "note": "reference CPU path (oracle port of the reference classes) on a "
+                   "bounded sample: 4 images per step on the host cores"},
+        "cpu_baseline": {"value": r["value"], "unit": "img/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+    import cartseg
+    from oracle import unet_oracle as O       # synthetic-input generator + the cpu_baseline leg only
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: cartseg has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, S = wl["batch"], wl["size"]
+    torch.manual_seed(0)
+    model = cartseg.UNet().to(dev).train()
+    if world > 1:
+        cartseg.parallel.init_data_parallel(model)
+    if wl["loss"] == "focal_dice":
+        crit = cartseg.FocalDiceLoss(alpha=0.5, gamma=2.0, smooth=1.0, w_focal=0.7)
+    elif wl["loss"] == "composite":
+        crit = cartseg.CompositeSegLoss(bce_weight=0.5, boundary_weight=0.3)
+    else:
+        crit = cartseg.BCEDiceLoss()
+    if args.workload == "k3":                    # src/train_with_focalDice_unfrozen.py:388-392
+        opt = torch.optim.AdamW([{"params": list(model.encoder.parameters()), "lr": 1e-4},
+                                 {"params": list(model.decoder.parameters()), "lr": 1e-3},
+                                 {"params": list(model.segmentation_head.parameters()), "lr": 3e-3}],
+                                weight_decay=1e-4, fused=True)
+    else:
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True)
+
+    x_h, t_h = O.synth_batch(B, S, S, seed=rank)
+    x_h, t_h = x_h.pin_memory(), t_h.pin_memory()
+    x_d, t_d = x_h.to(dev), t_h.to(dev)
+
+    def step(x, t):
+        opt.zero_grad(set_to_none=True)
+        logits = model(x)
+        loss = crit(logits, t)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(x_d, t_d)
+    barrier()
+
+    # ---- device-resident timing (value) -------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = cartseg.lib().cs_kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(x_d, t_d)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = cartseg.lib().cs_kernel_launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    last_loss = float(loss.item())
+
+    # ---- end to end: pinned host inputs -> H2D -> step -> loss read back, every step ----------
+    for _ in range(2):
+        x_d.copy_(x_h, non_blocking=True); t_d.copy_(t_h, non_blocking=True); step(x_d, t_d).item()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        x_d.copy_(x_h, non_blocking=True)
+        t_d.copy_(t_h, non_blocking=True)
+        loss_val = step(x_d, t_d).item()
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - t0)
+
+    if world > 1:
+        tt = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = tt.tolist()
+    value = world * B * args.steps / (ms / 1e3)
+    e2e = world * B * args.steps / (e2e_ms / 1e3)
+
+    if rank == 0:
+        pk = peaks()
+        per_gpu_tflops = (value / world) * GFLOP_TRAIN[S] / 1e3
+        line = {
+            "metric": "train_images_per_sec", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": wl["desc"], "per_gpu_batch": B, "global_batch": B * world, "image": f"3x{S}x{S}",
+                       "loss": wl["loss"], "optimizer": "AdamW(fused)", "parallelism": f"dp{world}",
+                       "l2": "per-step working set (>10 GB of activations) exceeds the 126 MB L2; no flush needed",
+                       "last_loss": last_loss},
+            "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": int(x_h.numel() * 4 + t_h.numel() * 4),
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": per_gpu_tflops, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                         "frac": per_gpu_tflops / pk["tf_sust"], "traffic": None,
+                         "kernel": "all conv / conv-transpose implicit GEMMs of one step, over the WHOLE step time "
+                                   f"({GFLOP_TRAIN[S]} algorithmic GFLOP per image)",
+                         "peak_source": pk["source"] + ", sustained bf16"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_reference_step_rate(wl["loss"], S, steps=3, warmup=1)
+            line["cpu_baseline"] = {"value": r["value"], "unit": "img/s", "cores": r["cores"], "kind": "port",
+                                    "sample": r["sample"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="k2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

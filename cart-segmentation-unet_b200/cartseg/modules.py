@@ -1,0 +1,334 @@
+"""Drop-in ``nn.Module`` shells with the reference's names, constructor arguments and state-dict keys.
+
+  UNet, DoubleConv                      src/create_testset.py:40-83
+  BCEDiceLoss                           train_bce_dice.py:186-199   (dims=(1,2,3): src/finetune_pseudo.py:178-190)
+  BCEDiceLossPerSample                  src/finetune_for_224.py:208-221
+  FocalLoss, FocalDiceLoss              src/train_with_focalDice.py:195-235
+  batch_sdf_from_masks, SymmetricBoundaryLoss, CompositeSegLoss
+                                        src/train_with_boundary_loss.py:204-282
+
+The modules own ordinary fp32 ``nn.Parameter``s (so optimizers, param groups, ``state_dict`` /
+``load_state_dict`` and ``requires_grad`` toggling work unchanged); all arithmetic happens in the
+``cartseg::`` ops.  Inputs must be CUDA tensors: there is no CPU path.
+"""
+from __future__ import annotations
+
+from typing import Iterator, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from . import ops
+from ._lib import CartsegError
+
+
+# =============================================================================================
+# Model
+# =============================================================================================
+class DoubleConv(nn.Module):
+    """Parameter container with the reference layout (conv.0 / conv.1 / conv.3 / conv.4).
+
+    Only the whole-network op exists on the GPU, so calling a DoubleConv on its own raises."""
+
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        self.conv = nn.Sequential(
+            nn.Conv2d(in_channels, out_channels, 3, padding=1),
+            nn.BatchNorm2d(out_channels),
+            nn.ReLU(inplace=True),
+            nn.Conv2d(out_channels, out_channels, 3, padding=1),
+            nn.BatchNorm2d(out_channels),
+            nn.ReLU(inplace=True),
+        )
+
+    def forward(self, x):  # pragma: no cover - deliberate hard error
+        raise CartsegError("DoubleConv is executed as part of cartseg.UNet (one fused op); it has no standalone path")
+
+
+class _ParamGroup:
+    """A view over some sub-modules of the UNet (``model.encoder`` etc.): lets training scripts build
+    optimizer param groups and freeze / unfreeze them (src/train_with_focalDice.py:384-391,413-419)
+    without registering duplicate state-dict entries."""
+
+    def __init__(self, modules: Sequence[nn.Module]):
+        self._modules_list = list(modules)
+
+    def parameters(self) -> Iterator[nn.Parameter]:
+        for m in self._modules_list:
+            yield from m.parameters()
+
+    def named_parameters(self):
+        for i, m in enumerate(self._modules_list):
+            for n, p in m.named_parameters():
+                yield f"{i}.{n}", p
+
+    def modules(self):
+        for m in self._modules_list:
+            yield from m.modules()
+
+    def requires_grad_(self, flag: bool = True):
+        for p in self.parameters():
+            p.requires_grad_(flag)
+        return self
+
+    def train(self, mode: bool = True):
+        for m in self._modules_list:
+            m.train(mode)
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+
+class UNet(nn.Module):
+    """U-Net of src/create_testset.py:53-83 running as one B200-native op.
+
+    ``forward`` returns **logits** (the output of ``final_conv``): every loss in the reference takes
+    logits (train_bce_dice.py:194-195).  ``final_sigmoid=True`` reproduces the reference class's own
+    ``torch.sigmoid`` tail (:83) for the interactive tool.
+    """
+
+    def __init__(self, in_channels: int = 3, out_channels: int = 1, final_sigmoid: bool = False):
+        super().__init__()
+        if out_channels != 1:
+            raise CartsegError("cartseg.UNet implements the binary-segmentation head only (out_channels=1)")
+        if not 1 <= in_channels <= 7:
+            raise CartsegError("in_channels must be in [1, 7]")
+        self.in_channels = in_channels
+        self.final_sigmoid = final_sigmoid
+        self.maxpool = nn.MaxPool2d(2, 2)
+        self.conv1 = DoubleConv(in_channels, 64)
+        self.conv2 = DoubleConv(64, 128)
+        self.conv3 = DoubleConv(128, 256)
+        self.conv4 = DoubleConv(256, 512)
+        self.conv5 = DoubleConv(512, 1024)
+        self.upconv4 = nn.ConvTranspose2d(1024, 512, 2, stride=2)
+        self.upconv3 = nn.ConvTranspose2d(512, 256, 2, stride=2)
+        self.upconv2 = nn.ConvTranspose2d(256, 128, 2, stride=2)
+        self.upconv1 = nn.ConvTranspose2d(128, 64, 2, stride=2)
+        self.dconv4 = DoubleConv(1024, 512)
+        self.dconv3 = DoubleConv(512, 256)
+        self.dconv2 = DoubleConv(256, 128)
+        self.dconv1 = DoubleConv(128, 64)
+        self.final_conv = nn.Conv2d(64, out_channels, 1)
+        self._dp_handle = 0
+
+    # ---- groups the training scripts address (smp.Unet naming) --------------------------------
+    @property
+    def encoder(self) -> _ParamGroup:
+        return _ParamGroup([self.conv1, self.conv2, self.conv3, self.conv4, self.conv5])
+
+    @property
+    def decoder(self) -> _ParamGroup:
+        return _ParamGroup([self.upconv4, self.upconv3, self.upconv2, self.upconv1,
+                            self.dconv4, self.dconv3, self.dconv2, self.dconv1])
+
+    @property
+    def segmentation_head(self) -> _ParamGroup:
+        return _ParamGroup([self.final_conv])
+
+    # ---- flat views in the order the C ABI expects (state-dict order) -------------------------
+    def _double_convs(self) -> List[DoubleConv]:
+        return [self.conv1, self.conv2, self.conv3, self.conv4, self.conv5,
+                self.dconv4, self.dconv3, self.dconv2, self.dconv1]
+
+    def _flat_params(self) -> List[nn.Parameter]:
+        out: List[nn.Parameter] = []
+
+        def dc(m: DoubleConv):
+            s = m.conv
+            out.extend([s[0].weight, s[0].bias, s[1].weight, s[1].bias, s[3].weight, s[3].bias, s[4].weight, s[4].bias])
+
+        for m in (self.conv1, self.conv2, self.conv3, self.conv4, self.conv5):
+            dc(m)
+        for u in (self.upconv4, self.upconv3, self.upconv2, self.upconv1):
+            out.extend([u.weight, u.bias])
+        for m in (self.dconv4, self.dconv3, self.dconv2, self.dconv1):
+            dc(m)
+        out.extend([self.final_conv.weight, self.final_conv.bias])
+        return out
+
+    def _flat_buffers(self) -> List[Tensor]:
+        out: List[Tensor] = []
+        for m in self._double_convs():
+            for bn in (m.conv[1], m.conv[4]):
+                out.extend([bn.running_mean, bn.running_var, bn.num_batches_tracked])
+        return out
+
+    def _frozen_encoder_convs(self, params: List[nn.Parameter]) -> int:
+        n = 0
+        for j in range(10):
+            base = (j // 2) * 8 + (j % 2) * 4
+            if any(params[i].requires_grad for i in range(base, base + 4)):
+                break
+            n += 1
+        return n
+
+    def forward(self, x: Tensor) -> Tensor:
+        if not x.is_cuda:
+            raise CartsegError("cartseg.UNet takes CUDA tensors only (no CPU fallback)")
+        if x.dim() != 4 or x.shape[1] != self.in_channels:
+            raise CartsegError(f"expected input [B,{self.in_channels},H,W], got {tuple(x.shape)}")
+        B, C, H, W = x.shape
+        if H % 16 or W % 16:
+            raise CartsegError("H and W must be multiples of 16 (four 2x2 poolings)")
+        x = x.detach().to(torch.float32).contiguous()
+        params = self._flat_params()
+        buffers = self._flat_buffers()
+        need_grad = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        plan = ops.get_plan(B, C, H, W, x.device, inference_only=not self.training)
+        if need_grad:
+            frozen = self._frozen_encoder_convs(params)
+            logits = ops.UNetFunction.apply(x, plan.id, True, frozen, self._dp_handle, len(params), *params, *buffers)
+        else:
+            logits = torch.ops.cartseg.unet_forward(x, [p.detach() for p in params], buffers, self.training, plan.id)
+        return torch.sigmoid(logits) if self.final_sigmoid else logits
+
+
+# =============================================================================================
+# Losses
+# =============================================================================================
+def _prep(logits: Tensor, targets: Tensor) -> Tuple[Tensor, Tensor]:
+    if not logits.is_cuda:
+        raise CartsegError("cartseg losses take CUDA tensors only (no CPU fallback)")
+    if logits.shape != targets.shape:
+        raise CartsegError(f"logits {tuple(logits.shape)} and targets {tuple(targets.shape)} differ in shape")
+    lg = logits if (logits.dtype == torch.float32 and logits.is_contiguous()) else logits.float().contiguous()
+    tg = targets.detach()
+    tg = tg if (tg.dtype == torch.float32 and tg.is_contiguous()) else tg.float().contiguous()
+    return lg, tg
+
+
+def _rows(logits: Tensor, dims: Tuple[int, ...]) -> int:
+    if logits.dim() != 4:
+        raise CartsegError("expected [B,C,H,W] logits")
+    if tuple(dims) == (2, 3):
+        return logits.shape[0] * logits.shape[1]
+    if tuple(dims) == (1, 2, 3):
+        return logits.shape[0]
+    raise CartsegError("Dice dims must be (2,3) or (1,2,3)")
+
+
+def _seg_loss(logits, targets, sdf_gt, sdf_pred, rows, *, w_elem=0.0, alpha=1.0, gamma=0.0, elem_sum=False,
+              w_dice=0.0, smooth=1.0, w_bgt=0.0, w_bpred=0.0, use_abs=True, per_row=False) -> Tensor:
+    loss, _ = torch.ops.cartseg.seg_loss(logits, targets, sdf_gt, sdf_pred, rows, float(w_elem), float(alpha),
+                                         float(gamma), bool(elem_sum), float(w_dice), float(smooth), float(w_bgt),
+                                         float(w_bpred), bool(use_abs), bool(per_row))
+    return loss
+
+
+class BCEDiceLoss(nn.Module):
+    """train_bce_dice.py:186-199.  ``dims=(1,2,3)`` gives the variant of src/finetune_pseudo.py:178-190."""
+
+    def __init__(self, bce_weight: float = 0.5, smooth: float = 1.0, dims: Tuple[int, ...] = (2, 3)):
+        super().__init__()
+        self.w, self.smooth, self.dims = bce_weight, smooth, tuple(dims)      # attribute names as in the reference
+
+    def forward(self, logits: Tensor, targets: Tensor) -> Tensor:
+        lg, tg = _prep(logits, targets)
+        return _seg_loss(lg, tg, None, None, _rows(lg, self.dims), w_elem=self.w, alpha=1.0, gamma=0.0,
+                         w_dice=1.0 - self.w, smooth=self.smooth)
+
+
+class BCEDiceLossPerSample(nn.Module):
+    """src/finetune_for_224.py:208-221 — returns one loss per sample ([B]); fixed .5/.5 mix (:221)."""
+
+    def __init__(self, bce_weight: float = 0.5, smooth: float = 1.0):
+        super().__init__()
+        self.w, self.smooth = bce_weight, smooth
+
+    def forward(self, logits: Tensor, targets: Tensor) -> Tensor:
+        lg, tg = _prep(logits, targets)
+        return _seg_loss(lg, tg, None, None, lg.shape[0], w_elem=0.5, alpha=1.0, gamma=0.0, w_dice=0.5,
+                         smooth=self.smooth, per_row=True)
+
+
+class FocalLoss(nn.Module):
+    """src/train_with_focalDice.py:195-219 (alpha applied uniformly to both classes, :210-212)."""
+
+    def __init__(self, alpha: float = 0.25, gamma: float = 2.0, reduction: str = "mean"):
+        super().__init__()
+        if reduction not in ("mean", "sum"):
+            raise CartsegError("cartseg.FocalLoss provides the fused reductions 'mean' and 'sum' "
+                               "(the reference only ever uses 'mean', src/train_with_focalDice.py:226)")
+        self.alpha, self.gamma, self.reduction = alpha, gamma, reduction
+
+    def forward(self, logits: Tensor, targets: Tensor) -> Tensor:
+        lg, tg = _prep(logits, targets)
+        return _seg_loss(lg, tg, None, None, lg.shape[0], w_elem=1.0, alpha=self.alpha, gamma=self.gamma,
+                         elem_sum=self.reduction == "sum")
+
+
+class FocalDiceLoss(nn.Module):
+    """src/train_with_focalDice.py:221-235."""
+
+    def __init__(self, alpha: float = 0.5, gamma: float = 2.0, smooth: float = 1.0, w_focal: float = 0.5):
+        super().__init__()
+        self.focal = FocalLoss(alpha=alpha, gamma=gamma, reduction="mean")
+        self.smooth, self.w_focal = smooth, w_focal
+
+    def forward(self, logits: Tensor, targets: Tensor) -> Tensor:
+        lg, tg = _prep(logits, targets)
+        return _seg_loss(lg, tg, None, None, _rows(lg, (2, 3)), w_elem=self.w_focal, alpha=self.focal.alpha,
+                         gamma=self.focal.gamma, w_dice=1.0 - self.w_focal, smooth=self.smooth)
+
+
+@torch.no_grad()
+def batch_sdf_from_masks(targets: Tensor) -> Tensor:
+    """src/train_with_boundary_loss.py:204-217 on the GPU: per image ``> 0.5`` -> exact-EDT signed
+    distance (outside positive, inside negative, zeros for empty / full masks) -> ``/ max(H, W)``."""
+    if targets.dim() != 4 or targets.shape[1] != 1:
+        raise CartsegError("expected [B,1,H,W] masks")
+    if not targets.is_cuda:
+        raise CartsegError("cartseg.batch_sdf_from_masks takes CUDA tensors only (no CPU fallback)")
+    t = targets.detach()
+    t = t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
+    H, W = t.shape[2], t.shape[3]
+    return torch.ops.cartseg.sdf(t, 0.5, False, float(max(H, W)))
+
+
+def _pred_sdf(logits: Tensor, t: float) -> Tensor:
+    # (sigmoid(x) > t).float() > 0.5  <=>  x >= x*(t)     (:250-251)
+    H, W = logits.shape[2], logits.shape[3]
+    return torch.ops.cartseg.sdf(logits.detach(), ops.logit_bound(t, ge=False), True, float(max(H, W)))
+
+
+class SymmetricBoundaryLoss(nn.Module):
+    """src/train_with_boundary_loss.py:219-264."""
+
+    def __init__(self, t: float = 0.5, w_gt: float = 1.0, w_pred: float = 0.5, use_abs: bool = True,
+                 scale: float = 1.0):
+        super().__init__()
+        self.t, self.w_gt, self.w_pred, self.use_abs, self.scale = t, w_gt, w_pred, use_abs, scale
+
+    def forward(self, logits: Tensor, targets: Tensor) -> Tensor:
+        lg, tg = _prep(logits, targets)
+        if lg.shape[1] != 1:
+            raise CartsegError("boundary loss expects single-channel logits")
+        sdf_gt = batch_sdf_from_masks(tg)
+        sdf_pred = _pred_sdf(lg, self.t)
+        return _seg_loss(lg, tg, sdf_gt, sdf_pred, lg.shape[0], w_bgt=self.scale * self.w_gt,
+                         w_bpred=self.scale * self.w_pred, use_abs=self.use_abs)
+
+
+class CompositeSegLoss(nn.Module):
+    """src/train_with_boundary_loss.py:266-282: (1-w)·BCEDice + w·SymmetricBoundary, one fused pass."""
+
+    def __init__(self, bce_weight: float = 0.5, boundary_weight: float = 0.3, sym_kwargs: Optional[dict] = None):
+        super().__init__()
+        self.region = BCEDiceLoss(bce_weight=bce_weight, smooth=1.0)
+        self.boundary = SymmetricBoundaryLoss(**(sym_kwargs or {}))
+        self.wb = boundary_weight
+
+    def forward(self, logits: Tensor, targets: Tensor) -> Tensor:
+        lg, tg = _prep(logits, targets)
+        if lg.shape[1] != 1:
+            raise CartsegError("boundary loss expects single-channel logits")
+        b, r, w = self.boundary, self.region, self.wb
+        sdf_gt = batch_sdf_from_masks(tg)
+        sdf_pred = _pred_sdf(lg, b.t)
+        return _seg_loss(lg, tg, sdf_gt, sdf_pred, lg.shape[0],
+                         w_elem=(1 - w) * r.w, alpha=1.0, gamma=0.0,
+                         w_dice=(1 - w) * (1 - r.w), smooth=r.smooth,
+                         w_bgt=w * b.scale * b.w_gt, w_bpred=w * b.scale * b.w_pred, use_abs=b.use_abs)

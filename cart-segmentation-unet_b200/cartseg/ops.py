@@ -1,0 +1,510 @@
+"""torch.library custom ops (namespace ``cartseg::``) over the C ABI of libcartseg.so.
+
+Every op is CUDA-only; there is no CPU implementation and no PyTorch fallback.  The ops are thin:
+argument checking, output allocation through torch (the caller owns every buffer, include/cartseg.h)
+and one ctypes call that enqueues work on the current torch stream.
+
+  cartseg::unet_forward / unet_backward      the whole U-Net (src/create_testset.py:40-83)
+  cartseg::seg_loss / seg_loss_backward      BCE+Dice, focal(-Dice), boundary, composite losses
+  cartseg::sdf                               exact-EDT signed distance maps
+  cartseg::threshold_stats / threshold_mask  sigmoid -> threshold -> sums / uint8 masks
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import CartsegError, LossDesc, UnetTensors, check, ptr
+
+# =============================================================================================
+# U-Net plans: one per (batch, channels, H, W, device, inference_only); each owns its workspace.
+# =============================================================================================
+_MAX_PLANS = {False: 2, True: 4}          # training / inference plans kept alive per process
+
+
+class Plan:
+    def __init__(self, plan_id: int, key, B, Cin, H, W, device, inference_only):
+        self.id = plan_id
+        self.key = key
+        self.shape = (B, Cin, H, W)
+        self.device = device
+        self.inference_only = inference_only
+        self.generation = 0               # bumped by every training-mode forward
+        self.pack_key = None              # identity + version of the weights currently packed
+        self.handle = C.c_void_p()
+        L = _lib.lib()
+        check(L.cs_unet_plan_create(C.byref(self.handle), B, Cin, H, W, int(inference_only)), "cs_unet_plan_create")
+        self.workspace_bytes = int(L.cs_unet_plan_workspace_bytes(self.handle))
+        self.workspace = torch.empty(self.workspace_bytes + 1024, dtype=torch.uint8, device=device)
+        base = self.workspace.data_ptr()
+        aligned = (base + 1023) & ~1023
+        with torch.cuda.device(device):
+            check(L.cs_unet_plan_bind(self.handle, aligned, self.workspace_bytes), "cs_unet_plan_bind")
+
+    def close(self):
+        if self.handle:
+            _lib.lib().cs_unet_plan_destroy(self.handle)
+            self.handle = C.c_void_p()
+        self.workspace = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_PLANS: Dict[int, Plan] = {}
+_PLAN_BY_KEY: "OrderedDict[tuple, int]" = OrderedDict()
+_next_plan_id = 1
+
+
+def get_plan(B: int, Cin: int, H: int, W: int, device: torch.device, inference_only: bool) -> Plan:
+    global _next_plan_id
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise CartsegError("cartseg U-Net runs on CUDA devices only (no CPU fallback)")
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    key = (B, Cin, H, W, idx, bool(inference_only))
+    pid = _PLAN_BY_KEY.get(key)
+    if pid is not None:
+        _PLAN_BY_KEY.move_to_end(key)
+        return _PLANS[pid]
+    # evict the least recently used plan of the same kind
+    same = [k for k in _PLAN_BY_KEY if k[5] == bool(inference_only) and k[4] == idx]
+    while len(same) >= _MAX_PLANS[bool(inference_only)]:
+        old = same.pop(0)
+        _PLANS.pop(_PLAN_BY_KEY.pop(old)).close()
+    plan = Plan(_next_plan_id, key, B, Cin, H, W, torch.device("cuda", idx), bool(inference_only))
+    _next_plan_id += 1
+    _PLANS[plan.id] = plan
+    _PLAN_BY_KEY[key] = plan.id
+    return plan
+
+
+def release_plans() -> None:
+    """Drop every cached plan (and its workspace)."""
+    for p in list(_PLANS.values()):
+        p.close()
+    _PLANS.clear()
+    _PLAN_BY_KEY.clear()
+
+
+def _plan(plan_id: int) -> Plan:
+    p = _PLANS.get(plan_id)
+    if p is None:
+        raise CartsegError(f"U-Net plan {plan_id} no longer exists (evicted or released before its backward ran)")
+    return p
+
+
+_WEIGHT_SLOTS = tuple([b + o for b in list(range(0, 40, 8)) + list(range(48, 80, 8)) for o in (0, 4)]
+                      + [40, 42, 44, 46])
+
+
+def _fill_tensors(params: List[Tensor], grads: Optional[List[Optional[Tensor]]],
+                  buffers: Optional[List[Tensor]]) -> UnetTensors:
+    t = UnetTensors()
+    if len(params) != _lib.NUM_PARAMS:
+        raise CartsegError(f"expected {_lib.NUM_PARAMS} parameters in state-dict order, got {len(params)}")
+    for i, p in enumerate(params):
+        if p.dtype != torch.float32 or not p.is_contiguous():
+            raise CartsegError(f"parameter {i} must be a contiguous float32 tensor")
+        t.param[i] = ptr(p)
+    if grads is not None:
+        for i, g in enumerate(grads):
+            t.grad[i] = ptr(g) if g is not None else None
+    if buffers is not None:
+        if len(buffers) != 3 * _lib.NUM_BN:
+            raise CartsegError(f"expected {3 * _lib.NUM_BN} BN buffers (mean, var, count per layer), got {len(buffers)}")
+        for i in range(_lib.NUM_BN):
+            rm, rv, nbt = buffers[3 * i], buffers[3 * i + 1], buffers[3 * i + 2]
+            if rm.dtype != torch.float32 or rv.dtype != torch.float32 or nbt.dtype != torch.int64:
+                raise CartsegError("BN buffers must be float32 running_mean / running_var and int64 num_batches_tracked")
+            t.running_mean[i] = ptr(rm)
+            t.running_var[i] = ptr(rv)
+            t.num_batches_tracked[i] = ptr(nbt)
+    return t
+
+
+def _ensure_packed(plan: Plan, params: List[Tensor], t: UnetTensors) -> None:
+    key = tuple((params[i].data_ptr(), params[i]._version) for i in _WEIGHT_SLOTS)
+    if key != plan.pack_key:
+        check(_lib.lib().cs_unet_pack_weights(plan.handle, C.byref(t), _lib.current_stream()), "cs_unet_pack_weights")
+        plan.pack_key = key
+
+
+@torch.library.custom_op("cartseg::unet_forward", mutates_args=("buffers",), device_types="cuda")
+def unet_forward(x: Tensor, params: List[Tensor], buffers: List[Tensor], training: bool, plan_id: int) -> Tensor:
+    plan = _plan(plan_id)
+    B, Cin, H, W = plan.shape
+    if tuple(x.shape) != (B, Cin, H, W) or x.dtype != torch.float32 or not x.is_contiguous():
+        raise CartsegError(f"x must be a contiguous float32 tensor of shape {(B, Cin, H, W)}, got {tuple(x.shape)} {x.dtype}")
+    logits = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
+    t = _fill_tensors(params, None, buffers)
+    with torch.cuda.device(x.device):
+        _ensure_packed(plan, params, t)
+        check(_lib.lib().cs_unet_forward(plan.handle, C.byref(t), ptr(x), int(training), ptr(logits),
+                                         _lib.current_stream()), "cs_unet_forward")
+    if training:
+        plan.generation += 1
+    return logits
+
+
+@unet_forward.register_fake
+def _(x, params, buffers, training, plan_id):
+    return x.new_empty((x.shape[0], 1, x.shape[2], x.shape[3]), dtype=torch.float32)
+
+
+# ---- backward ---------------------------------------------------------------------------------
+_stage_params_cache: Optional[List[List[int]]] = None
+
+
+def stage_params() -> List[List[int]]:
+    """Parameter indices finalised by each of the 23 backward stages (reverse execution order)."""
+    global _stage_params_cache
+    if _stage_params_cache is None:
+        L = _lib.lib()
+        out = []
+        buf = (C.c_int * 8)()
+        for s in range(_lib.NUM_BWD_STAGES):
+            n = L.cs_unet_stage_params(s, buf, 8)
+            if n < 0:
+                check(n, "cs_unet_stage_params")
+            out.append([int(buf[i]) for i in range(n)])
+        _stage_params_cache = out
+    return _stage_params_cache
+
+
+_DP_STATES: Dict[int, object] = {}         # handle -> parallel.GradSync (registered by cartseg.parallel)
+
+
+def grad_layout(params: List[Tensor]) -> Tuple[List[int], List[int], List[int]]:
+    """Flat gradient buffer layout, in backward-stage order so that a data-parallel bucket of
+    consecutive stages is one contiguous slice.  Returns (param order, element offset of each entry of
+    that order, element offset at which each of the 23 stages starts (+ the total))."""
+    order, offs, stage_off = [], [], []
+    off = 0
+    for st in stage_params():
+        stage_off.append(off)
+        for i in st:
+            order.append(i)
+            offs.append(off)
+            off += params[i].numel()
+    stage_off.append(off)
+    return order, offs, stage_off
+
+
+@torch.library.custom_op("cartseg::unet_backward", mutates_args=(), device_types="cuda")
+def unet_backward(dlogits: Tensor, params: List[Tensor], plan_id: int, generation: int, frozen_encoder_convs: int,
+                  dp_handle: int) -> Tensor:
+    """Returns ONE flat float32 buffer holding every parameter gradient (layout: grad_layout)."""
+    plan = _plan(plan_id)
+    if generation != plan.generation:
+        raise CartsegError("the activations of this forward pass were overwritten by a later training-mode forward "
+                           "of the same shape; run backward before the next forward")
+    B, _, H, W = plan.shape
+    if tuple(dlogits.shape) != (B, 1, H, W):
+        raise CartsegError(f"dlogits must have shape {(B, 1, H, W)}")
+    dlogits = dlogits.to(torch.float32).contiguous()
+    order, offs, stage_off = grad_layout(params)
+    flat = torch.empty(stage_off[-1], dtype=torch.float32, device=dlogits.device)
+    grads: List[Optional[Tensor]] = [None] * len(params)
+    for i, o in zip(order, offs):
+        grads[i] = flat[o:o + params[i].numel()]
+    for j in range(frozen_encoder_convs):
+        # frozen encoder convs are skipped by the kernels: their slices must not be garbage
+        base = (j // 2) * 8 + (j % 2) * 4
+        for i in range(base, base + 4):
+            grads[i].zero_()
+    t = _fill_tensors(params, grads, None)
+    L = _lib.lib()
+    sync = _DP_STATES.get(dp_handle) if dp_handle else None
+    if dp_handle and sync is None:
+        raise CartsegError(f"data-parallel handle {dp_handle} is not registered")
+    with torch.cuda.device(dlogits.device):
+        stream = _lib.current_stream()
+        if sync is None:
+            check(L.cs_unet_backward(plan.handle, C.byref(t), ptr(dlogits), 0, _lib.NUM_BWD_STAGES,
+                                     frozen_encoder_convs, stream), "cs_unet_backward")
+        else:
+            for (s0, s1) in sync.stage_buckets(stage_off):
+                check(L.cs_unet_backward(plan.handle, C.byref(t), ptr(dlogits), s0, s1, frozen_encoder_convs, stream),
+                      "cs_unet_backward")
+                sync.reduce_async(flat[stage_off[s0]:stage_off[s1]])
+            sync.finish()
+    return flat
+
+
+@unet_backward.register_fake
+def _(dlogits, params, plan_id, generation, frozen_encoder_convs, dp_handle):
+    return dlogits.new_empty(sum(p.numel() for p in params), dtype=torch.float32)
+
+
+class UNetFunction(torch.autograd.Function):
+    """Autograd glue: forward / backward are the two cartseg:: ops above."""
+
+    @staticmethod
+    def forward(ctx, x, plan_id, training, frozen, dp_handle, n_params, *tensors):
+        params = list(tensors[:n_params])
+        buffers = list(tensors[n_params:])
+        logits = torch.ops.cartseg.unet_forward(x, [p.detach() for p in params], buffers, training, plan_id)
+        ctx.plan_id = plan_id
+        ctx.generation = _plan(plan_id).generation
+        ctx.training = training
+        ctx.frozen = frozen
+        ctx.dp_handle = dp_handle
+        ctx.n_params = n_params
+        ctx.n_buffers = len(buffers)
+        ctx.save_for_backward(*params)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        if not ctx.training:
+            raise CartsegError("backward through an eval-mode forward is not available: call model.train() "
+                               "(batch-statistics BN) for training steps")
+        params = [p.detach() for p in ctx.saved_tensors]
+        flat = torch.ops.cartseg.unet_backward(dlogits, params, ctx.plan_id, ctx.generation, ctx.frozen, ctx.dp_handle)
+        order, offs, _ = grad_layout(params)
+        out: List[Optional[Tensor]] = [None] * ctx.n_params
+        need = ctx.needs_input_grad[6:6 + ctx.n_params]
+        for i, o in zip(order, offs):
+            if need[i]:
+                out[i] = flat[o:o + params[i].numel()].view(params[i].shape)
+        return (None, None, None, None, None, None, *out, *([None] * ctx.n_buffers))
+
+
+# =============================================================================================
+# Losses
+# =============================================================================================
+def _desc(rows: int, n: int, w_elem: float, alpha: float, gamma: float, elem_sum: bool, w_dice: float, smooth: float,
+          w_bgt: float, w_bpred: float, use_abs: bool, per_row: bool) -> LossDesc:
+    return LossDesc(rows, n, w_elem, alpha, gamma, int(elem_sum), w_dice, smooth, w_bgt, w_bpred, int(use_abs),
+                    int(per_row))
+
+
+def _check_loss_inputs(logits: Tensor, targets: Tensor, sdf_gt: Optional[Tensor], sdf_pred: Optional[Tensor],
+                       rows: int) -> int:
+    for name, v in (("logits", logits), ("targets", targets), ("sdf_gt", sdf_gt), ("sdf_pred", sdf_pred)):
+        if v is None:
+            continue
+        if not v.is_cuda:
+            raise CartsegError(f"{name} must be a CUDA tensor (no CPU fallback)")
+        if v.dtype != torch.float32 or not v.is_contiguous() or v.numel() != logits.numel():
+            raise CartsegError(f"{name} must be contiguous float32 with {logits.numel()} elements")
+    if rows < 1 or logits.numel() % rows:
+        raise CartsegError("rows must divide the number of elements")
+    n = logits.numel() // rows
+    if n % 4:
+        raise CartsegError("elements per Dice row must be a multiple of 4")
+    return n
+
+
+@torch.library.custom_op("cartseg::seg_loss", mutates_args=(), device_types="cuda")
+def seg_loss(logits: Tensor, targets: Tensor, sdf_gt: Optional[Tensor], sdf_pred: Optional[Tensor], rows: int,
+             w_elem: float, alpha: float, gamma: float, elem_sum: bool, w_dice: float, smooth: float, w_bgt: float,
+             w_bpred: float, use_abs: bool, per_row: bool) -> Tuple[Tensor, Tensor]:
+    n = _check_loss_inputs(logits, targets, sdf_gt, sdf_pred, rows)
+    L = _lib.lib()
+    scratch = torch.empty(int(L.cs_loss_scratch_bytes(rows)) // 8 + 1, dtype=torch.float64, device=logits.device)
+    out = torch.empty(rows if per_row else 1, dtype=torch.float32, device=logits.device)
+    d = _desc(rows, n, w_elem, alpha, gamma, elem_sum, w_dice, smooth, w_bgt, w_bpred, use_abs, per_row)
+    with torch.cuda.device(logits.device):
+        check(L.cs_loss_forward(C.byref(d), ptr(logits), ptr(targets), ptr(sdf_gt), ptr(sdf_pred), ptr(scratch),
+                                ptr(out), _lib.current_stream()), "cs_loss_forward")
+    return (out if per_row else out.reshape(())), scratch
+
+
+@seg_loss.register_fake
+def _(logits, targets, sdf_gt, sdf_pred, rows, w_elem, alpha, gamma, elem_sum, w_dice, smooth, w_bgt, w_bpred,
+      use_abs, per_row):
+    out = logits.new_empty((rows,) if per_row else (), dtype=torch.float32)
+    return out, logits.new_empty(rows * 8 + 3, dtype=torch.float64)
+
+
+@torch.library.custom_op("cartseg::seg_loss_backward", mutates_args=(), device_types="cuda")
+def seg_loss_backward(grad_out: Tensor, logits: Tensor, targets: Tensor, sdf_gt: Optional[Tensor],
+                      sdf_pred: Optional[Tensor], scratch: Tensor, rows: int, w_elem: float, alpha: float,
+                      gamma: float, elem_sum: bool, w_dice: float, smooth: float, w_bgt: float, w_bpred: float,
+                      use_abs: bool, per_row: bool) -> Tensor:
+    n = _check_loss_inputs(logits, targets, sdf_gt, sdf_pred, rows)
+    go = grad_out.to(torch.float32).contiguous().reshape(-1)
+    if go.numel() != (rows if per_row else 1):
+        raise CartsegError("grad_out has the wrong number of elements")
+    dlogits = torch.empty_like(logits)
+    d = _desc(rows, n, w_elem, alpha, gamma, elem_sum, w_dice, smooth, w_bgt, w_bpred, use_abs, per_row)
+    with torch.cuda.device(logits.device):
+        check(_lib.lib().cs_loss_backward(C.byref(d), ptr(logits), ptr(targets), ptr(sdf_gt), ptr(sdf_pred),
+                                          ptr(scratch), ptr(go), ptr(dlogits), _lib.current_stream()),
+              "cs_loss_backward")
+    return dlogits
+
+
+@seg_loss_backward.register_fake
+def _(grad_out, logits, *args):
+    return torch.empty_like(logits)
+
+
+def _seg_loss_setup(ctx, inputs, output):
+    logits, targets, sdf_gt, sdf_pred = inputs[:4]
+    ctx.scalars = inputs[4:]
+    ctx.has = (sdf_gt is not None, sdf_pred is not None)
+    saved = [logits, targets] + [v for v in (sdf_gt, sdf_pred) if v is not None] + [output[1]]
+    ctx.save_for_backward(*saved)
+
+
+def _seg_loss_bwd(ctx, grad_loss, grad_scratch):
+    saved = list(ctx.saved_tensors)
+    logits, targets = saved[0], saved[1]
+    k = 2
+    sdf_gt = sdf_pred = None
+    if ctx.has[0]:
+        sdf_gt = saved[k]; k += 1
+    if ctx.has[1]:
+        sdf_pred = saved[k]; k += 1
+    scratch = saved[k]
+    dlogits = torch.ops.cartseg.seg_loss_backward(grad_loss, logits, targets, sdf_gt, sdf_pred, scratch, *ctx.scalars)
+    return (dlogits,) + (None,) * 14
+
+
+seg_loss.register_autograd(_seg_loss_bwd, setup_context=_seg_loss_setup)
+
+
+# =============================================================================================
+# Signed distance maps
+# =============================================================================================
+@torch.library.custom_op("cartseg::sdf", mutates_args=(), device_types="cuda")
+def sdf(src: Tensor, thr: float, ge: bool, norm: float) -> Tensor:
+    """src [B,1,H,W] or [B,H,W] float32.  fg = src >= thr if ge else src > thr."""
+    if not src.is_cuda:
+        raise CartsegError("cartseg::sdf takes CUDA tensors only (no CPU fallback)")
+    if src.dtype != torch.float32 or not src.is_contiguous():
+        raise CartsegError("src must be contiguous float32")
+    if src.dim() == 4 and src.shape[1] == 1:
+        B, H, W = src.shape[0], src.shape[2], src.shape[3]
+    elif src.dim() == 3:
+        B, H, W = src.shape
+    else:
+        raise CartsegError("src must be [B,1,H,W] or [B,H,W]")
+    out = torch.empty_like(src)
+    if src.numel() == 0:
+        return out
+    L = _lib.lib()
+    scratch = torch.empty(int(L.cs_sdf_scratch_bytes(B, H, W)), dtype=torch.uint8, device=src.device)
+    with torch.cuda.device(src.device):
+        check(L.cs_sdf(ptr(src), thr, int(ge), B, H, W, norm, ptr(out), ptr(scratch), _lib.current_stream()), "cs_sdf")
+    return out
+
+
+@sdf.register_fake
+def _(src, thr, ge, norm):
+    return torch.empty_like(src)
+
+
+# =============================================================================================
+# Thresholding / metric sums
+# =============================================================================================
+@torch.library.custom_op("cartseg::threshold_stats", mutates_args=(), device_types="cuda")
+def threshold_stats(logits: Tensor, targets: Tensor, rows: int, xs: Tensor) -> Tuple[Tensor, Tensor]:
+    """counts [rows, K, 2] = (sum pred, sum pred*t) with pred = logits >= xs[k];
+    soft [rows, 3] = (sum p, sum t, sum p*t).  float64."""
+    for v in (logits, targets, xs):
+        if not v.is_cuda or v.dtype != torch.float32 or not v.is_contiguous():
+            raise CartsegError("threshold_stats takes contiguous float32 CUDA tensors")
+    if logits.numel() != targets.numel() or rows < 1 or logits.numel() % rows:
+        raise CartsegError("logits / targets size mismatch")
+    K = xs.numel()
+    n = logits.numel() // rows
+    counts = torch.empty((rows, K, 2), dtype=torch.float64, device=logits.device)
+    soft = torch.empty((rows, 3), dtype=torch.float64, device=logits.device)
+    L = _lib.lib()
+    with torch.cuda.device(logits.device):
+        stream = _lib.current_stream()
+        for k0 in range(0, K, 32):                   # the kernel handles up to 32 thresholds per pass
+            k1 = min(K, k0 + 32)
+            part = counts if K <= 32 else torch.empty((rows, k1 - k0, 2), dtype=torch.float64, device=logits.device)
+            check(L.cs_threshold_stats(ptr(logits), ptr(targets), rows, n, xs.data_ptr() + 4 * k0, k1 - k0, ptr(part),
+                                       ptr(soft), stream), "cs_threshold_stats")
+            if part is not counts:
+                counts[:, k0:k1] = part
+    return counts, soft
+
+
+@threshold_stats.register_fake
+def _(logits, targets, rows, xs):
+    return (logits.new_empty((rows, xs.numel(), 2), dtype=torch.float64),
+            logits.new_empty((rows, 3), dtype=torch.float64))
+
+
+@torch.library.custom_op("cartseg::threshold_mask", mutates_args=(), device_types="cuda")
+def threshold_mask(logits: Tensor, xstar: float) -> Tensor:
+    """uint8 mask = logits >= xstar (same shape as logits)."""
+    if not logits.is_cuda or logits.dtype != torch.float32 or not logits.is_contiguous():
+        raise CartsegError("threshold_mask takes a contiguous float32 CUDA tensor")
+    if logits.numel() % 4:
+        raise CartsegError("number of logits must be a multiple of 4")
+    mask = torch.empty(logits.shape, dtype=torch.uint8, device=logits.device)
+    if logits.numel():
+        with torch.cuda.device(logits.device):
+            check(_lib.lib().cs_threshold_mask(ptr(logits), logits.numel(), xstar, ptr(mask), _lib.current_stream()),
+                  "cs_threshold_mask")
+    return mask
+
+
+@threshold_mask.register_fake
+def _(logits, xstar):
+    return logits.new_empty(logits.shape, dtype=torch.uint8)
+
+
+# ---------------------------------------------------------------------------------------------
+# sigmoid(x) > t  <=>  x >= x*(t): the smallest float32 whose sigmoid passes the comparison.
+# Found by bisection over float32 bit patterns with torch's own float32 sigmoid, so thresholded
+# masks are bit-identical to the reference's sigmoid-then-compare (train_bce_dice.py:209 uses >,
+# create_pseudo_labels_gpu.py:294 uses >=) without materialising probabilities.
+# ---------------------------------------------------------------------------------------------
+_bound_cache: Dict[Tuple[float, bool], float] = {}
+
+
+def _f32_from_ordered(u: int) -> float:
+    import struct
+    # ordered-int -> float32: monotone map of int32 order onto float order
+    if u < 0:
+        u = -(u + 1)
+        bits = (u & 0x7FFFFFFF) | 0x80000000
+    else:
+        bits = u
+    return struct.unpack("<f", struct.pack("<I", bits & 0xFFFFFFFF))[0]
+
+
+def logit_bound(t: float, ge: bool = False) -> float:
+    """Smallest float32 x with sigmoid(x) > t (or >= t if ge); +inf if none."""
+    key = (float(t), bool(ge))
+    if key in _bound_cache:
+        return _bound_cache[key]
+    tt = torch.tensor(float(t), dtype=torch.float32)
+
+    def passes(x: float) -> bool:
+        # a 16-wide tensor so that ATen takes its vectorised path, as it does for whole logit maps
+        p = torch.sigmoid(torch.full((16,), x, dtype=torch.float32))[0]
+        return bool(p >= tt) if ge else bool(p > tt)
+
+    lo, hi = -0x7F7FFFFF - 1, 0x7F7FFFFF          # ordered ints of -FLT_MAX .. +FLT_MAX
+    if passes(_f32_from_ordered(lo)):
+        res = float("-inf")
+    elif not passes(_f32_from_ordered(hi)):
+        res = float("inf")
+    else:
+        while hi - lo > 1:                          # invariant: !passes(lo), passes(hi)
+            mid = (lo + hi) // 2
+            if passes(_f32_from_ordered(mid)):
+                hi = mid
+            else:
+                lo = mid
+        res = _f32_from_ordered(hi)
+    _bound_cache[key] = res
+    return res

@@ -1,0 +1,109 @@
+"""Data-parallel training: one process per GPU, batch sharded across ranks, gradients all-reduced
+over NCCL (NVLink 5 / NVSwitch) while the backward pass is still running.
+
+The reference is single-device (no torch.distributed anywhere — SURVEY.md §2.3); this is the one
+parallel strategy the path admits: images are independent units, the only exchange step is the
+gradient average.  BatchNorm statistics stay per shard (standard DDP semantics).
+
+How the overlap works: ``cs_unet_backward`` runs the 23 backward stages in reverse execution order and
+writes parameter gradients into ONE flat buffer laid out in that same order (ops.grad_layout).  Stages
+are grouped into buckets of ~``bucket_mb``; as soon as the kernels of a bucket are enqueued, an event is
+recorded and the bucket's contiguous slice is all-reduced on a side stream while the compute stream
+continues with the next stages.  The compute stream joins the side stream once, after the last stage.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def plan_buckets(stage_off: Sequence[int], bucket_elems: int) -> List[Tuple[int, int]]:
+    """Group consecutive backward stages into buckets of at least ``bucket_elems`` gradient elements.
+    ``stage_off[s]`` is the flat offset at which stage ``s`` starts (len = stages + 1).
+    Returns [(stage_begin, stage_end), ...] covering every stage exactly once, in order."""
+    n = len(stage_off) - 1
+    out: List[Tuple[int, int]] = []
+    s0 = 0
+    for s in range(n):
+        if stage_off[s + 1] - stage_off[s0] >= bucket_elems or s == n - 1:
+            out.append((s0, s + 1))
+            s0 = s + 1
+    return out
+
+
+class GradSync:
+    """Averages slices of the flat gradient buffer across the process group, asynchronously."""
+
+    def __init__(self, group: Optional[dist.ProcessGroup] = None, bucket_mb: float = 16.0):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.bucket_elems = max(1, int(bucket_mb * (1 << 20) / 4))
+        self._comm_stream = None
+        self._works = []
+        self._use_avg = dist.get_backend(group) == "nccl"
+        self._pending_scale: List[torch.Tensor] = []
+
+    def stage_buckets(self, stage_off: Sequence[int]) -> List[Tuple[int, int]]:
+        return plan_buckets(stage_off, self.bucket_elems)
+
+    def reduce_async(self, flat_slice: torch.Tensor) -> None:
+        if flat_slice.numel() == 0 or self.world == 1:
+            return
+        if flat_slice.is_cuda:
+            if self._comm_stream is None:
+                self._comm_stream = torch.cuda.Stream(device=flat_slice.device)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(flat_slice.device))
+            self._comm_stream.wait_event(ev)
+            with torch.cuda.stream(self._comm_stream):
+                op = dist.ReduceOp.AVG if self._use_avg else dist.ReduceOp.SUM
+                dist.all_reduce(flat_slice, op=op, group=self.group)
+                if not self._use_avg:
+                    flat_slice.mul_(1.0 / self.world)
+        else:                                           # CPU tensors (gloo): used by the host-logic tests
+            self._works.append(dist.all_reduce(flat_slice, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            self._pending_scale.append(flat_slice)
+
+    def finish(self) -> None:
+        """Make the reduced gradients visible to the current stream (call once per backward)."""
+        if self._comm_stream is not None:
+            torch.cuda.current_stream(self._comm_stream.device).wait_stream(self._comm_stream)
+        for w in self._works:
+            w.wait()
+        for t in self._pending_scale:
+            t.mul_(1.0 / self.world)
+        self._works.clear()
+        self._pending_scale.clear()
+
+
+_next_handle = 1
+
+
+def init_data_parallel(model, group: Optional[dist.ProcessGroup] = None, bucket_mb: float = 16.0,
+                       broadcast_from: int = 0):
+    """Make ``model`` (a cartseg.UNet) data-parallel over ``group``: broadcast rank-``broadcast_from``'s
+    parameters and BN buffers, and hook the bucketed gradient all-reduce into its backward.  Returns the model."""
+    global _next_handle
+    from . import ops
+    sync = GradSync(group, bucket_mb)
+    with torch.no_grad():
+        for t in list(model.parameters()) + list(model.buffers()):
+            dist.broadcast(t, src=broadcast_from, group=group)
+    handle = _next_handle
+    _next_handle += 1
+    ops._DP_STATES[handle] = sync
+    model._dp_handle = handle
+    return model
+
+
+def shard_batch(x: torch.Tensor, rank: int, world: int) -> torch.Tensor:
+    """Contiguous equal shard of a global batch (the batch must divide evenly: equal shards are what
+    makes mean-of-shard-losses equal the global-batch loss)."""
+    if x.shape[0] % world:
+        raise ValueError(f"global batch {x.shape[0]} is not divisible by world size {world}")
+    per = x.shape[0] // world
+    return x[rank * per:(rank + 1) * per]

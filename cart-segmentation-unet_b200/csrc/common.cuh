@@ -144,7 +144,7 @@ CS_DEVINL void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::
 // descriptor" table): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) |
 // layout=2 (128B swizzle) [61,64).
 //  * K-major operand  (rows = M/N index, 64 bf16 = 128 B of K per row): SBO = 1024 (8 rows),
-//    LBO unused.  Advance 16 elements along K inside the swizzle atom: start += 32 B.
+//    LBO ignored by the hardware (encoded as 16 B like CUTLASS does).  Advance 16 elements along K inside the swizzle atom: start += 32 B.
 //  * MN-major operand (rows = K index, 64 bf16 = 128 B of M/N per row): SBO = 1024 (8 K rows),
 //    LBO = byte distance between consecutive 64-element M/N blocks.  Advance 16 along K: start += 2048 B.
 CS_DEVINL uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {

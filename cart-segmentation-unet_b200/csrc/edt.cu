@@ -101,11 +101,11 @@ cudaError_t launch_sdf(const float* src, float thr, int ge, int B, int H, int W,
   if (e != cudaSuccess) return e;
   const int cols = B * W;
   sdf_columns_kernel<<<(cols + 63) / 64, 64, 0, s>>>(src, thr, ge, B, H, W, g, flags);
-  e = cudaGetLastError();
+  e = launched();
   if (e != cudaSuccess) return e;
   const int threads = W >= 256 ? 256 : ((W + 31) / 32) * 32;
   sdf_rows_kernel<<<B * H, threads, 2 * W * sizeof(int), s>>>(g, flags, H, W, norm, sdf);
-  return cudaGetLastError();
+  return launched();
 }
 
 }  // namespace cs

@@ -57,7 +57,7 @@ cudaError_t launch_pack_pairs(const float* in, int Na, int Nb, int T, bf16* out_
                               TapMap map_ba, cudaStream_t s) {
   dim3 grid((Nb + 31) / 32, (Na + 31) / 32), block(32, 8);
   pack_pairs_kernel<<<grid, block, 0, s>>>(in, Na, Nb, T, out_ab, map_ab, out_ba, map_ba);
-  return cudaGetLastError();
+  return launched();
 }
 
 __global__ void pack_first_kernel(const float* __restrict__ in, int Cout, int Cin, bf16* __restrict__ out) {
@@ -73,7 +73,7 @@ __global__ void pack_first_kernel(const float* __restrict__ in, int Cout, int Ci
 }
 cudaError_t launch_pack_first(const float* in, int Cout, int Cin, bf16* out, cudaStream_t s) {
   pack_first_kernel<<<(Cout * 64 + 255) / 256, 256, 0, s>>>(in, Cout, Cin, out);
-  return cudaGetLastError();
+  return launched();
 }
 
 __global__ void unpack_pairs_kernel(const float* __restrict__ dwp, int Na, int Nb, int T, TapMap map,
@@ -85,7 +85,7 @@ __global__ void unpack_pairs_kernel(const float* __restrict__ dwp, int Na, int N
 }
 cudaError_t launch_unpack_pairs(const float* dwp, int Na, int Nb, int T, TapMap map, float* grad, cudaStream_t s) {
   unpack_pairs_kernel<<<grid_for((long long)Na * Nb, 256), 256, 0, s>>>(dwp, Na, Nb, T, map, grad);
-  return cudaGetLastError();
+  return launched();
 }
 
 __global__ void unpack_first_kernel(const float* __restrict__ dwp, int Cout, int Cin, float* __restrict__ grad) {
@@ -97,7 +97,7 @@ __global__ void unpack_first_kernel(const float* __restrict__ dwp, int Cout, int
 }
 cudaError_t launch_unpack_first(const float* dwp, int Cout, int Cin, float* grad, cudaStream_t s) {
   unpack_first_kernel<<<(Cout * Cin * 9 + 255) / 256, 256, 0, s>>>(dwp, Cout, Cin, grad);
-  return cudaGetLastError();
+  return launched();
 }
 
 // ============================================================================ input im2col
@@ -128,7 +128,7 @@ __global__ void im2col_first_kernel(const float* __restrict__ x, int B, int Cin,
 cudaError_t launch_im2col_first(const float* x, int B, int Cin, int H, int W, bf16* col, cudaStream_t s) {
   if (9 * Cin > 64) return cudaErrorInvalidValue;
   im2col_first_kernel<<<grid_for((long long)B * H * W * 8, 256), 256, 0, s>>>(x, B, Cin, H, W, col);
-  return cudaGetLastError();
+  return launched();
 }
 
 // ============================================================================ batch norm: statistics -> affine
@@ -157,7 +157,7 @@ __global__ void bn_finalize_train_kernel(BnFinalizeArgs a) {
 }
 cudaError_t launch_bn_finalize_train(const BnFinalizeArgs& a, cudaStream_t s) {
   bn_finalize_train_kernel<<<(a.C + 127) / 128, 128, 0, s>>>(a);
-  return cudaGetLastError();
+  return launched();
 }
 
 __global__ void bn_fold_eval_kernel(const float* gamma, const float* beta, const float* conv_bias, const float* rm,
@@ -172,7 +172,7 @@ __global__ void bn_fold_eval_kernel(const float* gamma, const float* beta, const
 cudaError_t launch_bn_fold_eval(const float* gamma, const float* beta, const float* conv_bias, const float* rm,
                                 const float* rv, float eps, float* scale, float* shift, int C, cudaStream_t s) {
   bn_fold_eval_kernel<<<(C + 127) / 128, 128, 0, s>>>(gamma, beta, conv_bias, rm, rv, eps, scale, shift, C);
-  return cudaGetLastError();
+  return launched();
 }
 
 // ============================================================================ BN apply + ReLU (+ 2x2 max-pool)
@@ -241,7 +241,7 @@ cudaError_t launch_bn_relu(const bf16* y, int B, int H, int W, int C, const floa
     bn_relu_kernel<false><<<grid_for((long long)B * H * W * (C / 8), 256), 256, 0, s>>>(y, B, H, W, C, scale, shift,
                                                                                          out, out_pitch, out_c0, pooled);
   }
-  return cudaGetLastError();
+  return launched();
 }
 
 __global__ void maxpool_kernel(const bf16* __restrict__ in, int in_pitch, int in_c0, int B, int H, int W, int C,
@@ -270,7 +270,7 @@ cudaError_t launch_maxpool(const bf16* in, int in_pitch, int in_c0, int B, int H
                            cudaStream_t s) {
   maxpool_kernel<<<grid_for((long long)B * (H / 2) * (W / 2) * (C / 8), 256), 256, 0, s>>>(in, in_pitch, in_c0, B, H, W,
                                                                                            C, pooled);
-  return cudaGetLastError();
+  return launched();
 }
 
 // ============================================================================ BN + ReLU (+ pool/skip) backward
@@ -386,7 +386,7 @@ cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t s) {
   const size_t smem = 2 * a.C * sizeof(float);
   if (a.g_pool) bn_bwd_reduce_kernel<true><<<grid, 256, smem, s>>>(a);
   else bn_bwd_reduce_kernel<false><<<grid, 256, smem, s>>>(a);
-  return cudaGetLastError();
+  return launched();
 }
 
 template <bool POOL>
@@ -431,7 +431,7 @@ cudaError_t launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t s) {
   const int grid = grid_for(units * (a.C / 8), 256);
   if (a.g_pool) bn_bwd_apply_kernel<true><<<grid, 256, 0, s>>>(a);
   else bn_bwd_apply_kernel<false><<<grid, 256, 0, s>>>(a);
-  return cudaGetLastError();
+  return launched();
 }
 
 // ============================================================================ 1x1 head (C -> 1)
@@ -460,7 +460,7 @@ cudaError_t launch_head_fwd(const bf16* act, long long P, int C, const float* w,
                             cudaStream_t s) {
   // P is always a multiple of 32 here (H, W multiples of 16), so every warp iterates uniformly
   head_fwd_kernel<<<grid_for(P * 8, 256), 256, 0, s>>>(act, P, C, w, b, logits);
-  return cudaGetLastError();
+  return launched();
 }
 
 __global__ void __launch_bounds__(256) head_bwd_kernel(const bf16* __restrict__ act, const float* __restrict__ dlogits,
@@ -501,7 +501,7 @@ cudaError_t launch_head_bwd(const bf16* act, const float* dlogits, long long P, 
   if (grad_b) { e = cudaMemsetAsync(grad_b, 0, sizeof(float), s); if (e != cudaSuccess) return e; }
   head_bwd_kernel<<<grid_for(P, rpb * 8, 148 * 4), 256, (C + 1) * sizeof(float), s>>>(act, dlogits, P, C, w, g_act,
                                                                                      grad_w, grad_b);
-  return cudaGetLastError();
+  return launched();
 }
 
 // ============================================================================ per-channel sum (convT bias grad)
@@ -534,7 +534,7 @@ cudaError_t launch_channel_sum(const bf16* g, int pitch, int c0, long long P, in
   if (e != cudaSuccess) return e;
   const int rpb = 256 / (C / 8);
   channel_sum_kernel<<<grid_for(P, rpb * 8, 148 * 4), 256, C * sizeof(float), s>>>(g, pitch, c0, P, C, out);
-  return cudaGetLastError();
+  return launched();
 }
 
 }  // namespace cs

@@ -142,8 +142,8 @@ __global__ void __launch_bounds__(kThreads, 1) pix_gemm_kernel(const __grid_cons
               const uint32_t b_addr = smem_u32(smem + L::kB + sb * L::kBSlot);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                umma_bf16(d_tmem, make_smem_desc(a_addr + k * 32, 0, kAtomBytes),
-                          make_smem_desc(b_addr + k * 32, 0, kAtomBytes), idesc, accumulate);
+                umma_bf16(d_tmem, make_smem_desc(a_addr + k * 32, 16, kAtomBytes),
+                          make_smem_desc(b_addr + k * 32, 16, kAtomBytes), idesc, accumulate);
                 accumulate = 1;
               }
               umma_commit(&emptyB[sb]);
@@ -228,13 +228,15 @@ __global__ void __launch_bounds__(kThreads, 1) pix_gemm_kernel(const __grid_cons
         }
         if (want_stats) {
           // Column sums over the staged bf16 tile: this warp covers rows [32*sub, 32*sub+32), lane
-          // covers the channel pair (2*lane, 2*lane+1); rows the image does not have are exact zeros.
+          // covers the channel pair (2*lane, 2*lane+1).  Tile rows that lie outside the image hold
+          // values the store clips away; they are masked out here.
           const uint32_t* s32 = reinterpret_cast<const uint32_t*>(sbuf);
           const int chunk = lane >> 2, word = lane & 3;
           float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll 8
           for (int rr = 0; rr < 32; ++rr) {
             const int r2 = sub * 32 + rr;
+            if (w0 + (r2 & 7) >= p.W || h0 + (r2 >> 3) >= p.H) continue;
             const uint32_t w = s32[r2 * 32 + (((chunk ^ (r2 & 7)) << 2) | word)];
             const float f0 = bf16_lo(w), f1 = bf16_hi(w);
             s0 += f0; q0 += f0 * f0; s1 += f1; q1 += f1 * f1;
@@ -288,7 +290,7 @@ static cudaError_t launch_pix(const PixGemmParams& p, int num_sms, cudaStream_t 
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
   if (grid <= 0) return cudaSuccess;
   kern<<<grid, kThreads, L::kDyn, stream>>>(p);
-  return cudaGetLastError();
+  return launched();
 }
 
 cudaError_t launch_pix_gemm(const PixGemmParams& p, int block_n, int num_sms, cudaStream_t stream) {
@@ -455,7 +457,7 @@ static cudaError_t launch_wg(const WgradParams& p, cudaStream_t stream) {
   const int grid = p.m_blocks * p.n_blocks * p.G * p.splits;
   if (grid <= 0) return cudaSuccess;
   kern<<<grid, kThreads, L::kDyn, stream>>>(p);
-  return cudaGetLastError();
+  return launched();
 }
 
 cudaError_t launch_wgrad_gemm(const WgradParams& p, int block_n, cudaStream_t stream) {

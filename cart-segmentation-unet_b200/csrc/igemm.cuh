@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "launch_count.cuh"
+
 namespace cs {
 
 // ---------------------------------------------------------------------------------------------
@@ -28,6 +30,7 @@ struct PixGemmParams {
   int Ntot;             // rows per tap in B
   int n_blocks;         // Ntot / BLOCK_N
   int tiles_w, tiles_h, batch;
+  int H, W;             // extent of the tile grid's image (pixels past it are excluded from statistics)
   int o_blocks_per_map; // n-blocks written through one output map
   int o_chan0;          // first output channel (coordinate offset inside the O maps)
   const float* scale;   // per output channel (index inside its map), may be null

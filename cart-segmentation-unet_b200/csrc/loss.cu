@@ -119,7 +119,7 @@ cudaError_t launch_loss_forward(const LossArgs& a, cudaStream_t s) {
   if (bpr < 1) bpr = 1;
   dim3 grid((unsigned)bpr, (unsigned)a.rows);
   loss_forward_kernel<<<grid, 256, 0, s>>>(a);
-  return cudaGetLastError();
+  return launched();
 }
 
 __global__ void __launch_bounds__(256) loss_backward_kernel(LossArgs a) {
@@ -185,7 +185,7 @@ cudaError_t launch_loss_backward(const LossArgs& a, cudaStream_t s) {
   if (bpr < 1) bpr = 1;
   dim3 grid((unsigned)bpr, (unsigned)a.rows);
   loss_backward_kernel<<<grid, 256, 0, s>>>(a);
-  return cudaGetLastError();
+  return launched();
 }
 
 // ============================================================================ thresholded metrics
@@ -250,7 +250,7 @@ cudaError_t launch_threshold_stats(const float* logits, const float* targets, in
   if (K <= 4) threshold_stats_kernel<4><<<grid, 256, 0, s>>>(logits, targets, n, xs, K, counts, soft);
   else if (K <= 16) threshold_stats_kernel<16><<<grid, 256, 0, s>>>(logits, targets, n, xs, K, counts, soft);
   else threshold_stats_kernel<32><<<grid, 256, 0, s>>>(logits, targets, n, xs, K, counts, soft);
-  return cudaGetLastError();
+  return launched();
 }
 
 __global__ void threshold_mask_kernel(const float* __restrict__ logits, long long n4, float xstar,
@@ -267,7 +267,7 @@ cudaError_t launch_threshold_mask(const float* logits, long long n, float xstar,
   if (g > 148 * 16) g = 148 * 16;
   if (g < 1) g = 1;
   threshold_mask_kernel<<<(unsigned)g, 256, 0, s>>>(logits, n / 4, xstar, reinterpret_cast<uint32_t*>(mask));
-  return cudaGetLastError();
+  return launched();
 }
 
 }  // namespace cs

@@ -1,0 +1,821 @@
+// U-Net plan: workspace layout, TMA descriptors and the forward / backward launch sequences, plus the
+// C ABI declared in include/cartseg.h.
+//
+// Network (reference src/create_testset.py:40-83, logits = final_conv output):
+//   conv index  0..9   encoder  conv1.0 conv1.3 conv2.0 ... conv5.3   (level L = i/2 + 1)
+//               10..17 decoder  dconv4.0 dconv4.3 ... dconv1.0 dconv1.3
+//   up index    0..3   upconv4 upconv3 upconv2 upconv1
+// Activations are NHWC bf16.  The skip activations and the conv-transpose outputs are written
+// straight into the concat buffers ([pixels][2C]: up-sampled half first, then the skip — :78-81),
+// so torch.cat never materialises.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/cartseg.h"
+#include "igemm.cuh"
+#include "kernels.cuh"
+
+namespace cs {
+
+std::atomic<long long> g_kernel_launches{0};
+static thread_local char g_err[512] = "";
+
+static int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return -1;
+}
+
+#define CS_CUDA(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t e__ = (expr);                                                                      \
+    if (e__ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+#define CS_TRY(expr)                \
+  do {                              \
+    int r__ = (expr);               \
+    if (r__ != 0) return r__;       \
+  } while (0)
+
+static int device_sm_count(int* out) {
+  int dev = 0;
+  CS_CUDA(cudaGetDevice(&dev));
+  int major = 0;
+  CS_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) return fail("cartseg needs an sm_100a device (found compute capability %d.x); there is no fallback", major);
+  CS_CUDA(cudaDeviceGetAttribute(out, cudaDevAttrMultiProcessorCount, dev));
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------
+// NHWC view: `pitch` channels per pixel, the tensor of interest starting at channel c0.
+struct View {
+  bf16* p = nullptr;
+  int pitch = 0, c0 = 0;
+};
+
+// TMA map over an NHWC buffer seen as (channels, W, H, B) with a (64, 8, rows, 1) box.
+static int nhwc_map(CUtensorMap* m, const bf16* base, int pitch, int B, int H, int W, int rows) {
+  const uint64_t dims[4] = {(uint64_t)pitch, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  const uint64_t st[3] = {(uint64_t)pitch * 2, (uint64_t)W * pitch * 2, (uint64_t)H * W * pitch * 2};
+  const uint32_t box[4] = {64, 8, (uint32_t)rows, 1};
+  int r = make_tmap_4d(m, base, dims, st, box);
+  if (r != 0) return fail("cuTensorMapEncodeTiled (NHWC %dx%dx%dx%d, pitch %d) failed: %d", B, H, W, pitch, pitch, r);
+  return 0;
+}
+// Same buffer at twice the resolution, sampled at pixels (2h+i, 2w+j): the conv-transpose scatter /
+// gather views.  (H, W) are the COARSE extents; the buffer is [B][2H][2W][pitch].
+static int nhwc_map_strided(CUtensorMap* m, const bf16* base, int pitch, int B, int H, int W, int i, int j) {
+  const uint64_t dims[4] = {(uint64_t)pitch, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  const uint64_t st[3] = {(uint64_t)2 * pitch * 2, (uint64_t)2 * (2 * W) * pitch * 2,
+                          (uint64_t)(2 * H) * (2 * W) * pitch * 2};
+  const uint32_t box[4] = {64, 8, 16, 1};
+  int r = make_tmap_4d(m, base + ((size_t)i * (2 * W) + j) * pitch, dims, st, box);
+  if (r != 0) return fail("cuTensorMapEncodeTiled (strided NHWC) failed: %d", r);
+  return 0;
+}
+static int weight_map(CUtensorMap* m, const bf16* base, int K, int rows, int block_n) {
+  int r = make_tmap_2d(m, base, (uint64_t)K, (uint64_t)rows, (uint64_t)K * 2, 64, (uint32_t)block_n);
+  if (r != 0) return fail("cuTensorMapEncodeTiled (weights %d x %d) failed: %d", rows, K, r);
+  return 0;
+}
+
+static int pick_block_n(int n) { return n % 256 == 0 ? 256 : (n % 128 == 0 ? 128 : 64); }
+
+static void pix_common(PixGemmParams& p, int B, int H, int W, int K, int Ntot, int block_n) {
+  memset(&p, 0, sizeof(p));
+  p.kchunks = K / 64;
+  p.Ntot = Ntot;
+  p.n_blocks = Ntot / block_n;
+  p.tiles_w = (W + 7) / 8;
+  p.tiles_h = (H + 15) / 16;
+  p.batch = B;
+  p.H = H;
+  p.W = W;
+  p.o_blocks_per_map = p.n_blocks;
+}
+
+// 3x3 convolution as 9 shifted GEMMs: group g = horizontal tap (dw = g-1), r = vertical tap.
+static int build_conv3x3(PixGemmParams& p, int* block_n, View in, int K, View out, int N, const bf16* wpack, int B,
+                         int H, int W) {
+  *block_n = pick_block_n(N);
+  pix_common(p, B, H, W, K, N, *block_n);
+  p.G = 3;
+  p.R = 3;
+  for (int g = 0; g < 3; ++g) { p.a_map[g] = 0; p.a_dw[g] = g - 1; p.a_dh[g] = -1; }
+  p.a_chan0 = in.c0;
+  p.o_chan0 = out.c0;
+  CS_TRY(nhwc_map(&p.tmapA[0], in.p, in.pitch, B, H, W, 18));
+  CS_TRY(weight_map(&p.tmapB, wpack, K, 9 * N, *block_n));
+  CS_TRY(nhwc_map(&p.tmapO[0], out.p, out.pitch, B, H, W, 16));
+  return 0;
+}
+// Plain [pixels x K] * [K x N] (the im2col'd first conv).
+static int build_pointwise(PixGemmParams& p, int* block_n, View in, int K, View out, int N, const bf16* wpack,
+                           int B, int H, int W) {
+  *block_n = pick_block_n(N);
+  pix_common(p, B, H, W, K, N, *block_n);
+  p.G = 1;
+  p.R = 1;
+  p.a_chan0 = in.c0;
+  p.o_chan0 = out.c0;
+  CS_TRY(nhwc_map(&p.tmapA[0], in.p, in.pitch, B, H, W, 16));
+  CS_TRY(weight_map(&p.tmapB, wpack, K, N, *block_n));
+  CS_TRY(nhwc_map(&p.tmapO[0], out.p, out.pitch, B, H, W, 16));
+  return 0;
+}
+// ConvTranspose2d(k=2, s=2): out[2h+i, 2w+j, co] = sum_ci in[h, w, ci] * W[ci, co, i, j] (+ bias).
+// (H, W) = input extents; `out` has twice the resolution.  wpack = [4][Cout][Cin].
+static int build_convT_fprop(PixGemmParams& p, int* block_n, View in, int Cin, View out, int Cout, const bf16* wpack,
+                             const float* bias, int B, int H, int W) {
+  *block_n = pick_block_n(Cout);
+  pix_common(p, B, H, W, Cin, 4 * Cout, *block_n);
+  p.G = 1;
+  p.R = 1;
+  p.a_chan0 = in.c0;
+  p.o_chan0 = out.c0;
+  p.o_blocks_per_map = Cout / *block_n;
+  p.shift = bias;
+  CS_TRY(nhwc_map(&p.tmapA[0], in.p, in.pitch, B, H, W, 16));
+  CS_TRY(weight_map(&p.tmapB, wpack, Cin, 4 * Cout, *block_n));
+  for (int ij = 0; ij < 4; ++ij) CS_TRY(nhwc_map_strided(&p.tmapO[ij], out.p, out.pitch, B, H, W, ij >> 1, ij & 1));
+  return 0;
+}
+// Its input gradient: dx[h, w, ci] = sum_{ij, co} dy[2h+i, 2w+j, co] * W[ci, co, i, j].  wpack = [4][Cin][Cout].
+static int build_convT_dgrad(PixGemmParams& p, int* block_n, View dy, int Cout, View dx, int Cin, const bf16* wpack,
+                             int B, int H, int W) {
+  *block_n = pick_block_n(Cin);
+  pix_common(p, B, H, W, Cout, Cin, *block_n);
+  p.G = 4;
+  p.R = 1;
+  for (int g = 0; g < 4; ++g) {
+    p.a_map[g] = g;
+    CS_TRY(nhwc_map_strided(&p.tmapA[g], dy.p, dy.pitch, B, H, W, g >> 1, g & 1));
+  }
+  p.a_chan0 = dy.c0;
+  p.o_chan0 = dx.c0;
+  CS_TRY(weight_map(&p.tmapB, wpack, Cout, 4 * Cin, *block_n));
+  CS_TRY(nhwc_map(&p.tmapO[0], dx.p, dx.pitch, B, H, W, 16));
+  return 0;
+}
+
+static void wgrad_common(WgradParams& p, int* block_n, int M, int N, int B, int H, int W, int G, float* dw) {
+  memset(&p, 0, sizeof(p));
+  *block_n = N % 128 == 0 ? 128 : 64;
+  p.G = G;
+  p.Mtot = M;
+  p.Ntot = N;
+  p.m_blocks = (M + 127) / 128;
+  p.n_blocks = N / *block_n;
+  p.tiles_w = (W + 7) / 8;
+  p.tiles_h = (H + 15) / 16;
+  p.batch = B;
+  const int tiles = p.tiles_w * p.tiles_h * B;
+  const int base = p.m_blocks * p.n_blocks * G;
+  int splits = (148 * 4 + base - 1) / base;
+  if (splits > tiles / 16) splits = tiles / 16;
+  if (splits < 1) splits = 1;
+  p.splits = splits;
+  p.dw = dw;
+}
+// dW[kw*3+kh][co][ci] = sum_pixels dy[pixel, co] * x[pixel + (kh-1, kw-1), ci]
+static int build_conv3x3_wgrad(WgradParams& p, int* block_n, View x, int Cin, View dy, int Cout, float* dw, int B,
+                               int H, int W) {
+  wgrad_common(p, block_n, Cout, Cin, B, H, W, 3, dw);
+  p.R = 3;
+  for (int g = 0; g < 3; ++g) { p.x_dw[g] = g - 1; p.x_dh[g] = -1; }
+  p.dy_chan0 = dy.c0;
+  p.x_chan0 = x.c0;
+  CS_TRY(nhwc_map(&p.tmapDY[0], dy.p, dy.pitch, B, H, W, 16));
+  CS_TRY(nhwc_map(&p.tmapX[0], x.p, x.pitch, B, H, W, 18));
+  return 0;
+}
+// dW[co][k] = sum_pixels dy[pixel, co] * col[pixel, k]   (first conv on its im2col matrix)
+static int build_pointwise_wgrad(WgradParams& p, int* block_n, View x, int K, View dy, int Cout, float* dw, int B,
+                                 int H, int W) {
+  wgrad_common(p, block_n, Cout, K, B, H, W, 1, dw);
+  p.R = 1;
+  p.dy_chan0 = dy.c0;
+  p.x_chan0 = x.c0;
+  CS_TRY(nhwc_map(&p.tmapDY[0], dy.p, dy.pitch, B, H, W, 16));
+  CS_TRY(nhwc_map(&p.tmapX[0], x.p, x.pitch, B, H, W, 16));
+  return 0;
+}
+// dW[ij][ci][co] = sum_pixels x[pixel, ci] * dy[(2h+i, 2w+j), co]; the coarse input x plays the
+// "M" operand, the four strided views of dy the "N" operand.
+static int build_convT_wgrad(WgradParams& p, int* block_n, View x, int Cin, View dy, int Cout, float* dw, int B,
+                             int H, int W) {
+  wgrad_common(p, block_n, Cin, Cout, B, H, W, 4, dw);
+  p.R = 1;
+  for (int g = 0; g < 4; ++g) {
+    p.x_map[g] = g;
+    CS_TRY(nhwc_map_strided(&p.tmapX[g], dy.p, dy.pitch, B, H, W, g >> 1, g & 1));
+  }
+  p.dy_chan0 = x.c0;
+  p.x_chan0 = dy.c0;
+  CS_TRY(nhwc_map(&p.tmapDY[0], x.p, x.pitch, B, H, W, 16));
+  return 0;
+}
+
+static const TapMap kTapFprop = {{0, 3, 6, 1, 4, 7, 2, 5, 8}};   // (kh,kw) -> kw*3 + kh
+static const TapMap kTapDgrad = {{8, 5, 2, 7, 4, 1, 6, 3, 0}};   // (kh,kw) -> (2-kw)*3 + (2-kh)
+static const TapMap kTapWgrad = {{0, 3, 6, 1, 4, 7, 2, 5, 8}};   // packed tap g*3+r -> kh*3+kw = r*3+g
+static const TapMap kTapIdent = {{0, 1, 2, 3, 4, 5, 6, 7, 8}};
+
+}  // namespace cs
+
+using namespace cs;
+
+// =============================================================================================
+//                                         the plan
+// =============================================================================================
+struct ConvL {
+  int cin, cout, H, W;
+  long long P;                       // B*H*W
+  int pw, pb, pgamma, pbeta;         // parameter indices
+  View in, out, g_out, g_in;         // input act, post-ReLU act, grad wrt out, grad wrt in (p == null: none)
+  bf16 *y, *dy, *pooled, *g_pool;
+  bf16 *wf, *wd;
+  double *st_sum, *st_sq, *bst1, *bst2;
+  float *scale, *shift, *mean, *invstd;
+  PixGemmParams fp_train, fp_eval, dg;
+  WgradParams wg;
+  int bn_f, bn_d, bn_w;
+};
+struct UpL {
+  int cin, cout, H, W;               // H, W: input (coarse) extents
+  long long P;
+  int pw, pb;
+  View in, out, g_out, g_in;         // out / g_out live in the concat buffers (pitch 2*cout, c0 = 0)
+  bf16 *wf, *wd;
+  PixGemmParams fp, dg;
+  WgradParams wg;
+  int bn_f, bn_d, bn_w;
+};
+
+struct cs_unet_plan {
+  int B, Cin, H, W;
+  int num_sms;
+  size_t ws_bytes;
+  uint8_t* ws;
+  bool bound, forward_done, infer;
+  ConvL conv[18];
+  UpL up[4];
+  bf16* col;                         // im2col of the input image [P1][64]
+  float* dwp;                        // packed weight-gradient accumulator, shared by all layers
+  uint8_t* stats_begin;
+  size_t stats_bytes;
+};
+
+namespace {
+
+struct Arena {
+  uint8_t* base;
+  size_t off;
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 1023) & ~(size_t)1023;
+    T* p = reinterpret_cast<T*>(base + off);
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+int conv_param_base(int i) { return i < 10 ? (i / 2) * 8 + (i % 2) * 4 : 48 + ((i - 10) / 2) * 8 + ((i - 10) % 2) * 4; }
+
+// Assigns every buffer.  Run once with base == nullptr to size the workspace, once more at bind time.
+void layout(cs_unet_plan* pl, uint8_t* base) {
+  Arena a{base, 0};
+  const int B = pl->B;
+  const bool train = !pl->infer;
+  int LH[6], LW[6], LC[6];
+  long long LP[6];
+  for (int L = 1; L <= 5; ++L) {
+    LH[L] = pl->H >> (L - 1);
+    LW[L] = pl->W >> (L - 1);
+    LC[L] = 64 << (L - 1);
+    LP[L] = (long long)B * LH[L] * LW[L];
+  }
+  pl->col = a.take<bf16>(LP[1] * 64);
+  bf16* cat[5];
+  bf16* gcat[5];
+  for (int L = 1; L <= 4; ++L) {
+    cat[L] = a.take<bf16>(LP[L] * 2 * LC[L]);
+    gcat[L] = train ? a.take<bf16>(LP[L] * 2 * LC[L]) : nullptr;
+  }
+  size_t dwp_elems = 0;
+  for (int i = 0; i < 18; ++i) {
+    ConvL& c = pl->conv[i];
+    int L;
+    if (i < 10) {
+      L = i / 2 + 1;
+      c.cout = LC[L];
+      c.cin = (i % 2) ? LC[L] : (L == 1 ? 64 /* padded K of the im2col'd image */ : LC[L - 1]);
+    } else {
+      L = 4 - (i - 10) / 2;
+      c.cout = LC[L];
+      c.cin = (i % 2) ? LC[L] : 2 * LC[L];
+    }
+    c.H = LH[L];
+    c.W = LW[L];
+    c.P = LP[L];
+    const int pb = conv_param_base(i);
+    c.pw = pb; c.pb = pb + 1; c.pgamma = pb + 2; c.pbeta = pb + 3;
+    c.y = train ? a.take<bf16>(c.P * c.cout) : nullptr;
+    c.dy = train ? a.take<bf16>(c.P * c.cout) : nullptr;
+    c.pooled = nullptr;
+    c.g_pool = nullptr;
+    const bool skip_producer = i < 8 && (i % 2) == 1;          // conv1.3 .. conv4.3
+    if (skip_producer) {
+      c.out = View{cat[L], 2 * LC[L], LC[L]};
+      c.g_out = View{gcat[L], 2 * LC[L], LC[L]};
+      c.pooled = a.take<bf16>(LP[L + 1] * LC[L]);
+      c.g_pool = train ? a.take<bf16>(LP[L + 1] * LC[L]) : nullptr;
+    } else {
+      c.out = View{a.take<bf16>(c.P * c.cout), c.cout, 0};
+      c.g_out = View{train ? a.take<bf16>(c.P * c.cout) : nullptr, c.cout, 0};
+    }
+    c.wf = a.take<bf16>((size_t)9 * c.cout * c.cin);
+    c.wd = train ? a.take<bf16>((size_t)9 * c.cout * c.cin) : nullptr;
+    c.scale = a.take<float>(c.cout);
+    c.shift = a.take<float>(c.cout);
+    c.mean = a.take<float>(c.cout);
+    c.invstd = a.take<float>(c.cout);
+    const size_t e = (size_t)(i == 0 ? 1 : 9) * c.cout * c.cin;
+    if (e > dwp_elems) dwp_elems = e;
+  }
+  // inputs / input gradients (wired after all outputs exist)
+  for (int i = 0; i < 18; ++i) {
+    ConvL& c = pl->conv[i];
+    if (i == 0) {
+      c.in = View{pl->col, 64, 0};
+      c.g_in = View{};
+    } else if (i < 10 && (i % 2) == 0) {                        // convL.0, L >= 2: pooled skip of the level above
+      c.in = View{pl->conv[i - 1].pooled, pl->conv[i - 1].cout, 0};
+      c.g_in = View{pl->conv[i - 1].g_pool, pl->conv[i - 1].cout, 0};
+    } else if (i >= 10 && (i % 2) == 0) {                       // dconvL.0: the concat buffer
+      const int L = 4 - (i - 10) / 2;
+      c.in = View{cat[L], 2 * LC[L], 0};
+      c.g_in = View{gcat[L], 2 * LC[L], 0};
+    } else {                                                    // X.3: output of X.0
+      c.in = pl->conv[i - 1].out;
+      c.g_in = pl->conv[i - 1].g_out;
+    }
+  }
+  for (int k = 0; k < 4; ++k) {
+    UpL& u = pl->up[k];
+    const int L = 4 - k;                                        // output level
+    u.cin = LC[L + 1];
+    u.cout = LC[L];
+    u.H = LH[L + 1];
+    u.W = LW[L + 1];
+    u.P = LP[L + 1];
+    u.pw = 40 + 2 * k;
+    u.pb = 41 + 2 * k;
+    const ConvL& src = k == 0 ? pl->conv[9] : pl->conv[10 + 2 * (k - 1) + 1];
+    u.in = src.out;
+    u.g_in = src.g_out;
+    u.out = View{cat[L], 2 * LC[L], 0};
+    u.g_out = View{gcat[L], 2 * LC[L], 0};
+    u.wf = a.take<bf16>((size_t)4 * u.cin * u.cout);
+    u.wd = train ? a.take<bf16>((size_t)4 * u.cin * u.cout) : nullptr;
+    const size_t e = (size_t)4 * u.cin * u.cout;
+    if (e > dwp_elems) dwp_elems = e;
+  }
+  pl->dwp = train ? a.take<float>(dwp_elems) : nullptr;
+  // statistics (zeroed once per forward): forward sums and backward sums of every BN
+  a.off = (a.off + 1023) & ~(size_t)1023;
+  pl->stats_begin = base + a.off;
+  const size_t s0 = a.off;
+  for (int i = 0; i < 18; ++i) {
+    ConvL& c = pl->conv[i];
+    c.st_sum = a.take<double>(2 * (size_t)c.cout);
+    c.st_sq = c.st_sum + c.cout;
+    c.bst1 = a.take<double>(2 * (size_t)c.cout);      // re-zeroed by every backward stage
+    c.bst2 = c.bst1 + c.cout;
+  }
+  pl->stats_bytes = a.off - s0;
+  pl->ws_bytes = (a.off + 1023) & ~(size_t)1023;
+}
+
+int encode_maps(cs_unet_plan* pl) {
+  const int B = pl->B;
+  for (int i = 0; i < 18; ++i) {
+    ConvL& c = pl->conv[i];
+    const View y{c.y, c.cout, 0}, dy{c.dy, c.cout, 0};
+    const bool train = !pl->infer;
+    if (i == 0) {
+      CS_TRY(build_pointwise(c.fp_eval, &c.bn_f, c.in, 64, c.out, c.cout, c.wf, B, c.H, c.W));
+      if (train) {
+        CS_TRY(build_pointwise(c.fp_train, &c.bn_f, c.in, 64, y, c.cout, c.wf, B, c.H, c.W));
+        CS_TRY(build_pointwise_wgrad(c.wg, &c.bn_w, c.in, 64, dy, c.cout, pl->dwp, B, c.H, c.W));
+      }
+      c.bn_d = 0;
+    } else {
+      CS_TRY(build_conv3x3(c.fp_eval, &c.bn_f, c.in, c.cin, c.out, c.cout, c.wf, B, c.H, c.W));
+      if (train) {
+        CS_TRY(build_conv3x3(c.fp_train, &c.bn_f, c.in, c.cin, y, c.cout, c.wf, B, c.H, c.W));
+        CS_TRY(build_conv3x3(c.dg, &c.bn_d, dy, c.cout, c.g_in, c.cin, c.wd, B, c.H, c.W));
+        CS_TRY(build_conv3x3_wgrad(c.wg, &c.bn_w, c.in, c.cin, dy, c.cout, pl->dwp, B, c.H, c.W));
+      }
+    }
+    c.fp_train.stat_sum = c.st_sum;
+    c.fp_train.stat_sq = c.st_sq;
+    c.fp_eval.scale = c.scale;
+    c.fp_eval.shift = c.shift;
+    c.fp_eval.relu = 1;
+  }
+  for (int k = 0; k < 4; ++k) {
+    UpL& u = pl->up[k];
+    CS_TRY(build_convT_fprop(u.fp, &u.bn_f, u.in, u.cin, u.out, u.cout, u.wf, nullptr, B, u.H, u.W));
+    if (!pl->infer) {
+      CS_TRY(build_convT_dgrad(u.dg, &u.bn_d, u.g_out, u.cout, u.g_in, u.cin, u.wd, B, u.H, u.W));
+      CS_TRY(build_convT_wgrad(u.wg, &u.bn_w, u.in, u.cin, u.g_out, u.cout, pl->dwp, B, u.H, u.W));
+    }
+  }
+  return 0;
+}
+
+}  // namespace
+
+// =============================================================================================
+//                                          C ABI
+// =============================================================================================
+extern "C" {
+
+const char* cs_last_error(void) { return g_err; }
+int cs_version(void) { return 1; }
+long long cs_kernel_launch_count(void) { return g_kernel_launches.load(); }
+
+int cs_unet_plan_create(cs_unet_plan** out, int batch, int in_channels, int height, int width, int inference_only) {
+  if (!out) return fail("plan pointer is null");
+  *out = nullptr;
+  if (batch < 1) return fail("batch must be >= 1 (got %d)", batch);
+  if (in_channels < 1 || in_channels > 7) return fail("in_channels must be in [1, 7] (got %d)", in_channels);
+  if (height < 16 || width < 16 || height % 16 || width % 16)
+    return fail("height and width must be positive multiples of 16 (got %d x %d)", height, width);
+  cs_unet_plan* pl = new (std::nothrow) cs_unet_plan();
+  if (!pl) return fail("out of host memory");
+  memset(pl, 0, sizeof(*pl));
+  pl->B = batch; pl->Cin = in_channels; pl->H = height; pl->W = width;
+  pl->infer = inference_only != 0;
+  layout(pl, nullptr);
+  *out = pl;
+  return 0;
+}
+
+void cs_unet_plan_destroy(cs_unet_plan* plan) { delete plan; }
+
+size_t cs_unet_plan_workspace_bytes(const cs_unet_plan* plan) { return plan ? plan->ws_bytes : 0; }
+
+int cs_unet_plan_bind(cs_unet_plan* pl, void* workspace, size_t bytes) {
+  if (!pl) return fail("plan is null");
+  if (!workspace || bytes < pl->ws_bytes) return fail("workspace too small: %zu < %zu bytes", bytes, pl->ws_bytes);
+  if ((uintptr_t)workspace & 1023) return fail("workspace must be 1024-byte aligned");
+  CS_TRY(device_sm_count(&pl->num_sms));
+  pl->ws = static_cast<uint8_t*>(workspace);
+  layout(pl, pl->ws);
+  CS_TRY(encode_maps(pl));
+  pl->bound = true;
+  pl->forward_done = false;
+  return 0;
+}
+
+int cs_unet_pack_weights(cs_unet_plan* pl, const cs_unet_tensors* t, cs_stream_t stream) {
+  if (!pl || !pl->bound) return fail("plan is not bound to a workspace");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  for (int i = 0; i < 18; ++i) {
+    const ConvL& c = pl->conv[i];
+    if (!t->param[c.pw]) return fail("parameter %d is null", c.pw);
+    if (i == 0) CS_CUDA(launch_pack_first(t->param[c.pw], c.cout, pl->Cin, c.wf, s));
+    else CS_CUDA(launch_pack_pairs(t->param[c.pw], c.cout, c.cin, 9, c.wf, kTapFprop, c.wd, kTapDgrad, s));
+  }
+  for (int k = 0; k < 4; ++k) {
+    const UpL& u = pl->up[k];
+    if (!t->param[u.pw]) return fail("parameter %d is null", u.pw);
+    // IOHW [ci][co][ij]: dgrad pack [ij][ci][co] (a-major), fprop pack [ij][co][ci] (b-major)
+    CS_CUDA(launch_pack_pairs(t->param[u.pw], u.cin, u.cout, 4, u.wd, kTapIdent, u.wf, kTapIdent, s));
+  }
+  return 0;
+}
+
+int cs_unet_forward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* x, int training, float* logits,
+                    cs_stream_t stream) {
+  if (!pl || !pl->bound) return fail("plan is not bound to a workspace");
+  if (!x || !logits) return fail("x / logits is null");
+  if (training && pl->infer) return fail("this plan was created inference_only: training-mode forward is not available");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int B = pl->B;
+  if (training) CS_CUDA(cudaMemsetAsync(pl->stats_begin, 0, pl->stats_bytes, s));
+  CS_CUDA(launch_im2col_first(x, B, pl->Cin, pl->H, pl->W, pl->col, s));
+
+  auto run_conv = [&](int i) -> int {
+    ConvL& c = pl->conv[i];
+    if (training) {
+      CS_CUDA(launch_pix_gemm(c.fp_train, c.bn_f, pl->num_sms, s));
+      BnFinalizeArgs f{};
+      f.sum = c.st_sum; f.sq = c.st_sq; f.count = (double)c.P;
+      f.gamma = t->param[c.pgamma]; f.beta = t->param[c.pbeta]; f.conv_bias = t->param[c.pb];
+      f.running_mean = t->running_mean[i]; f.running_var = t->running_var[i];
+      f.num_batches_tracked = t->num_batches_tracked[i];
+      f.momentum = 0.1f; f.eps = 1e-5f;
+      f.scale = c.scale; f.shift = c.shift; f.mean = c.mean; f.invstd = c.invstd; f.C = c.cout;
+      CS_CUDA(launch_bn_finalize_train(f, s));
+      CS_CUDA(launch_bn_relu(c.y, B, c.H, c.W, c.cout, c.scale, c.shift, c.out.p, c.out.pitch, c.out.c0, c.pooled, s));
+    } else {
+      if (!t->running_mean[i] || !t->running_var[i]) return fail("running statistics of BN %d are null", i);
+      CS_CUDA(launch_bn_fold_eval(t->param[c.pgamma], t->param[c.pbeta], t->param[c.pb], t->running_mean[i],
+                                  t->running_var[i], 1e-5f, c.scale, c.shift, c.cout, s));
+      CS_CUDA(launch_pix_gemm(c.fp_eval, c.bn_f, pl->num_sms, s));
+      if (c.pooled) CS_CUDA(launch_maxpool(c.out.p, c.out.pitch, c.out.c0, B, c.H, c.W, c.cout, c.pooled, s));
+    }
+    return 0;
+  };
+  for (int i = 0; i < 10; ++i) CS_TRY(run_conv(i));
+  for (int k = 0; k < 4; ++k) {
+    UpL& u = pl->up[k];
+    u.fp.shift = t->param[u.pb];
+    CS_CUDA(launch_pix_gemm(u.fp, u.bn_f, pl->num_sms, s));
+    CS_TRY(run_conv(10 + 2 * k));
+    CS_TRY(run_conv(11 + 2 * k));
+  }
+  const ConvL& last = pl->conv[17];
+  CS_CUDA(launch_head_fwd(last.out.p, last.P, 64, t->param[80], t->param[81], logits, s));
+  pl->forward_done = training != 0;
+  return 0;
+}
+
+// Backward stage list: 0 = head, then convs / up-convs in reverse execution order.
+//   kind 0: head, 1: conv (idx), 2: up (idx)
+static void stage_decode(int stage, int* kind, int* idx) {
+  if (stage == 0) { *kind = 0; *idx = 0; return; }
+  int s = stage - 1;
+  if (s < 12) {                       // decoder: (dconvL.3, dconvL.0, upconvL) for L = 1..4
+    const int grp = s / 3, w = s % 3; // grp 0 -> L = 1 (k = 3), grp 3 -> L = 4 (k = 0)
+    const int k = 3 - grp;
+    if (w == 0) { *kind = 1; *idx = 11 + 2 * k; }
+    else if (w == 1) { *kind = 1; *idx = 10 + 2 * k; }
+    else { *kind = 2; *idx = k; }
+    return;
+  }
+  *kind = 1;
+  *idx = 9 - (s - 12);
+}
+
+int cs_unet_stage_params(int stage, int* out_indices, int capacity) {
+  if (stage < 0 || stage >= CS_UNET_NUM_BWD_STAGES) return fail("stage %d out of range", stage);
+  int kind, idx, n = 0, tmp[4];
+  stage_decode(stage, &kind, &idx);
+  if (kind == 0) { tmp[0] = 80; tmp[1] = 81; n = 2; }
+  else if (kind == 1) { const int pb = conv_param_base(idx); for (int j = 0; j < 4; ++j) tmp[j] = pb + j; n = 4; }
+  else { tmp[0] = 40 + 2 * idx; tmp[1] = 41 + 2 * idx; n = 2; }
+  for (int j = 0; j < n && j < capacity; ++j) out_indices[j] = tmp[j];
+  return n;
+}
+
+int cs_unet_backward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* dlogits, int stage_begin, int stage_end,
+                     int frozen_encoder_convs, cs_stream_t stream) {
+  if (!pl || !pl->bound) return fail("plan is not bound to a workspace");
+  if (!pl->forward_done) return fail("cs_unet_backward needs a preceding training-mode cs_unet_forward");
+  if (stage_begin < 0 || stage_end > CS_UNET_NUM_BWD_STAGES || stage_begin > stage_end)
+    return fail("bad stage range [%d, %d)", stage_begin, stage_end);
+  if (frozen_encoder_convs < 0 || frozen_encoder_convs > 10) return fail("frozen_encoder_convs must be in [0, 10]");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int B = pl->B;
+  for (int stage = stage_begin; stage < stage_end; ++stage) {
+    int kind, idx;
+    stage_decode(stage, &kind, &idx);
+    if (kind == 0) {
+      if (!dlogits) return fail("dlogits is null");
+      const ConvL& last = pl->conv[17];
+      if (!t->grad[80] || !t->grad[81]) return fail("gradient buffers of final_conv are null");
+      CS_CUDA(launch_head_bwd(last.out.p, dlogits, last.P, 64, t->param[80], last.g_out.p, t->grad[80], t->grad[81], s));
+    } else if (kind == 1) {
+      ConvL& c = pl->conv[idx];
+      if (idx < frozen_encoder_convs) continue;          // nothing below a frozen prefix needs gradients
+      BnBwdArgs a{};
+      a.g = c.g_out.p; a.g_pitch = c.g_out.pitch; a.g_c0 = c.g_out.c0;
+      a.g_pool = c.g_pool; a.y = c.y;
+      a.scale = c.scale; a.shift = c.shift; a.mean = c.mean; a.invstd = c.invstd;
+      a.s1 = c.bst1; a.s2 = c.bst2; a.dy = c.dy;
+      a.grad_gamma = t->grad[c.pgamma]; a.grad_beta = t->grad[c.pbeta]; a.grad_conv_bias = t->grad[c.pb];
+      a.B = B; a.H = c.H; a.W = c.W; a.C = c.cout;
+      CS_CUDA(cudaMemsetAsync(c.bst1, 0, 2 * (size_t)c.cout * sizeof(double), s));
+      CS_CUDA(launch_bn_bwd_reduce(a, s));
+      CS_CUDA(launch_bn_bwd_apply(a, s));
+      if (t->grad[c.pw]) {
+        const size_t e = (size_t)(idx == 0 ? 1 : 9) * c.cout * c.cin;
+        CS_CUDA(cudaMemsetAsync(pl->dwp, 0, e * sizeof(float), s));
+        CS_CUDA(launch_wgrad_gemm(c.wg, c.bn_w, s));
+        if (idx == 0) CS_CUDA(launch_unpack_first(pl->dwp, c.cout, pl->Cin, t->grad[c.pw], s));
+        else CS_CUDA(launch_unpack_pairs(pl->dwp, c.cout, c.cin, 9, kTapWgrad, t->grad[c.pw], s));
+      }
+      if (idx > 0 && idx > frozen_encoder_convs) CS_CUDA(launch_pix_gemm(c.dg, c.bn_d, pl->num_sms, s));
+    } else {
+      UpL& u = pl->up[idx];
+      if (t->grad[u.pb]) CS_CUDA(launch_channel_sum(u.g_out.p, u.g_out.pitch, u.g_out.c0, 4 * u.P, u.cout, t->grad[u.pb], s));
+      if (t->grad[u.pw]) {
+        CS_CUDA(cudaMemsetAsync(pl->dwp, 0, (size_t)4 * u.cin * u.cout * sizeof(float), s));
+        CS_CUDA(launch_wgrad_gemm(u.wg, u.bn_w, s));
+        CS_CUDA(launch_unpack_pairs(pl->dwp, u.cin, u.cout, 4, kTapIdent, t->grad[u.pw], s));
+      }
+      CS_CUDA(launch_pix_gemm(u.dg, u.bn_d, pl->num_sms, s));
+    }
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// SDF / losses / thresholds
+// ---------------------------------------------------------------------------------------------
+size_t cs_sdf_scratch_bytes(int batch, int height, int width) { return sdf_scratch_bytes(batch, height, width); }
+
+int cs_sdf(const float* src, float thr, int ge, int batch, int height, int width, float norm, float* sdf, void* scratch,
+           cs_stream_t stream) {
+  if (!src || !sdf || !scratch) return fail("cs_sdf: null pointer");
+  if (batch < 1 || height < 1 || width < 1) return fail("cs_sdf: empty input");
+  if (!(norm > 0.f)) return fail("cs_sdf: norm must be positive");
+  CS_CUDA(launch_sdf(src, thr, ge, batch, height, width, norm, sdf, scratch, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+size_t cs_loss_scratch_bytes(int rows) { return loss_scratch_bytes(rows); }
+
+static int loss_args(const cs_loss_desc* d, LossArgs* a) {
+  if (!d) return fail("loss descriptor is null");
+  if (d->rows < 1 || d->n < 4 || d->n % 4) return fail("loss: rows >= 1 and n a positive multiple of 4 required");
+  memset(a, 0, sizeof(*a));
+  a->rows = d->rows; a->n = d->n;
+  a->w_elem = d->w_elem; a->alpha = d->alpha; a->gamma = d->gamma; a->elem_sum = d->elem_sum;
+  a->w_dice = d->w_dice; a->smooth = d->smooth;
+  a->w_bgt = d->w_bgt; a->w_bpred = d->w_bpred; a->use_abs = d->use_abs; a->per_row = d->per_row;
+  return 0;
+}
+
+int cs_loss_forward(const cs_loss_desc* d, const float* logits, const float* targets, const float* sdf_gt,
+                    const float* sdf_pred, void* scratch, float* loss_out, cs_stream_t stream) {
+  LossArgs a;
+  CS_TRY(loss_args(d, &a));
+  if (!logits || !targets || !scratch || !loss_out) return fail("cs_loss_forward: null pointer");
+  a.logits = logits; a.targets = targets; a.sdf_gt = sdf_gt; a.sdf_pred = sdf_pred;
+  a.stats = static_cast<double*>(scratch); a.loss_out = loss_out;
+  CS_CUDA(launch_loss_forward(a, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int cs_loss_backward(const cs_loss_desc* d, const float* logits, const float* targets, const float* sdf_gt,
+                     const float* sdf_pred, const void* scratch, const float* grad_out, float* dlogits,
+                     cs_stream_t stream) {
+  LossArgs a;
+  CS_TRY(loss_args(d, &a));
+  if (!logits || !targets || !scratch || !dlogits) return fail("cs_loss_backward: null pointer");
+  a.logits = logits; a.targets = targets; a.sdf_gt = sdf_gt; a.sdf_pred = sdf_pred;
+  a.stats = const_cast<double*>(static_cast<const double*>(scratch)); a.grad_out = grad_out; a.dlogits = dlogits;
+  CS_CUDA(launch_loss_backward(a, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int cs_threshold_stats(const float* logits, const float* targets, int rows, long long n, const float* xs, int K,
+                       double* counts, double* soft, cs_stream_t stream) {
+  if (!logits || !targets || !xs || !counts || !soft) return fail("cs_threshold_stats: null pointer");
+  if (rows < 1 || n < 1) return fail("cs_threshold_stats: empty input");
+  if (K < 1 || K > 32) return fail("cs_threshold_stats: 1 <= K <= 32 thresholds per call");
+  CS_CUDA(launch_threshold_stats(logits, targets, rows, n, xs, K, counts, soft, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int cs_threshold_mask(const float* logits, long long n, float xstar, uint8_t* mask, cs_stream_t stream) {
+  if (!logits || !mask) return fail("cs_threshold_mask: null pointer");
+  if (n < 4 || n % 4) return fail("cs_threshold_mask: n must be a positive multiple of 4");
+  CS_CUDA(launch_threshold_mask(logits, n, xstar, mask, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Single-layer entry points (tests / micro-benchmarks).  scratch = [fprop pack | dgrad pack | fp32 dW pack]
+// ---------------------------------------------------------------------------------------------
+size_t cs_layer_scratch_bytes(int cin, int cout) {
+  const size_t e = (size_t)9 * cin * cout;
+  return 2 * ((e * 2 + 1023) & ~(size_t)1023) + ((e * 4 + 1023) & ~(size_t)1023);
+}
+
+namespace {
+struct LayerScratch {
+  bf16 *wf, *wd;
+  float* dwp;
+};
+LayerScratch carve(void* scratch, int cin, int cout) {
+  const size_t e = (size_t)9 * cin * cout, hb = (e * 2 + 1023) & ~(size_t)1023;
+  uint8_t* b = static_cast<uint8_t*>(scratch);
+  return LayerScratch{reinterpret_cast<bf16*>(b), reinterpret_cast<bf16*>(b + hb), reinterpret_cast<float*>(b + 2 * hb)};
+}
+int check_layer(const void* a, const void* b, const void* scratch, int batch, int h, int w, int cin, int cout) {
+  if (!a || !b || !scratch) return fail("layer op: null pointer");
+  if ((uintptr_t)scratch & 1023) return fail("layer op: scratch must be 1024-byte aligned");
+  if (batch < 1 || h < 1 || w < 1) return fail("layer op: empty input");
+  if (cin % 64 || cout % 64 || cin < 64 || cout < 64) return fail("layer op: channels must be multiples of 64");
+  return 0;
+}
+}  // namespace
+
+int cs_conv3x3_fprop(const void* x, int batch, int height, int width, int cin, const float* w_oihw, int cout, void* y,
+                     double* stat_sum, double* stat_sq, void* scratch, cs_stream_t stream) {
+  CS_TRY(check_layer(x, y, scratch, batch, height, width, cin, cout));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int sms, bn;
+  CS_TRY(device_sm_count(&sms));
+  LayerScratch ls = carve(scratch, cin, cout);
+  CS_CUDA(launch_pack_pairs(w_oihw, cout, cin, 9, ls.wf, kTapFprop, ls.wd, kTapDgrad, s));
+  PixGemmParams p;
+  CS_TRY(build_conv3x3(p, &bn, View{(bf16*)x, cin, 0}, cin, View{(bf16*)y, cout, 0}, cout, ls.wf, batch, height, width));
+  p.stat_sum = stat_sum;
+  p.stat_sq = stat_sq;
+  CS_CUDA(launch_pix_gemm(p, bn, sms, s));
+  return 0;
+}
+
+int cs_conv3x3_dgrad(const void* dy, int batch, int height, int width, int cin, const float* w_oihw, int cout, void* dx,
+                     void* scratch, cs_stream_t stream) {
+  CS_TRY(check_layer(dy, dx, scratch, batch, height, width, cin, cout));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int sms, bn;
+  CS_TRY(device_sm_count(&sms));
+  LayerScratch ls = carve(scratch, cin, cout);
+  CS_CUDA(launch_pack_pairs(w_oihw, cout, cin, 9, ls.wf, kTapFprop, ls.wd, kTapDgrad, s));
+  PixGemmParams p;
+  CS_TRY(build_conv3x3(p, &bn, View{(bf16*)dy, cout, 0}, cout, View{(bf16*)dx, cin, 0}, cin, ls.wd, batch, height, width));
+  CS_CUDA(launch_pix_gemm(p, bn, sms, s));
+  return 0;
+}
+
+int cs_conv3x3_wgrad(const void* x, const void* dy, int batch, int height, int width, int cin, int cout, float* dw_oihw,
+                     void* scratch, cs_stream_t stream) {
+  CS_TRY(check_layer(x, dy, scratch, batch, height, width, cin, cout));
+  if (!dw_oihw) return fail("layer op: null pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int bn;
+  LayerScratch ls = carve(scratch, cin, cout);
+  WgradParams p;
+  CS_TRY(build_conv3x3_wgrad(p, &bn, View{(bf16*)x, cin, 0}, cin, View{(bf16*)dy, cout, 0}, cout, ls.dwp, batch, height, width));
+  CS_CUDA(cudaMemsetAsync(ls.dwp, 0, (size_t)9 * cin * cout * sizeof(float), s));
+  CS_CUDA(launch_wgrad_gemm(p, bn, s));
+  CS_CUDA(launch_unpack_pairs(ls.dwp, cout, cin, 9, kTapWgrad, dw_oihw, s));
+  return 0;
+}
+
+int cs_convT2x2_fprop(const void* x, int batch, int height, int width, int cin, const float* w_iohw, const float* bias,
+                      int cout, void* y, int y_pitch, void* scratch, cs_stream_t stream) {
+  CS_TRY(check_layer(x, y, scratch, batch, height, width, cin, cout));
+  if (y_pitch < cout || y_pitch % 8) return fail("layer op: bad output pitch %d", y_pitch);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int sms, bn;
+  CS_TRY(device_sm_count(&sms));
+  LayerScratch ls = carve(scratch, cin, cout);
+  CS_CUDA(launch_pack_pairs(w_iohw, cin, cout, 4, ls.wd, kTapIdent, ls.wf, kTapIdent, s));
+  PixGemmParams p;
+  CS_TRY(build_convT_fprop(p, &bn, View{(bf16*)x, cin, 0}, cin, View{(bf16*)y, y_pitch, 0}, cout, ls.wf, bias, batch,
+                           height, width));
+  CS_CUDA(launch_pix_gemm(p, bn, sms, s));
+  return 0;
+}
+
+int cs_convT2x2_dgrad(const void* dy, int dy_pitch, int batch, int height, int width, int cin, const float* w_iohw,
+                      int cout, void* dx, void* scratch, cs_stream_t stream) {
+  CS_TRY(check_layer(dy, dx, scratch, batch, height, width, cin, cout));
+  if (dy_pitch < cout || dy_pitch % 8) return fail("layer op: bad gradient pitch %d", dy_pitch);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int sms, bn;
+  CS_TRY(device_sm_count(&sms));
+  LayerScratch ls = carve(scratch, cin, cout);
+  CS_CUDA(launch_pack_pairs(w_iohw, cin, cout, 4, ls.wd, kTapIdent, ls.wf, kTapIdent, s));
+  PixGemmParams p;
+  CS_TRY(build_convT_dgrad(p, &bn, View{(bf16*)dy, dy_pitch, 0}, cout, View{(bf16*)dx, cin, 0}, cin, ls.wd, batch, height,
+                           width));
+  CS_CUDA(launch_pix_gemm(p, bn, sms, s));
+  return 0;
+}
+
+int cs_convT2x2_wgrad(const void* x, const void* dy, int dy_pitch, int batch, int height, int width, int cin, int cout,
+                      float* dw_iohw, void* scratch, cs_stream_t stream) {
+  CS_TRY(check_layer(x, dy, scratch, batch, height, width, cin, cout));
+  if (!dw_iohw) return fail("layer op: null pointer");
+  if (dy_pitch < cout || dy_pitch % 8) return fail("layer op: bad gradient pitch %d", dy_pitch);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int bn;
+  LayerScratch ls = carve(scratch, cin, cout);
+  WgradParams p;
+  CS_TRY(build_convT_wgrad(p, &bn, View{(bf16*)x, cin, 0}, cin, View{(bf16*)dy, dy_pitch, 0}, cout, ls.dwp, batch, height,
+                           width));
+  CS_CUDA(cudaMemsetAsync(ls.dwp, 0, (size_t)4 * cin * cout * sizeof(float), s));
+  CS_CUDA(launch_wgrad_gemm(p, bn, s));
+  CS_CUDA(launch_unpack_pairs(ls.dwp, cin, cout, 4, kTapIdent, dw_iohw, s));
+  return 0;
+}
+
+}  // extern "C"

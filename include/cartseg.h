@@ -6,7 +6,7 @@
  * (src/training/abl_training/losses/lsr_cpp/csrc/lsr_kernel.cu:296-322), sets the conventions kept
  * here: CUDA-only (hard error otherwise, :300-302), work is enqueued on the caller's stream (:220),
  * no host synchronisation.  Each entry point below names the reference code it replaces; the
- * Python host (cartseg/ops.py) binds them with ctypes and exposes them as torch.library ops.
+ * Python host (cart-segmentation-unet_b200/cartseg/_lib.py) binds them with ctypes and exposes them as torch.library ops.
  *
  * Conventions
  *   - every pointer is a DEVICE pointer on the current CUDA device unless stated otherwise;
@@ -30,6 +30,8 @@ typedef void* cs_stream_t; /* cudaStream_t */
 
 const char* cs_last_error(void);
 int cs_version(void);
+/* Number of CUDA kernels this library has launched in this process (bench.py reports it). */
+long long cs_kernel_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * U-Net  (replaces DoubleConv / UNet, src/create_testset.py:40-83; logits = final_conv output,
@@ -53,8 +55,11 @@ typedef struct cs_unet_tensors {
   long long* num_batches_tracked[CS_UNET_NUM_BN];
 } cs_unet_tensors;
 
-/* Host-side: lay out activations / packed weights / gradients for one (batch, H, W). */
-int cs_unet_plan_create(cs_unet_plan** plan, int batch, int in_channels, int height, int width);
+/* Host-side: lay out activations / packed weights / gradients for one (batch, H, W).
+ * inference_only != 0 drops everything the backward pass needs (raw conv outputs, gradient and
+ * weight-gradient buffers, dgrad weight packs): such a plan only accepts training == 0 forwards
+ * (the pseudo-label path, src/data_preprocessing/create_pseudo_labels_gpu.py:201-215). */
+int cs_unet_plan_create(cs_unet_plan** plan, int batch, int in_channels, int height, int width, int inference_only);
 void cs_unet_plan_destroy(cs_unet_plan* plan);
 size_t cs_unet_plan_workspace_bytes(const cs_unet_plan* plan);
 /* Attach a caller-owned device workspace (>= workspace_bytes, 1024-byte aligned) and encode the

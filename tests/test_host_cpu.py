@@ -1,0 +1,173 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol the header declares, the
+host mirror keeps the reference's state-dict layout, thresholds map to exact logit bounds, and the
+data-parallel gradient bucketing / averaging works across two gloo ranks."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "cartseg.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cs_[a-zA-Z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_header_symbol():
+    from cartseg import _lib
+    names = _header_functions()
+    assert len(names) >= 20
+    L = _lib.lib()
+    for n in names:
+        assert hasattr(L, n), f"libcartseg.so does not export {n}"
+    assert sorted(_lib.EXPORTED_SYMBOLS) == names        # the ctypes table covers the header, nothing else
+    assert L.cs_version() >= 1
+
+
+def test_plan_argument_validation_without_gpu():
+    import ctypes as C
+    from cartseg import _lib
+    L = _lib.lib()
+    h = C.c_void_p()
+    assert L.cs_unet_plan_create(C.byref(h), 2, 3, 30, 32, 0) != 0          # H not a multiple of 16
+    assert b"multiples of 16" in L.cs_last_error()
+    assert L.cs_unet_plan_create(C.byref(h), 0, 3, 32, 32, 0) != 0
+    assert L.cs_unet_plan_create(C.byref(h), 2, 3, 224, 224, 0) == 0
+    train_bytes = L.cs_unet_plan_workspace_bytes(h)
+    L.cs_unet_plan_destroy(h)
+    assert L.cs_unet_plan_create(C.byref(h), 2, 3, 224, 224, 1) == 0
+    infer_bytes = L.cs_unet_plan_workspace_bytes(h)
+    L.cs_unet_plan_destroy(h)
+    assert 0 < infer_bytes < train_bytes / 2
+    # 23 backward stages cover the 82 parameters exactly once
+    seen = []
+    buf = (C.c_int * 8)()
+    for s in range(_lib.NUM_BWD_STAGES):
+        n = L.cs_unet_stage_params(s, buf, 8)
+        seen += [buf[i] for i in range(n)]
+    assert sorted(seen) == list(range(82))
+    assert seen[:2] == [80, 81]                                             # the head finishes first
+
+
+def test_module_state_dict_matches_reference_layout():
+    import cartseg
+    from oracle import unet_oracle as O
+    m = cartseg.UNet()
+    spec = O.state_dict_spec()
+    sd = m.state_dict()
+    assert list(sd.keys()) == [k for k, _ in spec]
+    assert all(tuple(sd[k].shape) == s for k, s in spec)
+    flat = m._flat_params()
+    named = {id(p): k for k, p in m.named_parameters()}
+    assert [named[id(p)] for p in flat] == O.param_keys(sd)                 # C-ABI order == state-dict order
+    assert len(m._flat_buffers()) == 54
+    # loading a reference-format checkpoint works with strict=True (create_testset.py:89)
+    m.load_state_dict(O.synth_state_dict(seed=4), strict=True)
+    # smp-style groups used by the training scripts (train_with_focalDice.py:384-391)
+    for p in m.encoder.parameters():
+        p.requires_grad = False
+    assert m._frozen_encoder_convs(m._flat_params()) == 10
+    assert all(p.requires_grad for p in m.decoder.parameters())
+    assert sum(1 for _ in m.segmentation_head.parameters()) == 2
+
+
+def test_no_cpu_fallback():
+    import cartseg
+    m = cartseg.UNet()
+    with pytest.raises(cartseg.CartsegError):
+        m(torch.zeros(1, 3, 32, 32))
+    with pytest.raises(cartseg.CartsegError):
+        cartseg.BCEDiceLoss()(torch.zeros(1, 1, 16, 16), torch.zeros(1, 1, 16, 16))
+    with pytest.raises(cartseg.CartsegError):
+        cartseg.batch_sdf_from_masks(torch.zeros(1, 1, 16, 16))
+    with pytest.raises(cartseg.CartsegError):
+        cartseg.dice_metric(torch.zeros(1, 1, 16, 16), torch.zeros(1, 1, 16, 16))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "cart-segmentation-unet_b200", "cartseg")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            assert "oracle" not in open(os.path.join(pkg, f)).read().replace("the oracle", ""), f
+
+
+@pytest.mark.parametrize("t", [0.05, 0.2, 0.35, 0.5, 0.65, 0.8, 0.95])
+@pytest.mark.parametrize("ge", [False, True])
+def test_logit_bound_is_the_exact_float32_threshold(t, ge):
+    from cartseg import ops
+    xb = ops.logit_bound(t, ge)
+    x = torch.tensor([xb], dtype=torch.float32)
+    below = torch.nextafter(x, torch.tensor([-float("inf")]))
+    tt = torch.tensor(t, dtype=torch.float32)
+    f = (lambda v: torch.sigmoid(v.repeat(16))[0] >= tt) if ge else (lambda v: torch.sigmoid(v.repeat(16))[0] > tt)
+    assert bool(f(x)) and not bool(f(below))
+    # and it reproduces sigmoid-then-compare on a dense sample around the boundary
+    xs = x + torch.linspace(-1e-4, 1e-4, 20001)
+    ref = (torch.sigmoid(xs) >= tt) if ge else (torch.sigmoid(xs) > tt)
+    assert torch.equal(xs >= x, ref)
+
+
+def test_plan_buckets_cover_all_stages():
+    from cartseg.parallel import plan_buckets
+    off = [0, 65, 37000, 110000, 118000, 200000, 500000, 510000, 900000, 5000000, 5000100]
+    for be in (1, 50000, 10 ** 6, 10 ** 9):
+        b = plan_buckets(off, be)
+        assert b[0][0] == 0 and b[-1][1] == len(off) - 1
+        assert all(b[i][1] == b[i + 1][0] for i in range(len(b) - 1))
+        assert all(off[e] - off[s] >= be for s, e in b[:-1])
+
+
+_DP_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.path.join(sys.argv[1], "cart-segmentation-unet_b200"))
+from cartseg.parallel import GradSync, shard_batch
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+sync = GradSync(None, bucket_mb=0.001)
+# a fake "backward": 6 stages, each fills its slice of the flat buffer with rank-dependent values
+stage_off = [0, 10, 700, 705, 2000, 2600, 4000]
+flat = torch.empty(stage_off[-1])
+buckets = sync.stage_buckets(stage_off)
+assert buckets[0][0] == 0 and buckets[-1][1] == 6
+for s0, s1 in buckets:
+    for s in range(s0, s1):
+        flat[stage_off[s]:stage_off[s + 1]] = torch.arange(stage_off[s], stage_off[s + 1]).float() * (rank + 1) + s
+    sync.reduce_async(flat[stage_off[s0]:stage_off[s1]])
+sync.finish()
+expect = torch.empty(stage_off[-1])
+for s in range(6):
+    idx = torch.arange(stage_off[s], stage_off[s + 1]).float()
+    expect[stage_off[s]:stage_off[s + 1]] = sum(idx * (r + 1) + s for r in range(world)) / world
+assert torch.allclose(flat, expect), (flat - expect).abs().max()
+x = torch.arange(8 * 3).reshape(8, 3)
+sh = shard_batch(x, rank, world)
+assert sh.shape[0] == 8 // world and int(sh[0, 0]) == rank * (8 // world) * 3
+# mean of equal-shard means == global mean (SURVEY 8e): the loss-averaging identity the DP path relies on
+g = torch.Generator().manual_seed(0); v = torch.randn(8, 5, generator=g)
+local = shard_batch(v, rank, world).mean().reshape(1)
+dist.all_reduce(local); local /= world
+assert torch.allclose(local, v.mean().reshape(1), atol=1e-6)
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_data_parallel_gradient_average_two_gloo_ranks(tmp_path):
+    script = tmp_path / "dp_worker.py"
+    script.write_text(_DP_WORKER)
+    port = 29500 + os.getpid() % 2000
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, f"rank {r} failed:\n{o}"
+        assert f"rank {r} ok" in o

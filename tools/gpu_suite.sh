@@ -1,0 +1,30 @@
+#!/bin/bash
+# Runs on the GPU box (via gpurun): diagnostics, the -m gpu parity tests file by file (each in its own process so a
+# faulting kernel cannot take the other files down), then smoke + a short bench.  Logs land in gpurun_out/.
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,driver_version,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
+nproc > gpurun_out/host.txt; lscpu | grep -E "Model name|^CPU\(s\)" >> gpurun_out/host.txt
+status=0
+run() {  # name, timeout, command...
+  local name=$1 to=$2; shift 2
+  timeout "$to" "$@" > "gpurun_out/$name.log" 2>&1
+  local rc=$?
+  echo "[$name] exit $rc"
+  tail -n 6 "gpurun_out/$name.log" | sed "s/^/    /"
+  [ $rc -ne 0 ] && status=1
+}
+for part in "$@"; do
+  case $part in
+    diag)   run diag 300 python tools/diag_conv.py ;;
+    sdf)    run test_gpu_sdf 600 python -m pytest tests/test_gpu_sdf.py -m gpu -q --tb=short -s --timeout 300 ;;
+    losses) run test_gpu_losses 600 python -m pytest tests/test_gpu_losses.py -m gpu -q --tb=short -s --timeout 300 ;;
+    layers) run test_gpu_layers 900 python -m pytest tests/test_gpu_layers.py -m gpu -q --tb=short -s --timeout 300 ;;
+    unet)   run test_gpu_unet 1200 python -m pytest tests/test_gpu_unet.py -m gpu -q --tb=short -s --timeout 600 ;;
+    smoke)  run smoke 600 python -c "import __graft_entry__ as g; g.smoke()" ;;
+    bench)  run bench 900 python bench.py --steps 5 --warmup 3 ;;
+    benchref) run bench_ref 600 python bench.py --impl reference --steps 3 --warmup 1 ;;
+    all)    run tests_all 1800 python -m pytest tests -m gpu -q -x --tb=short --timeout 600 ;;
+  esac
+done
+exit $status
