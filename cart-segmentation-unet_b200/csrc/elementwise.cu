@@ -537,4 +537,23 @@ cudaError_t launch_channel_sum(const bf16* g, int pitch, int c0, long long P, in
   return launched();
 }
 
+// ============================================================================ debug read-back
+// NHWC bf16 view (pitch, c0) -> dense fp32 NCHW (tests compare internal tensors stage by stage).
+__global__ void nhwc_to_nchw_f32_kernel(const bf16* __restrict__ src, int pitch, int c0, int B, int H, int W, int C,
+                                        float* __restrict__ dst) {
+  const long long total = (long long)B * C * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    const int h = (int)((i / W) % H);
+    const int c = (int)((i / ((long long)W * H)) % C);
+    const int b = (int)(i / ((long long)W * H * C));
+    dst[i] = __bfloat162float(src[(((long long)b * H + h) * W + w) * pitch + c0 + c]);
+  }
+}
+cudaError_t launch_nhwc_to_nchw_f32(const bf16* src, int pitch, int c0, int B, int H, int W, int C, float* dst,
+                                    cudaStream_t s) {
+  nhwc_to_nchw_f32_kernel<<<grid_for((long long)B * C * H * W, 256), 256, 0, s>>>(src, pitch, c0, B, H, W, C, dst);
+  return launched();
+}
+
 }  // namespace cs

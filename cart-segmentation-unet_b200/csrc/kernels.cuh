@@ -70,6 +70,10 @@ cudaError_t launch_head_bwd(const bf16* act, const float* dlogits, long long P, 
 // grad_b[c] = sum_p g[p][c0 + c]
 cudaError_t launch_channel_sum(const bf16* g, int pitch, int c0, long long P, int C, float* out, cudaStream_t s);
 
+// ---- debug read-back ------------------------------------------------------------------------
+cudaError_t launch_nhwc_to_nchw_f32(const bf16* src, int pitch, int c0, int B, int H, int W, int C, float* dst,
+                                    cudaStream_t s);
+
 // ---- exact EDT / signed distance map --------------------------------------------------------
 // fg(pixel) = ge ? (src >= thr) : (src > thr);  sdf = (+dist to nearest fg | -dist to nearest bg) / norm,
 // all-fg / all-bg images give 0.  scratch: B*H*W*4 bytes + B*8 bytes.

@@ -631,6 +631,41 @@ int cs_unet_backward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* dl
   return 0;
 }
 
+// Debug read-back of an internal NHWC bf16 tensor as dense fp32 NCHW (tests only).
+//   kind 0: conv raw output y   1: conv activation (post BN+ReLU)   2: grad wrt y   3: grad wrt activation
+//        4: pooled activation   5: grad wrt pooled   (index = conv 0..17)
+//        6: conv-transpose output   7: grad wrt it   (index = up 0..3)
+int cs_unet_debug_read(cs_unet_plan* pl, int kind, int index, int dims_out[4], float* dst, cs_stream_t stream) {
+  if (!pl || !pl->bound) return fail("plan is not bound to a workspace");
+  View v;
+  int C, H, W;
+  if (kind >= 0 && kind <= 5) {
+    if (index < 0 || index >= 18) return fail("conv index out of range");
+    const ConvL& c = pl->conv[index];
+    C = c.cout; H = c.H; W = c.W;
+    switch (kind) {
+      case 0: v = View{c.y, c.cout, 0}; break;
+      case 1: v = c.out; break;
+      case 2: v = View{c.dy, c.cout, 0}; break;
+      case 3: v = c.g_out; break;
+      case 4: v = View{c.pooled, c.cout, 0}; H /= 2; W /= 2; break;
+      default: v = View{c.g_pool, c.cout, 0}; H /= 2; W /= 2; break;
+    }
+  } else if (kind == 6 || kind == 7) {
+    if (index < 0 || index >= 4) return fail("up index out of range");
+    const UpL& u = pl->up[index];
+    C = u.cout; H = 2 * u.H; W = 2 * u.W;
+    v = kind == 6 ? u.out : u.g_out;
+  } else {
+    return fail("unknown debug tensor kind %d", kind);
+  }
+  if (dims_out) { dims_out[0] = pl->B; dims_out[1] = C; dims_out[2] = H; dims_out[3] = W; }
+  if (!dst) return 0;
+  if (!v.p) return fail("tensor (kind %d, index %d) does not exist in this plan", kind, index);
+  CS_CUDA(launch_nhwc_to_nchw_f32(v.p, v.pitch, v.c0, pl->B, H, W, C, dst, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // SDF / losses / thresholds
 // ---------------------------------------------------------------------------------------------

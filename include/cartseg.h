@@ -80,6 +80,10 @@ int cs_unet_forward(cs_unet_plan* plan, const cs_unet_tensors* t, const float* x
  * 0 trains everything, 10 freezes the whole encoder (src/train_with_focalDice.py:384-391). */
 int cs_unet_backward(cs_unet_plan* plan, const cs_unet_tensors* t, const float* dlogits, int stage_begin,
                      int stage_end, int frozen_encoder_convs, cs_stream_t stream);
+/* Test hook: copies one internal NHWC bf16 tensor of the plan into `dst` as dense fp32 NCHW (dst == NULL: only
+ * report dims_out = {B, C, H, W}).  kind 0..5 index a conv (0..17): raw output, activation, grad wrt raw output,
+ * grad wrt activation, pooled activation, grad wrt pooled; kind 6/7 index a conv-transpose (0..3): output, its grad. */
+int cs_unet_debug_read(cs_unet_plan* plan, int kind, int index, int dims_out[4], float* dst, cs_stream_t stream);
 /* Which parameter indices (into param[]/grad[]) a backward stage finalises; returns the count. */
 int cs_unet_stage_params(int stage, int* out_indices, int capacity);
 

@@ -103,37 +103,71 @@ def synth_state_dict(seed: int = 0, in_channels: int = 3, out_channels: int = 1,
     return sd
 
 
-def _double_conv(x: Tensor, sd: Dict[str, Tensor], p: str, training: bool) -> Tensor:
+def bf16_ste(t: Tensor) -> Tensor:
+    """Round to bfloat16 (value), identity gradient (straight-through).  Used by the bf16-emulating variant
+    of the model below, which places a rounding wherever the B200 kernels store a bf16 tensor — it separates
+    "bf16 storage noise" from real defects when the fp32 oracle and the GPU path disagree."""
+    return t + (t.to(torch.bfloat16).to(t.dtype) - t).detach()
+
+
+def _double_conv(x: Tensor, sd: Dict[str, Tensor], p: str, training: bool, q=None, tape=None) -> Tensor:
     # src/create_testset.py:43-50 — Conv3x3(pad 1, bias) -> BN(eps 1e-5, momentum .1) -> ReLU, twice
     for c, b in ((0, 1), (3, 4)):
-        x = F.conv2d(x, sd[f"{p}.conv.{c}.weight"], sd[f"{p}.conv.{c}.bias"], padding=1)
+        w = sd[f"{p}.conv.{c}.weight"]
+        x = F.conv2d(x, q(w) if q else w, sd[f"{p}.conv.{c}.bias"], padding=1)
+        if q:
+            # the kernels never add the conv bias before a train-mode BN (it cancels); in eval mode the bias is
+            # folded into the epilogue affine, so only the train-mode pre-BN tensor is rounded
+            x = q(x - sd[f"{p}.conv.{c}.bias"].view(1, -1, 1, 1)) + sd[f"{p}.conv.{c}.bias"].view(1, -1, 1, 1) \
+                if training else x
+        if tape is not None:
+            tape[f"{p}.conv.{c}.y"] = x
+            if x.requires_grad:
+                x.retain_grad()
         x = F.batch_norm(x, sd[f"{p}.conv.{b}.running_mean"], sd[f"{p}.conv.{b}.running_var"],
                          sd[f"{p}.conv.{b}.weight"], sd[f"{p}.conv.{b}.bias"],
                          training=training, momentum=0.1, eps=1e-5)
         if training and f"{p}.conv.{b}.num_batches_tracked" in sd:
             sd[f"{p}.conv.{b}.num_batches_tracked"] += 1
         x = F.relu(x)
+        if q:
+            x = q(x)
+        if tape is not None:
+            tape[f"{p}.conv.{c}.out"] = x
+            if x.requires_grad:
+                x.retain_grad()
     return x
 
 
-def unet_logits(x: Tensor, sd: Dict[str, Tensor], training: bool = False) -> Tensor:
+def unet_logits(x: Tensor, sd: Dict[str, Tensor], training: bool = False, emulate_bf16: bool = False,
+                tape: Dict[str, Tensor] = None) -> Tensor:
     """src/create_testset.py:72-82 — returns the final_conv output (logits), sigmoid dropped.
 
     In training mode the BN running buffers inside ``sd`` are updated in place, as
-    ``nn.BatchNorm2d`` does.
+    ``nn.BatchNorm2d`` does.  ``emulate_bf16`` rounds the input, the conv / conv-transpose weights and
+    every stored activation to bfloat16 (straight-through gradients): the storage precision of the GPU
+    path, everything else fp32.  ``tape`` (a dict) receives the per-layer tensors for stage-by-stage checks.
     """
+    q = bf16_ste if emulate_bf16 else None
     skips = []
-    h = x
+    h = q(x) if q else x
     for i, (name, _, _) in enumerate(ENCODER):
         if i:
             h = F.max_pool2d(h, 2, 2)
-        h = _double_conv(h, sd, name, training)
+        h = _double_conv(h, sd, name, training, q, tape)
         skips.append(h)
     skips.pop()                                   # x5 is the bottleneck, not a skip
     for up, dc, _, _ in DECODER:
-        h = F.conv_transpose2d(h, sd[f"{up}.weight"], sd[f"{up}.bias"], stride=2)
+        w = sd[f"{up}.weight"]
+        h = F.conv_transpose2d(h, q(w) if q else w, sd[f"{up}.bias"], stride=2)
+        if q:
+            h = q(h)
+        if tape is not None:
+            tape[f"{up}.out"] = h
+            if h.requires_grad:
+                h.retain_grad()
         h = torch.cat([h, skips.pop()], dim=1)    # upsampled first, then the skip (:78-81)
-        h = _double_conv(h, sd, dc, training)
+        h = _double_conv(h, sd, dc, training, q, tape)
     return F.conv2d(h, sd["final_conv.weight"], sd["final_conv.bias"])
 
 

@@ -22,6 +22,8 @@ CONV_SHAPES = [
     (3, 16, 8, 128, 64),
     (1, 48, 40, 64, 64),
     (2, 14, 14, 512, 512),
+    (8, 112, 112, 64, 64),        # 1568 tiles: several per persistent CTA, split-K wgrad
+    (4, 56, 56, 128, 256),
 ]
 
 
@@ -68,7 +70,8 @@ def test_conv3x3_dgrad(B, H, W, Cin, Cout):
     ref = F.conv_transpose2d(dy, w, padding=1)            # gradient of conv2d(pad=1) w.r.t. its input
     dx = torch.full((B, H, W, Cin), float("nan"), dtype=torch.bfloat16, device="cuda")
     buf, scratch = layer_scratch(Cin, Cout)
-    check(L.cs_conv3x3_dgrad(to_nhwc_bf16(dy).data_ptr(), B, H, W, Cin, w.cuda().data_ptr(), Cout, dx.data_ptr(),
+    dyg, wg = to_nhwc_bf16(dy), w.cuda()                  # kept alive until the synchronize below
+    check(L.cs_conv3x3_dgrad(dyg.data_ptr(), B, H, W, Cin, wg.data_ptr(), Cout, dx.data_ptr(),
                              scratch, stream()), "cs_conv3x3_dgrad")
     torch.cuda.synchronize()
     got = from_nhwc(dx)
@@ -109,7 +112,8 @@ def test_convT2x2_fprop_into_concat_slot(B, H, W, Cin, Cout):
     pitch = 2 * Cout                                        # written into the first half of a concat buffer
     y = torch.full((B, 2 * H, 2 * W, pitch), 7.0, dtype=torch.bfloat16, device="cuda")
     buf, scratch = layer_scratch(Cin, Cout)
-    check(L.cs_convT2x2_fprop(to_nhwc_bf16(x).data_ptr(), B, H, W, Cin, w.cuda().data_ptr(), bias.cuda().data_ptr(),
+    xg, wg, bg = to_nhwc_bf16(x), w.cuda(), bias.cuda()
+    check(L.cs_convT2x2_fprop(xg.data_ptr(), B, H, W, Cin, wg.data_ptr(), bg.data_ptr(),
                               Cout, y.data_ptr(), pitch, scratch, stream()), "cs_convT2x2_fprop")
     torch.cuda.synchronize()
     got = from_nhwc(y[..., :Cout])
@@ -132,10 +136,11 @@ def test_convT2x2_dgrad_and_wgrad(B, H, W, Cin, Cout):
     dyg[..., Cout:] = 3.0                                   # must be ignored
     dx = torch.full((B, H, W, Cin), float("nan"), dtype=torch.bfloat16, device="cuda")
     buf, scratch = layer_scratch(Cin, Cout)
-    check(L.cs_convT2x2_dgrad(dyg.data_ptr(), pitch, B, H, W, Cin, w.cuda().data_ptr(), Cout, dx.data_ptr(), scratch,
+    wg, xg = w.cuda(), to_nhwc_bf16(x)
+    check(L.cs_convT2x2_dgrad(dyg.data_ptr(), pitch, B, H, W, Cin, wg.data_ptr(), Cout, dx.data_ptr(), scratch,
                               stream()), "cs_convT2x2_dgrad")
     dw = torch.full((Cin, Cout, 2, 2), float("nan"), dtype=torch.float32, device="cuda")
-    check(L.cs_convT2x2_wgrad(to_nhwc_bf16(x).data_ptr(), dyg.data_ptr(), pitch, B, H, W, Cin, Cout, dw.data_ptr(),
+    check(L.cs_convT2x2_wgrad(xg.data_ptr(), dyg.data_ptr(), pitch, B, H, W, Cin, Cout, dw.data_ptr(),
                               scratch, stream()), "cs_convT2x2_wgrad")
     torch.cuda.synchronize()
     assert rel_l2(from_nhwc(dx), xr.grad) < 1e-2

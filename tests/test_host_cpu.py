@@ -171,3 +171,26 @@ def test_data_parallel_gradient_average_two_gloo_ranks(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, f"rank {r} failed:\n{o}"
         assert f"rank {r} ok" in o
+
+
+def test_bf16_storage_alone_moves_relu_network_gradients_by_tens_of_percent():
+    """Why tests/test_gpu_unet_stages.py checks gradients stage by stage: with the CPU oracle ALONE, rounding the
+    stored activations / weights to bfloat16 (fp32 arithmetic otherwise) leaves the loss unchanged to ~1e-4 but moves
+    per-tensor gradients by >10 % (ReLU masks flip for pre-activations within the rounding noise of zero)."""
+    from oracle import unet_oracle as O
+    import cartseg
+    x, t = O.synth_batch(2, 64, 64, seed=5)
+    torch.manual_seed(0)
+    sd0 = {k: v.detach().clone() for k, v in cartseg.UNet().state_dict().items()}
+    res = []
+    for emu in (False, True):
+        sd = {k: v.clone() for k, v in sd0.items()}
+        keys = O.param_keys(sd)
+        for k in keys:
+            sd[k].requires_grad_(True)
+        loss = O.focal_dice_loss(O.unet_logits(x, sd, training=True, emulate_bf16=emu), t, 0.5, 2.0, 1.0, 0.7)
+        loss.backward()
+        res.append((loss.item(), sd["conv3.conv.0.weight"].grad.clone()))
+    (l32, g32), (l16, g16) = res
+    assert abs(l32 - l16) / l32 < 1e-3
+    assert float((g16 - g32).norm() / g32.norm()) > 0.1

@@ -23,7 +23,8 @@ def conv_fprop(x, w, stats=False):
     Cout = w.shape[0]
     y = torch.full((B, H, W, Cout), float("nan"), dtype=torch.bfloat16, device="cuda")
     buf, scratch = layer_scratch(Cin, Cout)
-    _lib.check(L.cs_conv3x3_fprop(to_nhwc_bf16(x).data_ptr(), B, H, W, Cin, w.cuda().data_ptr(), Cout, y.data_ptr(),
+    xg, wg = to_nhwc_bf16(x), w.cuda()                  # keep alive until the synchronize
+    _lib.check(L.cs_conv3x3_fprop(xg.data_ptr(), B, H, W, Cin, wg.data_ptr(), Cout, y.data_ptr(),
                                   None, None, scratch, stream()), "fprop")
     torch.cuda.synchronize()
     return from_nhwc(y)

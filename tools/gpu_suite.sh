@@ -20,6 +20,7 @@ for part in "$@"; do
     sdf)    run test_gpu_sdf 600 python -m pytest tests/test_gpu_sdf.py -m gpu -q --tb=short -s --timeout 300 ;;
     losses) run test_gpu_losses 600 python -m pytest tests/test_gpu_losses.py -m gpu -q --tb=short -s --timeout 300 ;;
     layers) run test_gpu_layers 900 python -m pytest tests/test_gpu_layers.py -m gpu -q --tb=short -s --timeout 300 ;;
+    stages) run test_gpu_unet_stages 1200 python -m pytest tests/test_gpu_unet_stages.py -m gpu -q --tb=short -s --timeout 600 ;;
     unet)   run test_gpu_unet 1200 python -m pytest tests/test_gpu_unet.py -m gpu -q --tb=short -s --timeout 600 ;;
     smoke)  run smoke 600 python -c "import __graft_entry__ as g; g.smoke()" ;;
     bench)  run bench 900 python bench.py --steps 5 --warmup 3 ;;
