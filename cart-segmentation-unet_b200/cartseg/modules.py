@@ -113,6 +113,7 @@ class UNet(nn.Module):
         self.dconv1 = DoubleConv(128, 64)
         self.final_conv = nn.Conv2d(64, out_channels, 1)
         self._dp_handle = 0
+        self._weights_epoch = 0          # advanced by every training-mode forward (see ops._ensure_packed)
 
     # ---- groups the training scripts address (smp.Unet naming) --------------------------------
     @property
@@ -178,11 +179,15 @@ class UNet(nn.Module):
         buffers = self._flat_buffers()
         need_grad = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in params)
         plan = ops.get_plan(B, C, H, W, x.device, inference_only=not self.training)
+        if self.training:
+            self._weights_epoch += 1
         if need_grad:
             frozen = self._frozen_encoder_convs(params)
-            logits = ops.UNetFunction.apply(x, plan.id, True, frozen, self._dp_handle, len(params), *params, *buffers)
+            logits = ops.UNetFunction.apply(x, plan.id, True, frozen, self._dp_handle, self._weights_epoch,
+                                            len(params), *params, *buffers)
         else:
-            logits = torch.ops.cartseg.unet_forward(x, [p.detach() for p in params], buffers, self.training, plan.id)
+            logits = torch.ops.cartseg.unet_forward(x, [p.detach() for p in params], buffers, self.training, plan.id,
+                                                    self._weights_epoch)
         return torch.sigmoid(logits) if self.final_sigmoid else logits
 
 

@@ -131,15 +131,20 @@ def _fill_tensors(params: List[Tensor], grads: Optional[List[Optional[Tensor]]],
     return t
 
 
-def _ensure_packed(plan: Plan, params: List[Tensor], t: UnetTensors) -> None:
-    key = tuple((params[i].data_ptr(), params[i]._version) for i in _WEIGHT_SLOTS)
+def _ensure_packed(plan: Plan, params: List[Tensor], t: UnetTensors, pack_token: int) -> None:
+    """Re-pack the bf16 weight copies when the fp32 parameters may have changed.  Tensor version counters are not
+    enough (fused optimizers update parameters without bumping them), so the module also passes a token that
+    it advances on every training-mode forward: training steps always re-pack, and an eval-mode plan re-packs
+    after any training step that happened since its last use."""
+    key = (pack_token,) + tuple((params[i].data_ptr(), params[i]._version) for i in _WEIGHT_SLOTS)
     if key != plan.pack_key:
         check(_lib.lib().cs_unet_pack_weights(plan.handle, C.byref(t), _lib.current_stream()), "cs_unet_pack_weights")
         plan.pack_key = key
 
 
 @torch.library.custom_op("cartseg::unet_forward", mutates_args=("buffers",), device_types="cuda")
-def unet_forward(x: Tensor, params: List[Tensor], buffers: List[Tensor], training: bool, plan_id: int) -> Tensor:
+def unet_forward(x: Tensor, params: List[Tensor], buffers: List[Tensor], training: bool, plan_id: int,
+                 pack_token: int) -> Tensor:
     plan = _plan(plan_id)
     B, Cin, H, W = plan.shape
     if tuple(x.shape) != (B, Cin, H, W) or x.dtype != torch.float32 or not x.is_contiguous():
@@ -147,7 +152,7 @@ def unet_forward(x: Tensor, params: List[Tensor], buffers: List[Tensor], trainin
     logits = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
     t = _fill_tensors(params, None, buffers)
     with torch.cuda.device(x.device):
-        _ensure_packed(plan, params, t)
+        _ensure_packed(plan, params, t, pack_token)
         check(_lib.lib().cs_unet_forward(plan.handle, C.byref(t), ptr(x), int(training), ptr(logits),
                                          _lib.current_stream()), "cs_unet_forward")
     if training:
@@ -156,7 +161,7 @@ def unet_forward(x: Tensor, params: List[Tensor], buffers: List[Tensor], trainin
 
 
 @unet_forward.register_fake
-def _(x, params, buffers, training, plan_id):
+def _(x, params, buffers, training, plan_id, pack_token):
     return x.new_empty((x.shape[0], 1, x.shape[2], x.shape[3]), dtype=torch.float32)
 
 
@@ -249,10 +254,11 @@ class UNetFunction(torch.autograd.Function):
     """Autograd glue: forward / backward are the two cartseg:: ops above."""
 
     @staticmethod
-    def forward(ctx, x, plan_id, training, frozen, dp_handle, n_params, *tensors):
+    def forward(ctx, x, plan_id, training, frozen, dp_handle, pack_token, n_params, *tensors):
         params = list(tensors[:n_params])
         buffers = list(tensors[n_params:])
-        logits = torch.ops.cartseg.unet_forward(x, [p.detach() for p in params], buffers, training, plan_id)
+        logits = torch.ops.cartseg.unet_forward(x, [p.detach() for p in params], buffers, training, plan_id,
+                                                pack_token)
         ctx.plan_id = plan_id
         ctx.generation = _plan(plan_id).generation
         ctx.training = training
@@ -272,11 +278,11 @@ class UNetFunction(torch.autograd.Function):
         flat = torch.ops.cartseg.unet_backward(dlogits, params, ctx.plan_id, ctx.generation, ctx.frozen, ctx.dp_handle)
         order, offs, _ = grad_layout(params)
         out: List[Optional[Tensor]] = [None] * ctx.n_params
-        need = ctx.needs_input_grad[6:6 + ctx.n_params]
+        need = ctx.needs_input_grad[7:7 + ctx.n_params]
         for i, o in zip(order, offs):
             if need[i]:
                 out[i] = flat[o:o + params[i].numel()].view(params[i].shape)
-        return (None, None, None, None, None, None, *out, *([None] * ctx.n_buffers))
+        return (None, None, None, None, None, None, None, *out, *([None] * ctx.n_buffers))
 
 
 # =============================================================================================

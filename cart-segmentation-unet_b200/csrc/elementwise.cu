@@ -276,15 +276,21 @@ cudaError_t launch_maxpool(const bf16* in, int in_pitch, int in_c0, int B, int H
 // ============================================================================ BN + ReLU (+ pool/skip) backward
 // g_total(pixel) = g[pixel] (+ g_pool[window] if the pixel is the first maximum of its 2x2 window).
 // mask = (y*scale + shift > 0), evaluated on the bf16-rounded activation exactly as the forward stored it.
+//
+// Every thread owns ONE group of 8 channels for the whole kernel (its BN coefficients live in registers) and walks
+// over pixels (or 2x2 windows) with 16-byte loads.  Two passes over (g, y): pass 1 reduces sum(gm) and sum(gm*xhat)
+// per channel — per-block partials, combined in a fixed order, so the backward pass is run-to-run deterministic —
+// pass 2 writes dy.
 struct BnCoef { float sc[8], sh[8], mu[8], is[8]; };
+CS_DEVINL void load8(const float* p, float* d) {
+  *reinterpret_cast<float4*>(d) = __ldg(reinterpret_cast<const float4*>(p));
+  *reinterpret_cast<float4*>(d + 4) = __ldg(reinterpret_cast<const float4*>(p + 4));
+}
 CS_DEVINL void load_coef(const BnBwdArgs& a, int g, BnCoef& k) {
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    *reinterpret_cast<float4*>(k.sc + 4 * h) = __ldg(reinterpret_cast<const float4*>(a.scale + g * 8 + 4 * h));
-    *reinterpret_cast<float4*>(k.sh + 4 * h) = __ldg(reinterpret_cast<const float4*>(a.shift + g * 8 + 4 * h));
-    *reinterpret_cast<float4*>(k.mu + 4 * h) = __ldg(reinterpret_cast<const float4*>(a.mean + g * 8 + 4 * h));
-    *reinterpret_cast<float4*>(k.is + 4 * h) = __ldg(reinterpret_cast<const float4*>(a.invstd + g * 8 + 4 * h));
-  }
+  load8(a.scale + g * 8, k.sc);
+  load8(a.shift + g * 8, k.sh);
+  load8(a.mean + g * 8, k.mu);
+  load8(a.invstd + g * 8, k.is);
 }
 // Computes, for one pixel (no pool) or one 2x2 window (pool), the masked gradient gm[d][8] and xhat[d][8].
 template <bool POOL>
@@ -302,20 +308,22 @@ CS_DEVINL void masked_grad(const BnBwdArgs& a, const BnCoef& k, int g, long long
   } else {
     pix[0] = unit;
   }
+  Vec8 yv8[ND], gv8[ND];
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {                         // issue every load before the first use
+    yv8[d] = ld8(a.y + pix[d] * a.C + g * 8);
+    gv8[d] = ld8(a.g + pix[d] * a.g_pitch + a.g_c0 + g * 8);
+  }
 #pragma unroll
   for (int d = 0; d < ND; ++d) {
-    float yv[8], gv[8];
-    unpack8(ld8(a.y + pix[d] * a.C + g * 8), yv);
-    unpack8(ld8(a.g + pix[d] * a.g_pitch + a.g_c0 + g * 8), gv);
-    float t[8];
+    float yv[8], t[8];
+    unpack8(yv8[d], yv);
+    unpack8(gv8[d], gm[d]);
 #pragma unroll
     for (int j = 0; j < 8; ++j) t[j] = fmaxf(fmaf(yv[j], k.sc[j], k.sh[j]), 0.f);
     unpack8(pack8(t), act[d]);                          // bf16-rounded, as stored by the forward
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      gm[d][j] = gv[j];
-      xh[d][j] = (yv[j] - k.mu[j]) * k.is[j];
-    }
+    for (int j = 0; j < 8; ++j) xh[d][j] = (yv[j] - k.mu[j]) * k.is[j];
   }
   if (POOL) {
     float gp[8];
@@ -339,81 +347,92 @@ CS_DEVINL void masked_grad(const BnBwdArgs& a, const BnCoef& k, int g, long long
       if (!(act[d][j] > 0.f)) gm[d][j] = 0.f;
 }
 
+static constexpr int kBnBwdThreads = 256;
+static constexpr int kBnBwdMaxBlocks = 148 * 4;          // partials: [blocks][2*C] floats
+
+size_t bn_bwd_scratch_bytes(int maxC) { return (size_t)kBnBwdMaxBlocks * 2 * maxC * sizeof(float); }
+
+static int bn_bwd_grid(const BnBwdArgs& a) {
+  const int rpb = kBnBwdThreads / (a.C / 8);
+  const long long units = a.g_pool ? (long long)a.B * (a.H / 2) * (a.W / 2) : (long long)a.B * a.H * a.W;
+  return grid_for(units, rpb * 2, kBnBwdMaxBlocks);
+}
+
 template <bool POOL>
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BnBwdArgs a) {
+__global__ void __launch_bounds__(kBnBwdThreads, POOL ? 1 : 3) bn_bwd_reduce_kernel(BnBwdArgs a) {
   constexpr int ND = POOL ? 4 : 1;
-  extern __shared__ float sacc[];                       // [2][C]
+  __shared__ float sm[16 * kBnBwdThreads];               // [rows per block][2*C]  (rpb * 2C == 16 * threads)
   const int cg = a.C >> 3;
-  for (int i = threadIdx.x; i < 2 * a.C; i += blockDim.x) sacc[i] = 0.f;
-  __syncthreads();
-  const int g = threadIdx.x % cg;
-  const int ri = threadIdx.x / cg;
-  const int rpb = blockDim.x / cg;
+  const int g = threadIdx.x % cg, ri = threadIdx.x / cg, rpb = kBnBwdThreads / cg;
   const long long units = POOL ? (long long)a.B * (a.H >> 1) * (a.W >> 1) : (long long)a.B * a.H * a.W;
   BnCoef k;
   load_coef(a, g, k);
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
-  if (ri < rpb) {
-    for (long long u = (long long)blockIdx.x * rpb + ri; u < units; u += (long long)gridDim.x * rpb) {
-      float gm[ND][8], xh[ND][8];
-      long long pix[ND];
-      masked_grad<POOL>(a, k, g, u, gm, xh, pix);
+#pragma unroll(POOL ? 1 : 2)
+  for (long long u = (long long)blockIdx.x * rpb + ri; u < units; u += (long long)gridDim.x * rpb) {
+    float gm[ND][8], xh[ND][8];
+    long long pix[ND];
+    masked_grad<POOL>(a, k, g, u, gm, xh, pix);
 #pragma unroll
-      for (int d = 0; d < ND; ++d)
+    for (int d = 0; d < ND; ++d)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { s1[j] += gm[d][j]; s2[j] += gm[d][j] * xh[d][j]; }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sacc[g * 8 + j], s1[j]);
-      atomicAdd(&sacc[a.C + g * 8 + j], s2[j]);
-    }
+      for (int j = 0; j < 8; ++j) { s1[j] += gm[d][j]; s2[j] = fmaf(gm[d][j], xh[d][j], s2[j]); }
   }
+  float* row = sm + (size_t)ri * 2 * a.C;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { row[g * 8 + j] = s1[j]; row[a.C + g * 8 + j] = s2[j]; }
   __syncthreads();
-  for (int i = threadIdx.x; i < a.C; i += blockDim.x) {
-    atomicAdd(&a.s1[i], (double)sacc[i]);
-    atomicAdd(&a.s2[i], (double)sacc[a.C + i]);
+  for (int c = threadIdx.x; c < 2 * a.C; c += kBnBwdThreads) {   // fixed-order combine over the block's rows
+    float t = 0.f;
+    for (int r = 0; r < rpb; ++r) t += sm[(size_t)r * 2 * a.C + c];
+    a.partial[(size_t)blockIdx.x * 2 * a.C + c] = t;
   }
 }
+
+// s1/s2 totals (fixed order over blocks, fp64) -> per-channel means c1, c2 and the BN parameter gradients.
+__global__ void bn_bwd_finalize_kernel(BnBwdArgs a, int blocks) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.C) return;
+  double t1 = 0.0, t2 = 0.0;
+  for (int b = 0; b < blocks; ++b) {
+    t1 += (double)a.partial[(size_t)b * 2 * a.C + c];
+    t2 += (double)a.partial[(size_t)b * 2 * a.C + a.C + c];
+  }
+  const double inv_n = 1.0 / ((double)a.B * a.H * a.W);
+  a.c1[c] = (float)(t1 * inv_n);
+  a.c2[c] = (float)(t2 * inv_n);
+  if (a.grad_gamma) a.grad_gamma[c] = (float)t2;
+  if (a.grad_beta) a.grad_beta[c] = (float)t1;
+  if (a.grad_conv_bias) a.grad_conv_bias[c] = 0.f;      // exactly zero: BN removes the bias again
+}
+
 cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t s) {
   const int cg = a.C / 8;
-  if (cg > 256) return cudaErrorInvalidValue;
-  const int rpb = 256 / cg;
-  const long long units = a.g_pool ? (long long)a.B * (a.H / 2) * (a.W / 2) : (long long)a.B * a.H * a.W;
-  const int grid = grid_for(units, rpb * 4, 148 * 4);
-  const size_t smem = 2 * a.C * sizeof(float);
-  if (a.g_pool) bn_bwd_reduce_kernel<true><<<grid, 256, smem, s>>>(a);
-  else bn_bwd_reduce_kernel<false><<<grid, 256, smem, s>>>(a);
+  if (cg > kBnBwdThreads || kBnBwdThreads % cg) return cudaErrorInvalidValue;
+  const int grid = bn_bwd_grid(a);
+  if (a.g_pool) bn_bwd_reduce_kernel<true><<<grid, kBnBwdThreads, 0, s>>>(a);
+  else bn_bwd_reduce_kernel<false><<<grid, kBnBwdThreads, 0, s>>>(a);
+  cudaError_t e = launched();
+  if (e != cudaSuccess) return e;
+  bn_bwd_finalize_kernel<<<(a.C + 127) / 128, 128, 0, s>>>(a, grid);
   return launched();
 }
 
 template <bool POOL>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwdArgs a) {
+__global__ void __launch_bounds__(kBnBwdThreads, POOL ? 1 : 3) bn_bwd_apply_kernel(BnBwdArgs a) {
   constexpr int ND = POOL ? 4 : 1;
   const int cg = a.C >> 3;
+  const int g = threadIdx.x % cg, ri = threadIdx.x / cg, rpb = kBnBwdThreads / cg;
   const long long units = POOL ? (long long)a.B * (a.H >> 1) * (a.W >> 1) : (long long)a.B * a.H * a.W;
-  const double inv_n = 1.0 / ((double)a.B * a.H * a.W);
-  if (blockIdx.x == 0) {                                 // parameter gradients of the BN affine
-    for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
-      if (a.grad_gamma) a.grad_gamma[c] = (float)a.s2[c];
-      if (a.grad_beta) a.grad_beta[c] = (float)a.s1[c];
-      if (a.grad_conv_bias) a.grad_conv_bias[c] = 0.f;   // exactly zero: BN removes the bias again
-    }
-  }
-  const long long total = units * cg;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % cg);
-    const long long u = i / cg;
-    BnCoef k;
-    load_coef(a, g, k);
-    float c1[8], c2[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      c1[j] = (float)(a.s1[g * 8 + j] * inv_n);
-      c2[j] = (float)(a.s2[g * 8 + j] * inv_n);
-    }
+  BnCoef k;
+  load_coef(a, g, k);
+  float c1[8], c2[8];
+  load8(a.c1 + g * 8, c1);
+  load8(a.c2 + g * 8, c2);
+#pragma unroll(POOL ? 1 : 2)
+  for (long long u = (long long)blockIdx.x * rpb + ri; u < units; u += (long long)gridDim.x * rpb) {
     float gm[ND][8], xh[ND][8];
     long long pix[ND];
     masked_grad<POOL>(a, k, g, u, gm, xh, pix);
@@ -428,9 +447,10 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BnBwdArgs a) {
 }
 cudaError_t launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t s) {
   const long long units = a.g_pool ? (long long)a.B * (a.H / 2) * (a.W / 2) : (long long)a.B * a.H * a.W;
-  const int grid = grid_for(units * (a.C / 8), 256);
-  if (a.g_pool) bn_bwd_apply_kernel<true><<<grid, 256, 0, s>>>(a);
-  else bn_bwd_apply_kernel<false><<<grid, 256, 0, s>>>(a);
+  const int rpb = kBnBwdThreads / (a.C / 8);
+  const int grid = grid_for(units, rpb * 2, 148 * 8);
+  if (a.g_pool) bn_bwd_apply_kernel<true><<<grid, kBnBwdThreads, 0, s>>>(a);
+  else bn_bwd_apply_kernel<false><<<grid, kBnBwdThreads, 0, s>>>(a);
   return launched();
 }
 

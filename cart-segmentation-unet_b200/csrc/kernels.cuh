@@ -51,13 +51,15 @@ struct BnBwdArgs {
   const bf16* g_pool;                      // optional: gradient w.r.t. the 2x2-pooled activation (pitch C)
   const bf16* y;                           // raw conv output (pitch C)
   const float* scale; const float* shift; const float* mean; const float* invstd;
-  double* s1; double* s2;                  // per-channel sum(g*mask), sum(g*mask*xhat)
+  float* partial;                          // [blocks][2*C] per-block partial sums (bn_bwd_scratch_bytes)
+  float* c1; float* c2;                    // per-channel mean(g*mask), mean(g*mask*xhat)
   bf16* dy;                                // gradient w.r.t. the raw conv output (pitch C)
   float* grad_gamma; float* grad_beta; float* grad_conv_bias;
   int B, H, W, C;
 };
-cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t s);
-cudaError_t launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t s);   // also writes grad_gamma/beta/bias
+size_t bn_bwd_scratch_bytes(int maxC);
+cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t s);  // + finalize: c1/c2, grad_gamma/beta/bias
+cudaError_t launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t s);
 
 // ---- 1x1 head ------------------------------------------------------------------------------
 cudaError_t launch_head_fwd(const bf16* act, long long P, int C, const float* w, const float* b, float* logits,

@@ -242,7 +242,8 @@ struct ConvL {
   View in, out, g_out, g_in;         // input act, post-ReLU act, grad wrt out, grad wrt in (p == null: none)
   bf16 *y, *dy, *pooled, *g_pool;
   bf16 *wf, *wd;
-  double *st_sum, *st_sq, *bst1, *bst2;
+  double *st_sum, *st_sq;
+  float *bc1, *bc2;
   float *scale, *shift, *mean, *invstd;
   PixGemmParams fp_train, fp_eval, dg;
   WgradParams wg;
@@ -269,6 +270,7 @@ struct cs_unet_plan {
   UpL up[4];
   bf16* col;                         // im2col of the input image [P1][64]
   float* dwp;                        // packed weight-gradient accumulator, shared by all layers
+  float* bn_partial;                 // per-block partial sums of the BN backward reduction
   uint8_t* stats_begin;
   size_t stats_bytes;
 };
@@ -389,6 +391,7 @@ void layout(cs_unet_plan* pl, uint8_t* base) {
     if (e > dwp_elems) dwp_elems = e;
   }
   pl->dwp = train ? a.take<float>(dwp_elems) : nullptr;
+  pl->bn_partial = train ? reinterpret_cast<float*>(a.take<uint8_t>(bn_bwd_scratch_bytes(1024))) : nullptr;
   // statistics (zeroed once per forward): forward sums and backward sums of every BN
   a.off = (a.off + 1023) & ~(size_t)1023;
   pl->stats_begin = base + a.off;
@@ -397,8 +400,8 @@ void layout(cs_unet_plan* pl, uint8_t* base) {
     ConvL& c = pl->conv[i];
     c.st_sum = a.take<double>(2 * (size_t)c.cout);
     c.st_sq = c.st_sum + c.cout;
-    c.bst1 = a.take<double>(2 * (size_t)c.cout);      // re-zeroed by every backward stage
-    c.bst2 = c.bst1 + c.cout;
+    c.bc1 = a.take<float>(2 * (size_t)c.cout);
+    c.bc2 = c.bc1 + c.cout;
   }
   pl->stats_bytes = a.off - s0;
   pl->ws_bytes = (a.off + 1023) & ~(size_t)1023;
@@ -603,10 +606,9 @@ int cs_unet_backward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* dl
       a.g = c.g_out.p; a.g_pitch = c.g_out.pitch; a.g_c0 = c.g_out.c0;
       a.g_pool = c.g_pool; a.y = c.y;
       a.scale = c.scale; a.shift = c.shift; a.mean = c.mean; a.invstd = c.invstd;
-      a.s1 = c.bst1; a.s2 = c.bst2; a.dy = c.dy;
+      a.partial = pl->bn_partial; a.c1 = c.bc1; a.c2 = c.bc2; a.dy = c.dy;
       a.grad_gamma = t->grad[c.pgamma]; a.grad_beta = t->grad[c.pbeta]; a.grad_conv_bias = t->grad[c.pb];
       a.B = B; a.H = c.H; a.W = c.W; a.C = c.cout;
-      CS_CUDA(cudaMemsetAsync(c.bst1, 0, 2 * (size_t)c.cout * sizeof(double), s));
       CS_CUDA(launch_bn_bwd_reduce(a, s));
       CS_CUDA(launch_bn_bwd_apply(a, s));
       if (t->grad[c.pw]) {

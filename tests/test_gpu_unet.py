@@ -182,7 +182,7 @@ def test_frozen_encoder_and_param_groups():
         if id(p) in enc:
             assert p.grad is None
         else:
-            assert rel_l2(p.grad, fp[k].grad) < 5e-3, k
+            assert rel_l2(p.grad, fp[k].grad) < 1e-4, k
     # half-frozen: conv1..conv3 frozen, gradients of everything above unchanged
     half = _model(sd).train()
     for mod in (half.conv1, half.conv2, half.conv3):
@@ -193,7 +193,7 @@ def test_frozen_encoder_and_param_groups():
         if k.startswith(("conv1.", "conv2.", "conv3.")):
             assert p.grad is None
         else:
-            assert rel_l2(p.grad, fp[k].grad) < 5e-3, k
+            assert rel_l2(p.grad, fp[k].grad) < 1e-4, k
 
 
 def test_weight_tied_multi_step_drift():
@@ -232,6 +232,36 @@ def test_weight_tied_multi_step_drift():
     err, cos = _global_grad_agreement(upd_gpu, upd_ref)
     print(f"accumulated update after 4 steps: rel-L2 {err:.3f}, cosine {cos:.4f}")
     assert cos > 0.9
+
+
+def test_fused_optimizer_updates_reach_the_kernels():
+    """torch's fused AdamW updates parameters WITHOUT bumping their version counters: the bf16 weight packs must
+    still follow (training forwards always re-pack; eval plans re-pack after a training step)."""
+    import cartseg
+    from oracle import unet_oracle as O
+    x, tgt = O.synth_batch(2, 64, 64, seed=9)
+    m = _model(_torch_init_state_dict(5)).train()
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-2, fused=True)
+    crit = cartseg.BCEDiceLoss()
+    with torch.no_grad():
+        m.eval()
+        before = m(x.cuda()).clone()
+        m.train()
+    losses = []
+    for _ in range(6):
+        opt.zero_grad(set_to_none=True)
+        loss = crit(m(x.cuda()), tgt.cuda())
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert losses[-1] < losses[0] - 0.02, losses                  # the same batch six times: the loss must fall
+    m.eval()
+    with torch.no_grad():
+        after = m(x.cuda())
+        sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+        ref = O.unet_logits(x, sd, training=False)
+    assert rel_l2(after.cpu(), ref) < 2e-2                        # eval uses the UPDATED weights
+    assert rel_l2(after, before) > 0.05
 
 
 def test_backward_after_overwritten_forward_raises():

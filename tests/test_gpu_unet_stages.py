@@ -202,9 +202,11 @@ def test_forward_and_backward_are_run_to_run_deterministic():
         if i >= 10 and i % 2 == 0:
             border.append((G_UP, (i - 10) // 2))
     bwd_diff = [(k, rel_l2(snaps[1][k], snaps[0][k])) for k in border]
-    print("largest run-to-run backward-tensor differences:", sorted(bwd_diff, key=lambda r: -r[1])[:4])
-    bwd_diff = [(k, e) for k, e in bwd_diff if e > 5e-3]
+    print("run-to-run backward-tensor differences in backward order:",
+          [(f"{'gout,dy,gpool,gup'.split(',')[{G_OUT: 0, DY: 1, G_POOL: 2, G_UP: 3}[k[0]]]}{k[1]}", f"{e:.1e}") for k, e in bwd_diff])
+    bwd_diff = [(k, e) for k, e in bwd_diff if e > 0]
     worst = max((rel_l2(gr[1][k], gr[0][k]), k) for k in gr[0] if gr[0][k].abs().max() > 0)
     print("worst run-to-run parameter-gradient difference:", worst)
-    # fp32 atomic-add ordering flips an occasional bf16 rounding; anything beyond a few 1e-3 would be a race
-    assert not bwd_diff and worst[0] < 5e-3
+    # the activation-gradient chain has no atomics (fixed-order BN reductions): bit-identical run to run; weight
+    # gradients are reduced with fp32 atomic adds across split-K CTAs: identical up to summation order
+    assert not bwd_diff and worst[0] < 1e-4

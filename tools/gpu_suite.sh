@@ -13,6 +13,7 @@ run() {  # name, timeout, command...
   echo "[$name] exit $rc"
   tail -n 6 "gpurun_out/$name.log" | sed "s/^/    /"
   [ $rc -ne 0 ] && status=1
+  return $rc
 }
 for part in "$@"; do
   case $part in
@@ -25,6 +26,9 @@ for part in "$@"; do
     smoke)  run smoke 600 python -c "import __graft_entry__ as g; g.smoke()" ;;
     bench)  run bench 900 python bench.py --steps 5 --warmup 3 ;;
     benchref) run bench_ref 600 python bench.py --impl reference --steps 3 --warmup 1 ;;
+    launches) run profile_plain 300 python tools/profile_step.py && \
+            run ncu_launches 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none \
+                --csv --log-file gpurun_out/launches.csv python tools/profile_step.py ;;
     all)    run tests_all 1800 python -m pytest tests -m gpu -q -x --tb=short --timeout 600 ;;
   esac
 done
