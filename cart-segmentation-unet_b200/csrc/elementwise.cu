@@ -391,15 +391,23 @@ __global__ void __launch_bounds__(kBnBwdThreads, POOL ? 1 : 3) bn_bwd_reduce_ker
   }
 }
 
-// s1/s2 totals (fixed order over blocks, fp64) -> per-channel means c1, c2 and the BN parameter gradients.
-__global__ void bn_bwd_finalize_kernel(BnBwdArgs a, int blocks) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// s1/s2 totals -> per-channel means c1, c2 and the BN parameter gradients.  One warp per channel: lane l sums the
+// partials of blocks l, l+32, ... in fp64, then a fixed-order shuffle tree combines the lanes (deterministic).
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(BnBwdArgs a, int blocks) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (c >= a.C) return;
   double t1 = 0.0, t2 = 0.0;
-  for (int b = 0; b < blocks; ++b) {
+  for (int b = lane; b < blocks; b += 32) {
     t1 += (double)a.partial[(size_t)b * 2 * a.C + c];
     t2 += (double)a.partial[(size_t)b * 2 * a.C + a.C + c];
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+    t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+  }
+  if (lane != 0) return;
   const double inv_n = 1.0 / ((double)a.B * a.H * a.W);
   a.c1[c] = (float)(t1 * inv_n);
   a.c2[c] = (float)(t2 * inv_n);
@@ -416,7 +424,7 @@ cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t s) {
   else bn_bwd_reduce_kernel<false><<<grid, kBnBwdThreads, 0, s>>>(a);
   cudaError_t e = launched();
   if (e != cudaSuccess) return e;
-  bn_bwd_finalize_kernel<<<(a.C + 127) / 128, 128, 0, s>>>(a, grid);
+  bn_bwd_finalize_kernel<<<(a.C + 7) / 8, 256, 0, s>>>(a, grid);
   return launched();
 }
 

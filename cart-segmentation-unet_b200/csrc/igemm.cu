@@ -24,9 +24,14 @@ CS_DEVINL void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" 
 // =============================================================================================
 //                                   pixel-major GEMM
 // =============================================================================================
-template <int BLOCK_N, int SA, int SB>
+// PAIR = true: two CTAs (a cluster on one TPC) run ONE tcgen05.mma.cta_group::2 of M = 256 pixels: each CTA stages
+// its own 128-pixel A patches and HALF of the BLOCK_N weight rows, which halves the weight traffic from L2 and the
+// B-operand shared-memory reads per CTA; each CTA's TMEM holds the accumulator rows of its own pixels, so the
+// epilogue is unchanged.
+template <int BLOCK_N, int SA, int SB, bool PAIR>
 struct PixLayout {
-  static constexpr int kBSlot = BLOCK_N * 128;
+  static constexpr int kBRows = PAIR ? BLOCK_N / 2 : BLOCK_N;
+  static constexpr int kBSlot = kBRows * 128;
   static constexpr int kA = 0;
   static constexpr int kB = kA + SA * kASlotBytes;
   static constexpr int kStage = kB + SB * kBSlot;
@@ -40,9 +45,9 @@ struct PixLayout {
   static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
 };
 
-template <int BLOCK_N, int SA, int SB>
+template <int BLOCK_N, int SA, int SB, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1) pix_gemm_kernel(const __grid_constant__ PixGemmParams p) {
-  using L = PixLayout<BLOCK_N, SA, SB>;
+  using L = PixLayout<BLOCK_N, SA, SB, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
@@ -58,20 +63,29 @@ __global__ void __launch_bounds__(kThreads, 1) pix_gemm_kernel(const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;       // CTA rank inside the pair
+  const bool leader = rank == 0;
   const int m_tiles = p.tiles_w * p.tiles_h * p.batch;
-  const int num_tiles = m_tiles * p.n_blocks;
+  // work unit: PAIR ? (two consecutive m-tiles) x one n-block : one m-tile x one n-block
+  const int m_units = PAIR ? (m_tiles + 1) / 2 : m_tiles;
+  const int num_units = m_units * p.n_blocks;
+  const int first_unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const bool want_stats = p.stat_sum != nullptr;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < SA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
     for (int i = 0; i < SB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], PAIR ? 8 : 4); }
     fence_barrier_init();
     for (int g = 0; g < p.G; ++g) tma_prefetch_desc(&p.tmapA[p.a_map[g]]);
     tma_prefetch_desc(&p.tmapB);
     tma_prefetch_desc(&p.tmapO[0]);
   }
-  if (warp == 2) tmem_alloc<L::kTmemCols>(tmem_ptr);
+  if (warp == 2) {
+    if (PAIR) tmem_alloc_pair<L::kTmemCols>(tmem_ptr);
+    else tmem_alloc<L::kTmemCols>(tmem_ptr);
+  }
   {
     const int nvec = p.o_blocks_per_map * BLOCK_N;           // <= 1024
     for (int i = threadIdx.x; i < 1024; i += kThreads) {
@@ -85,36 +99,63 @@ __global__ void __launch_bounds__(kThreads, 1) pix_gemm_kernel(const __grid_cons
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync();                                  // both CTAs: barriers initialised, TMEM allocated
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
   const int per_img = p.tiles_w * p.tiles_h;
+  // Decodes work unit u into this CTA's tile; a CTA whose m-tile does not exist (odd tile count) gets batch
+  // coordinate == batch: every TMA load is zero-filled and every store clipped away.
+  auto decode = [&](int u, int& nb, int& b, int& w0, int& h0) -> bool {
+    const int m_unit = u / p.n_blocks;
+    nb = u - m_unit * p.n_blocks;
+    const int m_tile = PAIR ? 2 * m_unit + (int)rank : m_unit;
+    const bool valid = m_tile < m_tiles;
+    b = valid ? m_tile / per_img : p.batch;
+    const int rem = valid ? m_tile - b * per_img : 0;
+    const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
+    w0 = tw * 8;
+    h0 = th * 16;
+    return valid;
+  };
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     int sa = 0, pa = 0, sb = 0, pb = 0;
     const uint32_t a_bytes = (16 + p.R - 1) * kAtomBytes;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.n_blocks, nb = tile - m_tile * p.n_blocks;
-      const int b = m_tile / per_img, rem = m_tile - b * per_img;
-      const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
-      const int w0 = tw * 8, h0 = th * 16, n0 = nb * BLOCK_N;
+    for (int u = first_unit; u < num_units; u += unit_stride) {
+      int nb, b, w0, h0;
+      decode(u, nb, b, w0, h0);
+      const int n0 = nb * BLOCK_N + (PAIR ? (int)rank * L::kBRows : 0);
       for (int kc = 0; kc < p.kchunks; ++kc) {
         for (int g = 0; g < p.G; ++g) {
           mbar_wait(&emptyA[sa], pa ^ 1);
           if (lane == 0) {
-            mbar_arrive_expect_tx(&fullA[sa], a_bytes);
-            tma_load_4d(smem + L::kA + sa * kASlotBytes, &p.tmapA[p.a_map[g]], &fullA[sa], p.a_chan0 + kc * 64,
-                        w0 + p.a_dw[g], h0 + p.a_dh[g], b);
+            void* dst = smem + L::kA + sa * kASlotBytes;
+            const CUtensorMap* map = &p.tmapA[p.a_map[g]];
+            if (PAIR) {
+              if (leader) mbar_arrive_expect_tx(&fullA[sa], 2 * a_bytes);
+              tma_load_4d_pair(dst, map, mapa_cluster(smem_u32(&fullA[sa]), 0), p.a_chan0 + kc * 64, w0 + p.a_dw[g],
+                               h0 + p.a_dh[g], b);
+            } else {
+              mbar_arrive_expect_tx(&fullA[sa], a_bytes);
+              tma_load_4d(dst, map, &fullA[sa], p.a_chan0 + kc * 64, w0 + p.a_dw[g], h0 + p.a_dh[g], b);
+            }
           }
           if (++sa == SA) { sa = 0; pa ^= 1; }
           for (int r = 0; r < p.R; ++r) {
             mbar_wait(&emptyB[sb], pb ^ 1);
             if (lane == 0) {
-              mbar_arrive_expect_tx(&fullB[sb], L::kBSlot);
-              tma_load_2d(smem + L::kB + sb * L::kBSlot, &p.tmapB, &fullB[sb], kc * 64,
-                          (g * p.R + r) * p.Ntot + n0);
+              void* dst = smem + L::kB + sb * L::kBSlot;
+              const int row = (g * p.R + r) * p.Ntot + n0;
+              if (PAIR) {
+                if (leader) mbar_arrive_expect_tx(&fullB[sb], 2 * L::kBSlot);
+                tma_load_2d_pair(dst, &p.tmapB, mapa_cluster(smem_u32(&fullB[sb]), 0), kc * 64, row);
+              } else {
+                mbar_arrive_expect_tx(&fullB[sb], L::kBSlot);
+                tma_load_2d(dst, &p.tmapB, &fullB[sb], kc * 64, row);
+              }
             }
             if (++sb == SB) { sb = 0; pb ^= 1; }
           }
@@ -123,43 +164,42 @@ __global__ void __launch_bounds__(kThreads, 1) pix_gemm_kernel(const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = make_idesc(128, BLOCK_N, 0, 0);
-    int sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-      uint32_t accumulate = 0;
-      for (int kc = 0; kc < p.kchunks; ++kc) {
-        for (int g = 0; g < p.G; ++g) {
-          mbar_wait(&fullA[sa], pa);
-          for (int r = 0; r < p.R; ++r) {
-            mbar_wait(&fullB[sb], pb);
-            tc_fence_after();
-            if (lane == 0) {
-              const uint32_t a_addr = smem_u32(smem + L::kA + sa * kASlotBytes) + r * kAtomBytes;
-              const uint32_t b_addr = smem_u32(smem + L::kB + sb * L::kBSlot);
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader) {
+      // Every lane runs this (warp-uniform) code; one elected lane issues each tcgen05 instruction.
+      constexpr uint32_t idesc = make_idesc(PAIR ? 256 : 128, BLOCK_N, 0, 0);
+      const uint64_t desc_hi = make_smem_desc(0, 16, kAtomBytes);          // everything but the start address
+      const uint32_t a_base = smem_u32(smem + L::kA) >> 4, b_base = smem_u32(smem + L::kB) >> 4;
+      int sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, acc_phase = 0;
+      for (int u = first_unit; u < num_units; u += unit_stride) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        uint32_t accumulate = 0;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          for (int g = 0; g < p.G; ++g) {
+            mbar_wait(&fullA[sa], pa);
+            for (int r = 0; r < p.R; ++r) {
+              mbar_wait(&fullB[sb], pb);
+              tc_fence_after();
+              const uint64_t da = desc_hi | (uint64_t)(a_base + (uint32_t)(sa * (kASlotBytes >> 4) + r * (kAtomBytes >> 4)));
+              const uint64_t db = desc_hi | (uint64_t)(b_base + (uint32_t)(sb * (L::kBSlot >> 4)));
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                umma_bf16(d_tmem, make_smem_desc(a_addr + k * 32, 16, kAtomBytes),
-                          make_smem_desc(b_addr + k * 32, 16, kAtomBytes), idesc, accumulate);
+              for (int k = 0; k < 4; ++k) {                               // +32 bytes of K per step = +2 in the descriptor
+                umma_bf16_warp<PAIR>(d_tmem, da + 2 * k, db + 2 * k, idesc, accumulate);
                 accumulate = 1;
               }
-              umma_commit(&emptyB[sb]);
+              umma_commit_warp<PAIR>(&emptyB[sb]);
+              if (++sb == SB) { sb = 0; pb ^= 1; }
             }
-            __syncwarp();
-            if (++sb == SB) { sb = 0; pb ^= 1; }
+            umma_commit_warp<PAIR>(&emptyA[sa]);
+            if (++sa == SA) { sa = 0; pa ^= 1; }
           }
-          if (lane == 0) umma_commit(&emptyA[sa]);
-          __syncwarp();
-          if (++sa == SA) { sa = 0; pa ^= 1; }
         }
+        umma_commit_warp<PAIR>(&tmem_full[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
       }
-      if (lane == 0) umma_commit(&tmem_full[acc]);
-      __syncwarp();
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
     }
   } else {
     // ------------------------------------------------------------------ epilogue (128 threads)
@@ -171,11 +211,9 @@ __global__ void __launch_bounds__(kThreads, 1) pix_gemm_kernel(const __grid_cons
     int acc = 0, acc_phase = 0;
     uint32_t buf_ctr = 0;
     const bool affine = !want_stats && (p.scale != nullptr || p.shift != nullptr || p.relu);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.n_blocks, nb = tile - m_tile * p.n_blocks;
-      const int b = m_tile / per_img, rem = m_tile - b * per_img;
-      const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
-      const int w0 = tw * 8, h0 = th * 16;
+    for (int u = first_unit; u < num_units; u += unit_stride) {
+      int nb, b, w0, h0;
+      const bool valid = decode(u, nb, b, w0, h0);
       const int omap = nb / p.o_blocks_per_map;
       const int n_in_map0 = (nb - omap * p.o_blocks_per_map) * BLOCK_N;
 
@@ -192,10 +230,13 @@ __global__ void __launch_bounds__(kThreads, 1) pix_gemm_kernel(const __grid_cons
         tmem_ld32(taddr + cb * 64, v);
         tmem_ld32(taddr + cb * 64 + 32, v + 32);
         tmem_ld_wait();
-        if (cb == BLOCK_N / 64 - 1) {                    // accumulator fully read: hand it back
+        if (cb == BLOCK_N / 64 - 1) {                    // accumulator fully read: hand it back to the MMA issuer
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_cluster(mapa_cluster(smem_u32(&tmem_empty[acc]), 0));
+            else mbar_arrive(&tmem_empty[acc]);
+          }
         }
         uint32_t packed[32];
         if (affine) {
@@ -222,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, 1) pix_gemm_kernel(const __grid_cons
         }
         fence_proxy_async();
         bar_sync(2, 128);
-        if (et == 0) {
+        if (et == 0 && valid) {
           tma_store_4d(&p.tmapO[omap], sbuf, p.o_chan0 + n_in_map0 + cb * 64, w0, h0, b);
           tma_store_commit();
         }
@@ -233,13 +274,15 @@ __global__ void __launch_bounds__(kThreads, 1) pix_gemm_kernel(const __grid_cons
           const uint32_t* s32 = reinterpret_cast<const uint32_t*>(sbuf);
           const int chunk = lane >> 2, word = lane & 3;
           float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+          if (valid) {
 #pragma unroll 8
-          for (int rr = 0; rr < 32; ++rr) {
-            const int r2 = sub * 32 + rr;
-            if (w0 + (r2 & 7) >= p.W || h0 + (r2 >> 3) >= p.H) continue;
-            const uint32_t w = s32[r2 * 32 + (((chunk ^ (r2 & 7)) << 2) | word)];
-            const float f0 = bf16_lo(w), f1 = bf16_hi(w);
-            s0 += f0; q0 += f0 * f0; s1 += f1; q1 += f1 * f1;
+            for (int rr = 0; rr < 32; ++rr) {
+              const int r2 = sub * 32 + rr;
+              if (w0 + (r2 & 7) >= p.W || h0 + (r2 >> 3) >= p.H) continue;
+              const uint32_t w = s32[r2 * 32 + (((chunk ^ (r2 & 7)) << 2) | word)];
+              const float f0 = bf16_lo(w), f1 = bf16_hi(w);
+              s0 += f0; q0 += f0 * f0; s1 += f1; q1 += f1 * f1;
+            }
           }
           float* rw = red + (ewarp * 64 + 2 * lane) * 2;
           rw[0] = s0; rw[1] = q0; rw[2] = s1; rw[3] = q1;
@@ -268,36 +311,64 @@ __global__ void __launch_bounds__(kThreads, 1) pix_gemm_kernel(const __grid_cons
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync();                                  // the peer's smem / TMEM / barriers stay alive until here
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<L::kTmemCols>(tmem_base);
+    if (PAIR) tmem_dealloc_pair<L::kTmemCols>(tmem_base);
+    else tmem_dealloc<L::kTmemCols>(tmem_base);
   }
 }
 
-template <int BLOCK_N, int SA, int SB>
+template <int BLOCK_N, int SA, int SB, bool PAIR>
 static cudaError_t launch_pix(const PixGemmParams& p, int num_sms, cudaStream_t stream) {
-  using L = PixLayout<BLOCK_N, SA, SB>;
+  using L = PixLayout<BLOCK_N, SA, SB, PAIR>;
   static_assert(L::kDyn <= 232448, "shared memory budget exceeded");
-  auto kern = pix_gemm_kernel<BLOCK_N, SA, SB>;
+  auto kern = pix_gemm_kernel<BLOCK_N, SA, SB, PAIR>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
     attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDyn);
   });
   if (attr_err != cudaSuccess) return attr_err;
-  const int num_tiles = p.tiles_w * p.tiles_h * p.batch * p.n_blocks;
-  const int grid = num_tiles < num_sms ? num_tiles : num_sms;
-  if (grid <= 0) return cudaSuccess;
-  kern<<<grid, kThreads, L::kDyn, stream>>>(p);
+  const int m_tiles = p.tiles_w * p.tiles_h * p.batch;
+  const int units = (PAIR ? (m_tiles + 1) / 2 : m_tiles) * p.n_blocks;
+  if (units <= 0) return cudaSuccess;
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  if (PAIR) {
+    const int clusters = units < num_sms / 2 ? units : num_sms / 2;
+    cfg.gridDim = dim3(2 * clusters);
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  } else {
+    cfg.gridDim = dim3(units < num_sms ? units : num_sms);
+  }
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = L::kDyn;
+  cfg.stream = stream;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+  if (e != cudaSuccess) return e;
   return launched();
 }
 
 cudaError_t launch_pix_gemm(const PixGemmParams& p, int block_n, int num_sms, cudaStream_t stream) {
+  if (p.pair) {
+    switch (block_n) {
+      case 64: return launch_pix<64, 6, 12, true>(p, num_sms, stream);
+      case 128: return launch_pix<128, 6, 8, true>(p, num_sms, stream);
+      case 256: return launch_pix<256, 4, 6, true>(p, num_sms, stream);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   switch (block_n) {
-    case 64: return launch_pix<64, 6, 8>(p, num_sms, stream);
-    case 128: return launch_pix<128, 3, 7>(p, num_sms, stream);
-    case 256: return launch_pix<256, 3, 4>(p, num_sms, stream);
+    case 64: return launch_pix<64, 6, 8, false>(p, num_sms, stream);
+    case 128: return launch_pix<128, 3, 7, false>(p, num_sms, stream);
+    case 256: return launch_pix<256, 3, 4, false>(p, num_sms, stream);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -380,34 +451,33 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_gemm_kernel(const __grid_co
       if (++s == STAGES) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
+    // Every lane runs this (warp-uniform) code; one elected lane issues each tcgen05 instruction.
     constexpr uint32_t idesc = make_idesc(128, BLOCK_N, 1, 1);
     int s = 0, ph = 0;
     uint32_t accumulate = 0;
     // With a single 64-channel block of dY (Cout == 64) both halves of the M=128 operand alias the
     // same block (LBO = 0); rows 64..127 of the accumulator are duplicates and never stored.
     const uint32_t a_lbo = dy_blocks == 2 ? 16 * kAtomBytes : 0;
+    const uint64_t a_hi = make_smem_desc(0, a_lbo, kAtomBytes), b_hi = make_smem_desc(0, kASlotBytes, kAtomBytes);
+    const uint32_t base = smem_u32(smem) >> 4;
     for (int t = t_begin; t < t_end; ++t) {
       mbar_wait(&full[s], ph);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t dy_addr = smem_u32(smem + s * L::kStageSz);
-        const uint32_t x_addr = dy_addr + L::kDY;
-        for (int r = 0; r < p.R; ++r) {
+      const uint32_t dy_lo = base + (uint32_t)(s * (L::kStageSz >> 4));
+      const uint32_t x_lo = dy_lo + (L::kDY >> 4);
+      for (int r = 0; r < p.R; ++r) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            umma_bf16(tmem_base + r * BLOCK_N, make_smem_desc(dy_addr + k * 2 * kAtomBytes, a_lbo, kAtomBytes),
-                      make_smem_desc(x_addr + (r + 2 * k) * kAtomBytes, kASlotBytes, kAtomBytes), idesc,
-                      accumulate | (uint32_t)(k > 0));
-          }
+        for (int k = 0; k < 8; ++k) {
+          umma_bf16_warp<false>(tmem_base + r * BLOCK_N, a_hi | (uint64_t)(dy_lo + k * 2 * (kAtomBytes >> 4)),
+                                b_hi | (uint64_t)(x_lo + (r + 2 * k) * (kAtomBytes >> 4)), idesc,
+                                accumulate | (uint32_t)(k > 0));
         }
-        accumulate = 1;
-        umma_commit(&empty[s]);
       }
-      __syncwarp();
+      accumulate = 1;
+      umma_commit_warp<false>(&empty[s]);
       if (++s == STAGES) { s = 0; ph ^= 1; }
     }
-    if (lane == 0) umma_commit(tmem_full);
-    __syncwarp();
+    umma_commit_warp<false>(tmem_full);
   } else {
     const int sub = warp & 3;
     const int row = sub * 32 + lane;

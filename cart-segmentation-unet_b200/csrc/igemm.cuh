@@ -24,6 +24,7 @@ struct PixGemmParams {
   CUtensorMap tmapB;
   CUtensorMap tmapO[4];
   int G, R;
+  int pair;             // 1: CTA-pair kernel (cta_group::2, M = 256); tmapB's box then holds BLOCK_N/2 rows
   int a_map[4], a_dw[4], a_dh[4];
   int a_chan0;          // first input channel (coordinate offset inside the A maps)
   int kchunks;          // K / 64 per tap

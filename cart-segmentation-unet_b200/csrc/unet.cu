@@ -12,6 +12,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -80,8 +81,18 @@ static int nhwc_map_strided(CUtensorMap* m, const bf16* base, int pitch, int B, 
   if (r != 0) return fail("cuTensorMapEncodeTiled (strided NHWC) failed: %d", r);
   return 0;
 }
+// CTA-pair (cta_group::2) pixel GEMMs are the default; CARTSEG_PAIR=0 selects the single-CTA kernels (debugging).
+static bool use_pair() {
+  static const bool v = [] {
+    const char* e = getenv("CARTSEG_PAIR");
+    return !(e && e[0] == '0');
+  }();
+  return v;
+}
+
 static int weight_map(CUtensorMap* m, const bf16* base, int K, int rows, int block_n) {
-  int r = make_tmap_2d(m, base, (uint64_t)K, (uint64_t)rows, (uint64_t)K * 2, 64, (uint32_t)block_n);
+  const int box_rows = use_pair() ? block_n / 2 : block_n;
+  int r = make_tmap_2d(m, base, (uint64_t)K, (uint64_t)rows, (uint64_t)K * 2, 64, (uint32_t)box_rows);
   if (r != 0) return fail("cuTensorMapEncodeTiled (weights %d x %d) failed: %d", rows, K, r);
   return 0;
 }
@@ -99,6 +110,7 @@ static void pix_common(PixGemmParams& p, int B, int H, int W, int K, int Ntot, i
   p.H = H;
   p.W = W;
   p.o_blocks_per_map = p.n_blocks;
+  p.pair = use_pair() ? 1 : 0;
 }
 
 // 3x3 convolution as 9 shifted GEMMs: group g = horizontal tap (dw = g-1), r = vertical tap.
