@@ -141,6 +141,47 @@ CS_DEVINL void umma_bf16_warp(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
         : "memory");
   }
 }
+// NK consecutive K-steps of one operand pair in a single block: the descriptor low words advance by STEP (in
+// 16-byte units) per step; the first step overwrites the accumulator when accumulate_first == 0.
+// The descriptor high word is the same for every operand used here: SBO = 1024 B, version 1, 128B swizzle.
+static constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+template <bool PAIR, int NK, int STEP>
+CS_DEVINL void umma_bf16_steps_warp(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                    uint32_t accumulate_first) {
+  static_assert(NK == 4 || NK == 8, "NK");
+#define CS_MMA_STEP(i, PRED)                                                                     \
+  "add.u32 al, %1, " #i "*%7;\n\t"                                                               \
+  "add.u32 bl, %2, " #i "*%7;\n\t"                                                               \
+  "mov.b64 da, {al, %3};\n\t"                                                                    \
+  "mov.b64 db, {bl, %3};\n\t"                                                                    \
+  "@q tcgen05.mma.cta_group::%8.kind::f16 [%0], da, db, %5, " PRED ";\n\t"
+  if (NK == 4) {
+    asm volatile(
+        "{\n\t.reg .pred p, q, t;\n\t.reg .b64 da, db;\n\t.reg .b32 al, bl;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        CS_MMA_STEP(0, "p") CS_MMA_STEP(1, "t") CS_MMA_STEP(2, "t") CS_MMA_STEP(3, "t")
+        "}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "n"(kDescHiSw128), "n"(0), "r"(idesc), "r"(accumulate_first), "n"(STEP),
+        "n"(PAIR ? 2 : 1)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p, q, t;\n\t.reg .b64 da, db;\n\t.reg .b32 al, bl;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        CS_MMA_STEP(0, "p") CS_MMA_STEP(1, "t") CS_MMA_STEP(2, "t") CS_MMA_STEP(3, "t")
+        CS_MMA_STEP(4, "t") CS_MMA_STEP(5, "t") CS_MMA_STEP(6, "t") CS_MMA_STEP(7, "t")
+        "}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "n"(kDescHiSw128), "n"(0), "r"(idesc), "r"(accumulate_first), "n"(STEP),
+        "n"(PAIR ? 2 : 1)
+        : "memory");
+  }
+#undef CS_MMA_STEP
+}
+
 template <bool PAIR>
 CS_DEVINL void umma_commit_warp(uint64_t* bar) {
   if (PAIR) {
@@ -255,6 +296,10 @@ CS_DEVINL uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t s
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
   return d;
+}
+__host__ __device__ constexpr uint64_t make_smem_desc_c(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 // Instruction descriptor, kind::f16: D fp32 [4,6)=1, A bf16 [7,10)=1, B bf16 [10,13)=1,
 // A major bit 15, B major bit 16 (0 = K-major, 1 = MN-major), N>>3 [17,23), M>>4 [24,29).

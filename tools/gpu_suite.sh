@@ -34,6 +34,9 @@ for part in "$@"; do
                 -k regex:pix_gemm -c 12 -f -o gpurun_out/prof_pix python tools/profile_step.py && \
             run ncu_wgrad 900 ncu --profile-from-start off --set full --clock-control none --import-source on \
                 -k regex:wgrad -c 3 -f -o gpurun_out/prof_wgrad python tools/profile_step.py ;;
+    ncuone) run profile_plain 300 python tools/profile_step.py && \
+            run ncu_one 900 ncu --profile-from-start off --set full --clock-control none --import-source on \
+                -k regex:${NCU_KERNEL:-pix_gemm} -s ${NCU_SKIP:-1} -c ${NCU_COUNT:-1} -f -o gpurun_out/prof_one python tools/profile_step.py ;;
     all)    run tests_all 1800 python -m pytest tests -m gpu -q -x --tb=short --timeout 600 ;;
   esac
 done
