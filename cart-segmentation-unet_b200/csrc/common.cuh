@@ -240,7 +240,9 @@ CS_DEVINL uint32_t mapa_cluster(uint32_t cta_smem_addr, uint32_t rank) {   // ad
   return r;
 }
 CS_DEVINL void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // default (.release.cta) semantics, as CUTLASS' ClusterBarrier::arrive(cta_id): the .release.cluster form costs a
+  // MEMBAR.ALL.GPU per arrive (it was the top stall of the epilogue warps in ncu)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 CS_DEVINL void tma_load_2d_pair(void* smem, const CUtensorMap* m, uint32_t leader_bar, int c0, int c1) {
   asm volatile(

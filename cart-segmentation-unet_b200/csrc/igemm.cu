@@ -440,33 +440,50 @@ __global__ void __launch_bounds__(kThreads, 1) pix_gemm2_kernel(const __grid_con
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     if (leader) {
-      // Every lane runs this (warp-uniform) code; one elected lane issues each tcgen05 instruction.
+      // Every lane runs this (warp-uniform) code; one elected lane issues each tcgen05 instruction.  The loop is
+      // organised around the smem ring (stage index = compile-time constant of the unrolled body) so that every
+      // descriptor is "uniform base + immediate": the single issuing warp is the critical path of this kernel.
       constexpr uint32_t idesc = make_idesc(256, BLOCK_N, 0, 0);
       const uint32_t lbo_lo = (16u >> 4) << 16;                             // LBO field lives in the low word
       const uint32_t s_base = (smem_u32(smem) >> 4) | lbo_lo;
-      int st = 0, ph = 0, acc = 0, acc_phase = 0;
-      for (int u = first_unit; u < num_units; u += unit_stride) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        uint32_t accumulate = 0;
-        for (int kg = p.kchunks * p.G; kg > 0; --kg) {
-          mbar_wait(&full[st], ph);
-          tc_fence_after();
-          const uint32_t a_lo = s_base + (uint32_t)(st * (L::kStageSz >> 4));
-          const uint32_t b_lo = a_lo + (kASlotBytes >> 4);
-          for (int r = 0; r < p.R; ++r) {
-            // four K-steps of 16 channels: +32 bytes = +2 in the descriptor start field per step
-            umma_bf16_steps_warp<true, 4, 2>(d_tmem, a_lo + (uint32_t)(r * (kAtomBytes >> 4)),
-                                             b_lo + (uint32_t)(r * (L::kBSlot >> 4)), idesc, accumulate);
-            accumulate = 1;
+      const int per_unit = p.kchunks * p.G;
+      int ph = 0, acc = 0, acc_phase = 0, kg = 0, u = first_unit;
+      uint32_t accumulate = 0;
+      bool more = u < num_units;
+      while (more) {
+#pragma unroll
+        for (int st = 0; st < S; ++st) {
+          if (more) {
+            if (kg == 0) {
+              mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+              accumulate = 0;
+            }
+            mbar_wait(&full[st], ph);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+            const uint32_t a_lo = s_base + (uint32_t)(st * (L::kStageSz >> 4));
+            const uint32_t b_lo = a_lo + (kASlotBytes >> 4);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+              if (r < p.R) {
+                // four K-steps of 16 channels: +32 bytes = +2 in the descriptor start field per step
+                umma_bf16_steps_warp<true, 4, 2>(d_tmem, a_lo + (uint32_t)(r * (kAtomBytes >> 4)),
+                                                 b_lo + (uint32_t)(r * (L::kBSlot >> 4)), idesc, accumulate);
+                accumulate = 1;
+              }
+            }
+            umma_commit_warp<true>(&empty[st]);
+            if (++kg == per_unit) {
+              umma_commit_warp<true>(&tmem_full[acc]);
+              kg = 0;
+              acc ^= 1;
+              if (acc == 0) acc_phase ^= 1;
+              u += unit_stride;
+              more = u < num_units;
+            }
           }
-          umma_commit_warp<true>(&empty[st]);
-          if (++st == S) { st = 0; ph ^= 1; }
         }
-        umma_commit_warp<true>(&tmem_full[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        ph ^= 1;
       }
     }
   } else {
