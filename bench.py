@@ -54,8 +54,9 @@ def peaks():
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index = index
@@ -65,7 +66,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -76,9 +77,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples whose nvidia-smi timestamp lies inside [t0, t1] (wall clock, seconds); the sampler
+        is started before the warm-up so that the process is already streaming when the timed region begins."""
+        import datetime
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -88,13 +93,16 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [v.strip() for v in ln.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if t0 is not None and not (t0 <= ts <= t1 + 0.02):
+                    continue
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[3:7]):
+            for n, v in zip(names, f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
@@ -205,25 +213,42 @@ def run_ours(args, wl):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step(x_d, t_d)
     barrier()
 
     # ---- device-resident timing (value) -------------------------------------------------------
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    # per-launch CUDA events around every tensor-core kernel of the timed region (roofline of the dominant kernel)
+    import ctypes as C
+    from cartseg import ops as cs_ops
+    plan = cs_ops.get_plan(B, 3, S, S, dev, inference_only=False)
+    L = cartseg.lib()
+    L.cs_unet_profile(plan.handle, 1)
     n0 = cartseg.lib().cs_kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    w0 = time.time()
     e0.record()
     for _ in range(args.steps):
         loss = step(x_d, t_d)
     e1.record()
     barrier()
+    w1 = time.time()
     ms = e0.elapsed_time(e1)
     launches = cartseg.lib().cs_kernel_launch_count() - n0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(w0, w1) if rank == 0 else None
+    NC = 5
+    k_ms, k_fl, k_n = (C.c_double * NC)(), (C.c_double * NC)(), (C.c_longlong * NC)()
+    L.cs_unet_profile_read(plan.handle, NC, k_ms, k_fl, k_n)
+    L.cs_unet_profile(plan.handle, 0)
+    k_names = ["pix_gemm2_kernel<256> (conv/convT fprop+dgrad, Cout-side 256)", "pix_gemm2_kernel<128>",
+               "pix_gemm2_kernel<64>", "wgrad_gemm_kernel<128>", "wgrad_gemm_kernel<64>"]
+    kernels = [{"kernel": k_names[i], "launches_per_step": k_n[i] / args.steps, "ms_per_step": k_ms[i] / args.steps,
+                "avg_launch_us": 1e3 * k_ms[i] / max(1, k_n[i]), "tflops": k_fl[i] / max(1e-9, k_ms[i]) / 1e9}
+               for i in range(NC)]
     last_loss = float(loss.item())
 
     # ---- end to end: pinned host inputs -> H2D -> step -> loss read back, every step ----------
@@ -248,6 +273,9 @@ def run_ours(args, wl):
     if rank == 0:
         pk = peaks()
         per_gpu_tflops = (value / world) * GFLOP_TRAIN[S] / 1e3
+        dom = max(kernels, key=lambda k: k["ms_per_step"])
+        gemm_ms = sum(k["ms_per_step"] for k in kernels)
+        gemm_tflops = sum(k_fl) / max(1e-9, sum(k_ms)) / 1e9
         line = {
             "metric": "train_images_per_sec", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -260,11 +288,20 @@ def run_ours(args, wl):
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "achieved": per_gpu_tflops, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                         "frac": per_gpu_tflops / pk["tf_sust"], "traffic": None,
-                         "kernel": "all conv / conv-transpose implicit GEMMs of one step, over the WHOLE step time "
-                                   f"({GFLOP_TRAIN[S]} algorithmic GFLOP per image)",
-                         "peak_source": pk["source"] + ", sustained bf16"},
+            "roofline": {"bound": "tensor", "achieved": dom["tflops"], "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                         "frac": dom["tflops"] / pk["tf_sust"], "traffic": None,
+                         "kernel": dom["kernel"],
+                         "how": "algorithmic FLOPs (2*MACs) of the launches of this kernel in the timed region / their "
+                                "summed CUDA-event durations on the launch stream (rank 0)",
+                         "avg_launch_us": dom["avg_launch_us"], "launches_per_step": dom["launches_per_step"],
+                         "share_of_step": dom["ms_per_step"] / (ms / args.steps),
+                         "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                         "all_tensor_kernels": {"ms_per_step": gemm_ms, "tflops": gemm_tflops,
+                                                "frac": gemm_tflops / pk["tf_sust"],
+                                                "share_of_step": gemm_ms / (ms / args.steps)},
+                         "whole_step": {"tflops": per_gpu_tflops, "frac": per_gpu_tflops / pk["tf_sust"],
+                                        "gflop_per_image": GFLOP_TRAIN[S]},
+                         "kernels": kernels},
         }
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_step_rate(wl["loss"], S, steps=3, warmup=1)
@@ -278,7 +315,7 @@ def run_ours(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="k2", choices=sorted(WORKLOADS))

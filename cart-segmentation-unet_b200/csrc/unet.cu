@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "../../include/cartseg.h"
 #include "igemm.cuh"
@@ -260,6 +261,7 @@ struct ConvL {
   PixGemmParams fp_train, fp_eval, dg;
   WgradParams wg;
   int bn_f, bn_d, bn_w;
+  double flops;                      // algorithmic 2*MACs of one pass (fprop == dgrad == wgrad)
 };
 struct UpL {
   int cin, cout, H, W;               // H, W: input (coarse) extents
@@ -270,6 +272,7 @@ struct UpL {
   PixGemmParams fp, dg;
   WgradParams wg;
   int bn_f, bn_d, bn_w;
+  double flops;
 };
 
 struct cs_unet_plan {
@@ -285,7 +288,45 @@ struct cs_unet_plan {
   float* bn_partial;                 // per-block partial sums of the BN backward reduction
   uint8_t* stats_begin;
   size_t stats_bytes;
+  // optional per-launch timing of the tensor-core kernels (cs_unet_profile): CUDA events around each GEMM launch
+  bool profiling;
+  std::vector<cudaEvent_t> prof_events;   // pairs (begin, end)
+  std::vector<int> prof_class;
+  std::vector<double> prof_flops;
+  size_t prof_used;
 };
+
+namespace {
+// kernel classes reported by cs_unet_profile_read
+enum { kClsPix256 = 0, kClsPix128, kClsPix64, kClsWgrad128, kClsWgrad64, kNumCls };
+int pix_class(int bn) { return bn == 256 ? kClsPix256 : (bn == 128 ? kClsPix128 : kClsPix64); }
+int wgrad_class(int bn) { return bn == 128 ? kClsWgrad128 : kClsWgrad64; }
+
+// Runs `launch` between two events on `s` when profiling is on.
+template <typename F>
+cudaError_t timed(cs_unet_plan* pl, int cls, double flops, cudaStream_t s, F&& launch) {
+  if (!pl->profiling) return launch();
+  if (pl->prof_events.size() < 2 * (pl->prof_used + 1)) {
+    cudaEvent_t a, b;
+    cudaError_t e = cudaEventCreate(&a);
+    if (e != cudaSuccess) return e;
+    e = cudaEventCreate(&b);
+    if (e != cudaSuccess) return e;
+    pl->prof_events.push_back(a);
+    pl->prof_events.push_back(b);
+    pl->prof_class.push_back(0);
+    pl->prof_flops.push_back(0.0);
+  }
+  const size_t i = pl->prof_used++;
+  pl->prof_class[i] = cls;
+  pl->prof_flops[i] = flops;
+  cudaError_t e = cudaEventRecord(pl->prof_events[2 * i], s);
+  if (e != cudaSuccess) return e;
+  e = launch();
+  if (e != cudaSuccess) return e;
+  return cudaEventRecord(pl->prof_events[2 * i + 1], s);
+}
+}  // namespace
 
 namespace {
 
@@ -339,6 +380,7 @@ void layout(cs_unet_plan* pl, uint8_t* base) {
     c.H = LH[L];
     c.W = LW[L];
     c.P = LP[L];
+    c.flops = 2.0 * (double)c.P * c.cout * (i == 0 ? 9.0 * pl->Cin : 9.0 * c.cin);
     const int pb = conv_param_base(i);
     c.pw = pb; c.pb = pb + 1; c.pgamma = pb + 2; c.pbeta = pb + 3;
     c.y = train ? a.take<bf16>(c.P * c.cout) : nullptr;
@@ -390,6 +432,7 @@ void layout(cs_unet_plan* pl, uint8_t* base) {
     u.H = LH[L + 1];
     u.W = LW[L + 1];
     u.P = LP[L + 1];
+    u.flops = 2.0 * (double)u.P * u.cin * u.cout * 4.0;
     u.pw = 40 + 2 * k;
     u.pb = 41 + 2 * k;
     const ConvL& src = k == 0 ? pl->conv[9] : pl->conv[10 + 2 * (k - 1) + 1];
@@ -475,9 +518,8 @@ int cs_unet_plan_create(cs_unet_plan** out, int batch, int in_channels, int heig
   if (in_channels < 1 || in_channels > 7) return fail("in_channels must be in [1, 7] (got %d)", in_channels);
   if (height < 16 || width < 16 || height % 16 || width % 16)
     return fail("height and width must be positive multiples of 16 (got %d x %d)", height, width);
-  cs_unet_plan* pl = new (std::nothrow) cs_unet_plan();
+  cs_unet_plan* pl = new (std::nothrow) cs_unet_plan();   // value-initialised: all POD members zero
   if (!pl) return fail("out of host memory");
-  memset(pl, 0, sizeof(*pl));
   pl->B = batch; pl->Cin = in_channels; pl->H = height; pl->W = width;
   pl->infer = inference_only != 0;
   layout(pl, nullptr);
@@ -485,7 +527,11 @@ int cs_unet_plan_create(cs_unet_plan** out, int batch, int in_channels, int heig
   return 0;
 }
 
-void cs_unet_plan_destroy(cs_unet_plan* plan) { delete plan; }
+void cs_unet_plan_destroy(cs_unet_plan* plan) {
+  if (!plan) return;
+  for (cudaEvent_t e : plan->prof_events) cudaEventDestroy(e);
+  delete plan;
+}
 
 size_t cs_unet_plan_workspace_bytes(const cs_unet_plan* plan) { return plan ? plan->ws_bytes : 0; }
 
@@ -533,7 +579,7 @@ int cs_unet_forward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* x, 
   auto run_conv = [&](int i) -> int {
     ConvL& c = pl->conv[i];
     if (training) {
-      CS_CUDA(launch_pix_gemm(c.fp_train, c.bn_f, pl->num_sms, s));
+      CS_CUDA(timed(pl, pix_class(c.bn_f), c.flops, s, [&] { return launch_pix_gemm(c.fp_train, c.bn_f, pl->num_sms, s); }));
       BnFinalizeArgs f{};
       f.sum = c.st_sum; f.sq = c.st_sq; f.count = (double)c.P;
       f.gamma = t->param[c.pgamma]; f.beta = t->param[c.pbeta]; f.conv_bias = t->param[c.pb];
@@ -547,7 +593,7 @@ int cs_unet_forward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* x, 
       if (!t->running_mean[i] || !t->running_var[i]) return fail("running statistics of BN %d are null", i);
       CS_CUDA(launch_bn_fold_eval(t->param[c.pgamma], t->param[c.pbeta], t->param[c.pb], t->running_mean[i],
                                   t->running_var[i], 1e-5f, c.scale, c.shift, c.cout, s));
-      CS_CUDA(launch_pix_gemm(c.fp_eval, c.bn_f, pl->num_sms, s));
+      CS_CUDA(timed(pl, pix_class(c.bn_f), c.flops, s, [&] { return launch_pix_gemm(c.fp_eval, c.bn_f, pl->num_sms, s); }));
       if (c.pooled) CS_CUDA(launch_maxpool(c.out.p, c.out.pitch, c.out.c0, B, c.H, c.W, c.cout, c.pooled, s));
     }
     return 0;
@@ -556,7 +602,7 @@ int cs_unet_forward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* x, 
   for (int k = 0; k < 4; ++k) {
     UpL& u = pl->up[k];
     u.fp.shift = t->param[u.pb];
-    CS_CUDA(launch_pix_gemm(u.fp, u.bn_f, pl->num_sms, s));
+    CS_CUDA(timed(pl, pix_class(u.bn_f), u.flops, s, [&] { return launch_pix_gemm(u.fp, u.bn_f, pl->num_sms, s); }));
     CS_TRY(run_conv(10 + 2 * k));
     CS_TRY(run_conv(11 + 2 * k));
   }
@@ -626,22 +672,47 @@ int cs_unet_backward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* dl
       if (t->grad[c.pw]) {
         const size_t e = (size_t)(idx == 0 ? 1 : 9) * c.cout * c.cin;
         CS_CUDA(cudaMemsetAsync(pl->dwp, 0, e * sizeof(float), s));
-        CS_CUDA(launch_wgrad_gemm(c.wg, c.bn_w, s));
+        CS_CUDA(timed(pl, wgrad_class(c.bn_w), c.flops, s, [&] { return launch_wgrad_gemm(c.wg, c.bn_w, s); }));
         if (idx == 0) CS_CUDA(launch_unpack_first(pl->dwp, c.cout, pl->Cin, t->grad[c.pw], s));
         else CS_CUDA(launch_unpack_pairs(pl->dwp, c.cout, c.cin, 9, kTapWgrad, t->grad[c.pw], s));
       }
-      if (idx > 0 && idx > frozen_encoder_convs) CS_CUDA(launch_pix_gemm(c.dg, c.bn_d, pl->num_sms, s));
+      if (idx > 0 && idx > frozen_encoder_convs)
+        CS_CUDA(timed(pl, pix_class(c.bn_d), c.flops, s, [&] { return launch_pix_gemm(c.dg, c.bn_d, pl->num_sms, s); }));
     } else {
       UpL& u = pl->up[idx];
       if (t->grad[u.pb]) CS_CUDA(launch_channel_sum(u.g_out.p, u.g_out.pitch, u.g_out.c0, 4 * u.P, u.cout, t->grad[u.pb], s));
       if (t->grad[u.pw]) {
         CS_CUDA(cudaMemsetAsync(pl->dwp, 0, (size_t)4 * u.cin * u.cout * sizeof(float), s));
-        CS_CUDA(launch_wgrad_gemm(u.wg, u.bn_w, s));
+        CS_CUDA(timed(pl, wgrad_class(u.bn_w), u.flops, s, [&] { return launch_wgrad_gemm(u.wg, u.bn_w, s); }));
         CS_CUDA(launch_unpack_pairs(pl->dwp, u.cin, u.cout, 4, kTapIdent, t->grad[u.pw], s));
       }
-      CS_CUDA(launch_pix_gemm(u.dg, u.bn_d, pl->num_sms, s));
+      CS_CUDA(timed(pl, pix_class(u.bn_d), u.flops, s, [&] { return launch_pix_gemm(u.dg, u.bn_d, pl->num_sms, s); }));
     }
   }
+  return 0;
+}
+
+int cs_unet_profile(cs_unet_plan* pl, int enable) {
+  if (!pl) return fail("plan is null");
+  pl->profiling = enable != 0;
+  pl->prof_used = 0;
+  return 0;
+}
+
+int cs_unet_profile_read(cs_unet_plan* pl, int n_classes, double* ms, double* flops, long long* launches) {
+  if (!pl) return fail("plan is null");
+  if (n_classes != kNumCls || !ms || !flops || !launches) return fail("cs_unet_profile_read: expected %d classes", (int)kNumCls);
+  for (int i = 0; i < kNumCls; ++i) { ms[i] = 0.0; flops[i] = 0.0; launches[i] = 0; }
+  for (size_t i = 0; i < pl->prof_used; ++i) {
+    CS_CUDA(cudaEventSynchronize(pl->prof_events[2 * i + 1]));
+    float t = 0.f;
+    CS_CUDA(cudaEventElapsedTime(&t, pl->prof_events[2 * i], pl->prof_events[2 * i + 1]));
+    const int c = pl->prof_class[i];
+    ms[c] += t;
+    flops[c] += pl->prof_flops[i];
+    launches[c] += 1;
+  }
+  pl->prof_used = 0;
   return 0;
 }
 

@@ -80,6 +80,13 @@ int cs_unet_forward(cs_unet_plan* plan, const cs_unet_tensors* t, const float* x
  * 0 trains everything, 10 freezes the whole encoder (src/train_with_focalDice.py:384-391). */
 int cs_unet_backward(cs_unet_plan* plan, const cs_unet_tensors* t, const float* dlogits, int stage_begin,
                      int stage_end, int frozen_encoder_convs, cs_stream_t stream);
+/* Per-launch timing of the tensor-core kernels (bench.py's roofline): while enabled, every implicit-GEMM launch of
+ * cs_unet_forward / cs_unet_backward is bracketed by CUDA events on the launch stream.  cs_unet_profile_read waits for
+ * the recorded events and returns, per kernel class, the summed device time (ms), algorithmic FLOPs (2*MACs) and
+ * launch count since the last read.  Classes: 0 pixel GEMM N=256, 1 N=128, 2 N=64, 3 weight-gradient GEMM N=128, 4 N=64. */
+#define CS_UNET_NUM_PROFILE_CLASSES 5
+int cs_unet_profile(cs_unet_plan* plan, int enable);
+int cs_unet_profile_read(cs_unet_plan* plan, int n_classes, double* ms, double* flops, long long* launches);
 /* Test hook: copies one internal NHWC bf16 tensor of the plan into `dst` as dense fp32 NCHW (dst == NULL: only
  * report dims_out = {B, C, H, W}).  kind 0..5 index a conv (0..17): raw output, activation, grad wrt raw output,
  * grad wrt activation, pooled activation, grad wrt pooled; kind 6/7 index a conv-transpose (0..3): output, its grad. */
