@@ -769,23 +769,28 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_gemm_kernel(const __grid_co
     }
   } else if (warp == 1) {
     // Every lane runs this (warp-uniform) code; one elected lane issues each tcgen05 instruction.
-    constexpr uint32_t idesc = make_idesc(128, BLOCK_N, 1, 1);
+    // One MMA covers the R vertical taps of a 64-channel block of X at once: N = 64*R, the N-blocks of the MN-major
+    // B operand are the SAME 64 channels one image row (= one 1024-byte atom) further down (LBO = 1024), so the dY
+    // operand is read from shared memory once per K-step instead of once per tap.
+    const uint32_t idesc = p.R == 3 ? make_idesc(128, 192, 1, 1) : make_idesc(128, 64, 1, 1);
     int s = 0, ph = 0;
     uint32_t accumulate = 0;
     // With a single 64-channel block of dY (Cout == 64) both halves of the M=128 operand alias the
     // same block (LBO = 0); rows 64..127 of the accumulator are duplicates and never stored.
     const uint32_t a_lbo = dy_blocks == 2 ? 16 * kAtomBytes : 0;
-    const uint64_t a_full = make_smem_desc(0, a_lbo, kAtomBytes), b_full = make_smem_desc(0, kASlotBytes, kAtomBytes);
+    const uint64_t a_full = make_smem_desc(0, a_lbo, kAtomBytes), b_full = make_smem_desc(0, kAtomBytes, kAtomBytes);
     const uint32_t a_lbo_lo = (uint32_t)a_full, b_lbo_lo = (uint32_t)b_full;   // LBO fields (start address = 0)
     const uint32_t base = smem_u32(smem) >> 4;
+    const uint32_t acc_cols = 64 * p.R;
     for (int t = t_begin; t < t_end; ++t) {
       mbar_wait(&full[s], ph);
       tc_fence_after();
       const uint32_t dy_lo = base + (uint32_t)(s * (L::kStageSz >> 4));
       const uint32_t x_lo = dy_lo + (L::kDY >> 4);
-      for (int r = 0; r < p.R; ++r)   // eight K-steps of 16 pixels: two 1024-byte atoms (= 128 descriptor units) per step
-        umma_bf16_steps_warp<false, 8, 2 * (kAtomBytes >> 4)>(tmem_base + r * BLOCK_N, dy_lo | a_lbo_lo,
-                                                             (x_lo + r * (kAtomBytes >> 4)) | b_lbo_lo, idesc,
+#pragma unroll
+      for (int j = 0; j < BLOCK_N / 64; ++j)   // eight K-steps of 16 pixels: two 1024-byte atoms (= 128 descriptor units) per step
+        umma_bf16_steps_warp<false, 8, 2 * (kAtomBytes >> 4)>(tmem_base + j * acc_cols, dy_lo | a_lbo_lo,
+                                                             (x_lo + j * (kASlotBytes >> 4)) | b_lbo_lo, idesc,
                                                              accumulate);
       accumulate = 1;
       umma_commit_warp<false>(&empty[s]);
@@ -799,20 +804,22 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_gemm_kernel(const __grid_co
     tc_fence_after();
     if (t_end > t_begin) {
       const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16);
-      for (int r = 0; r < p.R; ++r) {
-        float* dst_row = p.dw + ((size_t)((g * p.R + r) * p.Mtot + mb * 128 + row)) * p.Ntot + nb * BLOCK_N;
+      for (int j = 0; j < BLOCK_N / 64; ++j) {
+        for (int r = 0; r < p.R; ++r) {
+          float* dst_row = p.dw + ((size_t)((g * p.R + r) * p.Mtot + mb * 128 + row)) * p.Ntot + nb * BLOCK_N + j * 64;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(taddr + r * BLOCK_N + c0, v);
-          tmem_ld_wait();
-          if (row < m_valid) {
+          for (int c0 = 0; c0 < 64; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(taddr + (j * p.R + r) * 64 + c0, v);
+            tmem_ld_wait();
+            if (row < m_valid) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst_row + c0 + 4 * j),
-                           "f"(__uint_as_float(v[4 * j])), "f"(__uint_as_float(v[4 * j + 1])),
-                           "f"(__uint_as_float(v[4 * j + 2])), "f"(__uint_as_float(v[4 * j + 3]))
-                           : "memory");
+              for (int q = 0; q < 8; ++q) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst_row + c0 + 4 * q),
+                             "f"(__uint_as_float(v[4 * q])), "f"(__uint_as_float(v[4 * q + 1])),
+                             "f"(__uint_as_float(v[4 * q + 2])), "f"(__uint_as_float(v[4 * q + 3]))
+                             : "memory");
+              }
             }
           }
         }
