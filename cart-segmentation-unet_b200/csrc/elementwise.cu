@@ -1,6 +1,8 @@
 // Bandwidth-bound kernels around the convolutions: weight (un)packing, input im2col, batch-norm
 // finalize / apply / backward, ReLU, 2x2 max-pool (+ its backward routing), the 1x1 head.
 // All of them are single coalesced passes with 16-byte vectors (8 bf16 channels per thread).
+#include <mutex>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -101,33 +103,56 @@ cudaError_t launch_unpack_first(const float* dwp, int Cout, int Cin, float* grad
 }
 
 // ============================================================================ input im2col
-__global__ void im2col_first_kernel(const float* __restrict__ x, int B, int Cin, int H, int W, bf16* __restrict__ col) {
-  // one thread per (pixel, 8-wide k group): 8 groups cover the 64-wide padded K
-  const long long total = (long long)B * H * W * 8;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int kg = (int)(i & 7);
-    const long long p = i >> 3;
-    const int w = (int)(p % W);
-    const int h = (int)((p / W) % H);
-    const int b = (int)(p / ((long long)W * H));
+// x fp32 NCHW -> col bf16 [pixels][64] with k = (kh*3+kw)*Cin + c (zero padded to 64).  One block builds 128
+// consecutive pixels of one image row band: the (3 x (128+2) x Cin) fp32 patch is staged in shared memory with
+// coalesced loads, then every thread emits 16-byte groups of 8 k-values so that a warp writes 512 contiguous bytes.
+static constexpr int kI2cPix = 128;
+__global__ void __launch_bounds__(256) im2col_first_kernel(const float* __restrict__ x, int B, int Cin, int H, int W,
+                                                          bf16* __restrict__ col) {
+  extern __shared__ float patch[];                       // [Cin][3][kI2cPix + 2]
+  const int PW = kI2cPix + 2;
+  const int wblocks = (W + kI2cPix - 1) / kI2cPix;
+  const int blk = blockIdx.x;
+  const int wb = blk % wblocks;
+  const int h = (blk / wblocks) % H;
+  const int b = blk / (wblocks * H);
+  const int w0 = wb * kI2cPix;
+  for (int i = threadIdx.x; i < Cin * 3 * PW; i += blockDim.x) {
+    const int pw = i % PW, r = (i / PW) % 3, c = i / (3 * PW);
+    const int hh = h + r - 1, ww = w0 + pw - 1;
+    float v = 0.f;
+    if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(&x[(((size_t)b * Cin + c) * H + hh) * W + ww]);
+    patch[i] = v;
+  }
+  __shared__ int koff[64];                               // k -> offset of its tap inside the patch (-1: zero padding)
+  if (threadIdx.x < 64) {
+    const int k = threadIdx.x;
+    int off = -1;
+    if (k < 9 * Cin) {
+      const int tap = k / Cin, c = k - tap * Cin;
+      off = (c * 3 + tap / 3) * PW + tap % 3;
+    }
+    koff[k] = off;
+  }
+  __syncthreads();
+  bf16* dst = col + (((size_t)b * H + h) * W + w0) * 64;
+  for (int i = threadIdx.x; i < kI2cPix * 8; i += blockDim.x) {
+    const int kg = i & 7, p = i >> 3;
+    if (w0 + p >= W) continue;
     float f[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int k = kg * 8 + j;
-      float v = 0.f;
-      if (k < 9 * Cin) {
-        const int tap = k / Cin, c = k - tap * Cin;
-        const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
-        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(&x[(((size_t)b * Cin + c) * H + hh) * W + ww]);
-      }
-      f[j] = v;
+      const int off = koff[kg * 8 + j];
+      f[j] = off >= 0 ? patch[off + p] : 0.f;
     }
-    st8(col + p * 64 + kg * 8, pack8(f));
+    st8(dst + (size_t)i * 8, pack8(f));
   }
 }
 cudaError_t launch_im2col_first(const float* x, int B, int Cin, int H, int W, bf16* col, cudaStream_t s) {
   if (9 * Cin > 64) return cudaErrorInvalidValue;
-  im2col_first_kernel<<<grid_for((long long)B * H * W * 8, 256), 256, 0, s>>>(x, B, Cin, H, W, col);
+  const int wblocks = (W + kI2cPix - 1) / kI2cPix;
+  const size_t smem = (size_t)Cin * 3 * (kI2cPix + 2) * sizeof(float);
+  im2col_first_kernel<<<B * H * wblocks, 256, smem, s>>>(x, B, Cin, H, W, col);
   return launched();
 }
 
@@ -352,10 +377,12 @@ static constexpr int kBnBwdMaxBlocks = 148 * 4;          // partials: [blocks][2
 
 size_t bn_bwd_scratch_bytes(int maxC) { return (size_t)kBnBwdMaxBlocks * 2 * maxC * sizeof(float); }
 
+// One full wave of resident blocks (3 per SM without pooling, 1 with: see the launch bounds) — a partial second
+// wave costs these bandwidth-bound kernels its whole duration again.
 static int bn_bwd_grid(const BnBwdArgs& a) {
   const int rpb = kBnBwdThreads / (a.C / 8);
   const long long units = a.g_pool ? (long long)a.B * (a.H / 2) * (a.W / 2) : (long long)a.B * a.H * a.W;
-  return grid_for(units, rpb * 2, kBnBwdMaxBlocks);
+  return grid_for(units, rpb * 2, a.g_pool ? 148 : 148 * 3);
 }
 
 template <bool POOL>
@@ -454,9 +481,7 @@ __global__ void __launch_bounds__(kBnBwdThreads, POOL ? 1 : 3) bn_bwd_apply_kern
   }
 }
 cudaError_t launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t s) {
-  const long long units = a.g_pool ? (long long)a.B * (a.H / 2) * (a.W / 2) : (long long)a.B * a.H * a.W;
-  const int rpb = kBnBwdThreads / (a.C / 8);
-  const int grid = grid_for(units, rpb * 2, 148 * 8);
+  const int grid = bn_bwd_grid(a);
   if (a.g_pool) bn_bwd_apply_kernel<true><<<grid, kBnBwdThreads, 0, s>>>(a);
   else bn_bwd_apply_kernel<false><<<grid, kBnBwdThreads, 0, s>>>(a);
   return launched();

@@ -321,15 +321,19 @@ __global__ void __launch_bounds__(kThreads, 1) pix_gemm_kernel(const __grid_cons
 
 // Pair-only kernel with unified pipeline stages (A patch + its R weight tiles per stage, one mbarrier wait and one
 // commit per 4*R MMAs): ncu showed the single MMA-issuing warp to be the bottleneck of the finer-grained ring.
-template <int BLOCK_N, int S, int NSTG>
+// EG = number of 4-warp epilogue groups: with EG = 2 the groups take alternate work units (group e owns TMEM
+// accumulator buffer e), which doubles the epilogue throughput of the small-N kernels whose BN-statistics epilogue
+// was slower than their MMAs (ncu: the MMA issuer waited on tmem_empty).
+template <int BLOCK_N, int S, int NSTG, int EG>
 struct Pix2Layout {
   static constexpr int kBRows = BLOCK_N / 2;
   static constexpr int kBSlot = kBRows * 128;
   static constexpr int kStageSz = kASlotBytes + 3 * kBSlot;
   static constexpr int kStage = S * kStageSz;                // epilogue staging
-  static constexpr int kVec = kStage + NSTG * kStageBytes;   // 2 x 1024 floats
-  static constexpr int kRed = kVec + 2 * 1024 * 4;           // 4 x 64 x 2 floats
-  static constexpr int kBar = kRed + 4 * 64 * 2 * 4;
+  static constexpr int kVec = kStage + NSTG * kStageBytes;   // EG x (2 x 1024 floats)
+  static constexpr int kRed = kVec + EG * 2 * 1024 * 4;      // EG x (4 x 64 x 2 floats)
+  static constexpr int kBar = kRed + EG * 4 * 64 * 2 * 4;
+  static constexpr int kThreadsTotal = 64 + 128 * EG;
   static constexpr int kNumBar = 2 * S + 4;
   static constexpr int kTmemPtr = kBar + kNumBar * 8;
   static constexpr int kTotal = kTmemPtr + 16;
@@ -337,10 +341,11 @@ struct Pix2Layout {
   static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
 };
 
-template <int BLOCK_N, int S, int NSTG>
-__global__ void __launch_bounds__(kThreads, 1) pix_gemm2_kernel(const __grid_constant__ PixGemmParams p) {
-  using L = Pix2Layout<BLOCK_N, S, NSTG>;
+template <int BLOCK_N, int S, int NSTG, int EG>
+__global__ void __launch_bounds__(64 + 128 * EG, 1) pix_gemm2_kernel(const __grid_constant__ PixGemmParams p) {
+  using L = Pix2Layout<BLOCK_N, S, NSTG, EG>;
   constexpr bool PAIR = true;
+  static_assert(EG == 1 || NSTG == 2, "two epilogue groups use one staging buffer each");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
@@ -378,14 +383,15 @@ __global__ void __launch_bounds__(kThreads, 1) pix_gemm2_kernel(const __grid_con
   }
   {
     const int nvec = p.o_blocks_per_map * BLOCK_N;           // <= 1024
-    for (int i = threadIdx.x; i < 1024; i += kThreads) {
+    for (int i = threadIdx.x; i < 1024; i += L::kThreadsTotal) {
       float a = 0.f, b = 0.f;
       if (!want_stats && i < nvec) {
         a = p.scale ? p.scale[i] : 1.f;
         b = p.shift ? p.shift[i] : 0.f;
       }
-      vec[i] = a;
+      vec[i] = a;                                          // group 0's copy doubles as the scale / shift table
       vec[1024 + i] = b;
+      if (EG == 2) { vec[2048 + i] = 0.f; vec[3072 + i] = 0.f; }
     }
   }
   tc_fence_before();
@@ -487,16 +493,24 @@ __global__ void __launch_bounds__(kThreads, 1) pix_gemm2_kernel(const __grid_con
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (128 threads)
-    const int et = threadIdx.x - 64;
+    // ------------------------------------------------------------------ epilogue (EG groups of 128 threads)
+    const int eg = (warp - 2) >> 2;            // epilogue group: owns accumulator buffer `eg` when EG == 2
+    const int et = threadIdx.x - 64 - eg * 128;
     const int sub = warp & 3;                  // TMEM sub-partition this warp may read
-    const int ewarp = warp - 2;
+    const int ewarp = (warp - 2) & 3;
+    const int bar0 = 3 * eg;                   // named barriers 1..3 (group 0), 4..6 (group 1)
+    float* gvec = vec + eg * 2048;             // this group's statistics accumulators
     const int row = sub * 32 + lane;           // pixel row of the tile held by this thread
-    float* red = reinterpret_cast<float*>(smem + L::kRed);
-    int acc = 0, acc_phase = 0;
+    float* red = reinterpret_cast<float*>(smem + L::kRed) + eg * 512;
+    int acc = 0, acc_phase = 0, unit_no = 0;
     uint32_t buf_ctr = 0;
     const bool affine = !want_stats && (p.scale != nullptr || p.shift != nullptr || p.relu);
-    for (int u = first_unit; u < num_units; u += unit_stride) {
+    for (int u = first_unit; u < num_units; u += unit_stride, ++unit_no) {
+      if (EG == 2) {                           // alternate units between the groups; acc buffer == group
+        if ((unit_no & 1) != eg) continue;
+        acc = eg;
+        acc_phase = (unit_no >> 1) & 1;
+      }
       int nb, b, w0, h0;
       const bool valid = decode(u, nb, b, w0, h0);
       const int omap = nb / p.o_blocks_per_map;
@@ -507,10 +521,13 @@ __global__ void __launch_bounds__(kThreads, 1) pix_gemm2_kernel(const __grid_con
       const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
       for (int cb = 0; cb < BLOCK_N / 64; ++cb) {
-        uint8_t* sbuf = smem + L::kStage + (NSTG == 2 ? (buf_ctr & 1) : 0) * kStageBytes;
+        uint8_t* sbuf = smem + L::kStage + (EG == 2 ? eg : (NSTG == 2 ? (int)(buf_ctr & 1) : 0)) * kStageBytes;
         ++buf_ctr;
-        if (et == 0) tma_store_wait_read<NSTG - 1>();    // the store that last used this buffer has drained
-        bar_sync(1, 128);
+        if (et == 0) {                                   // the store that last used this buffer has drained
+          if (EG == 2) tma_store_wait_read<0>();
+          else tma_store_wait_read<NSTG - 1>();
+        }
+        bar_sync(1 + bar0, 128);
         uint32_t v[64];
         tmem_ld32(taddr + cb * 64, v);
         tmem_ld32(taddr + cb * 64 + 32, v + 32);
@@ -547,7 +564,7 @@ __global__ void __launch_bounds__(kThreads, 1) pix_gemm2_kernel(const __grid_con
           }
         }
         fence_proxy_async();
-        bar_sync(2, 128);
+        bar_sync(2 + bar0, 128);
         if (et == 0 && valid) {
           tma_store_4d(&p.tmapO[omap], sbuf, p.o_chan0 + n_in_map0 + cb * 64, w0, h0, b);
           tma_store_commit();
@@ -571,23 +588,25 @@ __global__ void __launch_bounds__(kThreads, 1) pix_gemm2_kernel(const __grid_con
           }
           float* rw = red + (ewarp * 64 + 2 * lane) * 2;
           rw[0] = s0; rw[1] = q0; rw[2] = s1; rw[3] = q1;
-          bar_sync(3, 128);
+          bar_sync(3 + bar0, 128);
           const int c = et & 63, which = et >> 6;
           float tot = 0.f;
 #pragma unroll
           for (int w4 = 0; w4 < 4; ++w4) tot += red[(w4 * 64 + c) * 2 + which];
-          vec[which * 1024 + n_in_map0 + cb * 64 + c] += tot;
+          gvec[which * 1024 + n_in_map0 + cb * 64 + c] += tot;
         }
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      if (EG == 1) {
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
     }
     if (et == 0) tma_store_wait_all<0>();
     if (want_stats) {
-      bar_sync(1, 128);
+      bar_sync(1 + bar0, 128);
       const int nvec = p.o_blocks_per_map * BLOCK_N;
       for (int i = et; i < nvec; i += 128) {
-        const float s = vec[i], q = vec[1024 + i];
+        const float s = gvec[i], q = gvec[1024 + i];
         if (q != 0.f) {
           atomicAdd(&p.stat_sum[i], (double)s);
           atomicAdd(&p.stat_sq[i], (double)q);
@@ -605,11 +624,11 @@ __global__ void __launch_bounds__(kThreads, 1) pix_gemm2_kernel(const __grid_con
   }
 }
 
-template <int BLOCK_N, int S, int NSTG>
+template <int BLOCK_N, int S, int NSTG, int EG>
 static cudaError_t launch_pix2(const PixGemmParams& p, int num_sms, cudaStream_t stream) {
-  using L = Pix2Layout<BLOCK_N, S, NSTG>;
+  using L = Pix2Layout<BLOCK_N, S, NSTG, EG>;
   static_assert(L::kDyn <= 232448, "shared memory budget exceeded");
-  auto kern = pix_gemm2_kernel<BLOCK_N, S, NSTG>;
+  auto kern = pix_gemm2_kernel<BLOCK_N, S, NSTG, EG>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
@@ -629,7 +648,7 @@ static cudaError_t launch_pix2(const PixGemmParams& p, int num_sms, cudaStream_t
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(L::kThreadsTotal);
   cfg.dynamicSmemBytes = L::kDyn;
   cfg.stream = stream;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
@@ -676,9 +695,9 @@ static cudaError_t launch_pix(const PixGemmParams& p, int num_sms, cudaStream_t 
 cudaError_t launch_pix_gemm(const PixGemmParams& p, int block_n, int num_sms, cudaStream_t stream) {
   if (p.pair) {
     switch (block_n) {
-      case 64: return launch_pix2<64, 6, 2>(p, num_sms, stream);
-      case 128: return launch_pix2<128, 4, 2>(p, num_sms, stream);
-      case 256: return launch_pix2<256, 3, 1>(p, num_sms, stream);
+      case 64: return launch_pix2<64, 5, 2, 2>(p, num_sms, stream);
+      case 128: return launch_pix2<128, 4, 2, 2>(p, num_sms, stream);
+      case 256: return launch_pix2<256, 3, 1, 1>(p, num_sms, stream);
       default: return cudaErrorInvalidValue;
     }
   }
