@@ -289,7 +289,10 @@ struct cs_unet_plan {
   uint8_t* stats_begin;
   size_t stats_bytes;
   // optional per-launch timing of the tensor-core kernels (cs_unet_profile): CUDA events around each GEMM launch
-  bool profiling;
+  // internal streams of the backward pass (see cs_unet_backward)
+  cudaStream_t s_hi, s_lo;
+  cudaEvent_t ev_fork, ev_hi, ev_lo, ev_stage[CS_UNET_NUM_BWD_STAGES];
+  bool profiling, no_overlap;
   std::vector<cudaEvent_t> prof_events;   // pairs (begin, end)
   std::vector<int> prof_class;
   std::vector<double> prof_flops;
@@ -530,6 +533,14 @@ int cs_unet_plan_create(cs_unet_plan** out, int batch, int in_channels, int heig
 void cs_unet_plan_destroy(cs_unet_plan* plan) {
   if (!plan) return;
   for (cudaEvent_t e : plan->prof_events) cudaEventDestroy(e);
+  if (plan->s_hi) {
+    cudaStreamDestroy(plan->s_hi);
+    cudaStreamDestroy(plan->s_lo);
+    cudaEventDestroy(plan->ev_fork);
+    cudaEventDestroy(plan->ev_hi);
+    cudaEventDestroy(plan->ev_lo);
+    for (cudaEvent_t e : plan->ev_stage) cudaEventDestroy(e);
+  }
   delete plan;
 }
 
@@ -640,6 +651,34 @@ int cs_unet_stage_params(int stage, int* out_indices, int capacity) {
   return n;
 }
 
+// Stream layout of the backward pass.  The chain BN-backward -> dgrad -> BN-backward of the next layer is the
+// critical path; the weight-gradient GEMMs hang off it (they only produce parameter gradients).  They are therefore
+// issued on a second, lower-priority stream: their tensor-core work overlaps the HBM-bound BN-backward passes of the
+// following layers, and whenever both a dgrad and a wgrad are runnable the block scheduler serves the dgrad first.
+// Both internal streams are forked from / joined back into the caller's stream with events, so the call stays
+// asynchronous and stream-ordered for the caller (and capturable in a CUDA graph).  CARTSEG_OVERLAP=0 disables it.
+static bool use_overlap() {
+  static const bool v = [] {
+    const char* e = getenv("CARTSEG_OVERLAP");
+    return !(e && e[0] == '0');
+  }();
+  return v;
+}
+
+static int ensure_streams(cs_unet_plan* pl) {
+  if (pl->s_hi) return 0;
+  int lo = 0, hi = 0;
+  CS_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // lo = least priority (numerically greatest)
+  CS_CUDA(cudaStreamCreateWithPriority(&pl->s_hi, cudaStreamNonBlocking, hi));
+  CS_CUDA(cudaStreamCreateWithPriority(&pl->s_lo, cudaStreamNonBlocking, lo));
+  CS_CUDA(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
+  CS_CUDA(cudaEventCreateWithFlags(&pl->ev_hi, cudaEventDisableTiming));
+  CS_CUDA(cudaEventCreateWithFlags(&pl->ev_lo, cudaEventDisableTiming));
+  for (int i = 0; i < CS_UNET_NUM_BWD_STAGES; ++i)
+    CS_CUDA(cudaEventCreateWithFlags(&pl->ev_stage[i], cudaEventDisableTiming));
+  return 0;
+}
+
 int cs_unet_backward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* dlogits, int stage_begin, int stage_end,
                      int frozen_encoder_convs, cs_stream_t stream) {
   if (!pl || !pl->bound) return fail("plan is not bound to a workspace");
@@ -647,7 +686,17 @@ int cs_unet_backward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* dl
   if (stage_begin < 0 || stage_end > CS_UNET_NUM_BWD_STAGES || stage_begin > stage_end)
     return fail("bad stage range [%d, %d)", stage_begin, stage_end);
   if (frozen_encoder_convs < 0 || frozen_encoder_convs > 10) return fail("frozen_encoder_convs must be in [0, 10]");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaStream_t caller = static_cast<cudaStream_t>(stream);
+  cudaStream_t s = caller, sw = caller;      // s: critical path, sw: weight gradients
+  const bool overlap = use_overlap() && !pl->no_overlap;
+  if (overlap) {
+    CS_TRY(ensure_streams(pl));
+    s = pl->s_hi;
+    sw = pl->s_lo;
+    CS_CUDA(cudaEventRecord(pl->ev_fork, caller));
+    CS_CUDA(cudaStreamWaitEvent(s, pl->ev_fork, 0));
+    CS_CUDA(cudaStreamWaitEvent(sw, pl->ev_fork, 0));
+  }
   const int B = pl->B;
   for (int stage = stage_begin; stage < stage_end; ++stage) {
     int kind, idx;
@@ -670,24 +719,38 @@ int cs_unet_backward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* dl
       CS_CUDA(launch_bn_bwd_reduce(a, s));
       CS_CUDA(launch_bn_bwd_apply(a, s));
       if (t->grad[c.pw]) {
+        if (overlap) {                                    // dy is final: the wgrad may start on the side stream
+          CS_CUDA(cudaEventRecord(pl->ev_stage[stage], s));
+          CS_CUDA(cudaStreamWaitEvent(sw, pl->ev_stage[stage], 0));
+        }
         const size_t e = (size_t)(idx == 0 ? 1 : 9) * c.cout * c.cin;
-        CS_CUDA(cudaMemsetAsync(pl->dwp, 0, e * sizeof(float), s));
-        CS_CUDA(timed(pl, wgrad_class(c.bn_w), c.flops, s, [&] { return launch_wgrad_gemm(c.wg, c.bn_w, s); }));
-        if (idx == 0) CS_CUDA(launch_unpack_first(pl->dwp, c.cout, pl->Cin, t->grad[c.pw], s));
-        else CS_CUDA(launch_unpack_pairs(pl->dwp, c.cout, c.cin, 9, kTapWgrad, t->grad[c.pw], s));
+        CS_CUDA(cudaMemsetAsync(pl->dwp, 0, e * sizeof(float), sw));
+        CS_CUDA(timed(pl, wgrad_class(c.bn_w), c.flops, sw, [&] { return launch_wgrad_gemm(c.wg, c.bn_w, sw); }));
+        if (idx == 0) CS_CUDA(launch_unpack_first(pl->dwp, c.cout, pl->Cin, t->grad[c.pw], sw));
+        else CS_CUDA(launch_unpack_pairs(pl->dwp, c.cout, c.cin, 9, kTapWgrad, t->grad[c.pw], sw));
       }
       if (idx > 0 && idx > frozen_encoder_convs)
         CS_CUDA(timed(pl, pix_class(c.bn_d), c.flops, s, [&] { return launch_pix_gemm(c.dg, c.bn_d, pl->num_sms, s); }));
     } else {
       UpL& u = pl->up[idx];
-      if (t->grad[u.pb]) CS_CUDA(launch_channel_sum(u.g_out.p, u.g_out.pitch, u.g_out.c0, 4 * u.P, u.cout, t->grad[u.pb], s));
+      if (overlap && (t->grad[u.pb] || t->grad[u.pw])) {  // g_out of the conv-transpose is final on the main stream
+        CS_CUDA(cudaEventRecord(pl->ev_stage[stage], s));
+        CS_CUDA(cudaStreamWaitEvent(sw, pl->ev_stage[stage], 0));
+      }
+      if (t->grad[u.pb]) CS_CUDA(launch_channel_sum(u.g_out.p, u.g_out.pitch, u.g_out.c0, 4 * u.P, u.cout, t->grad[u.pb], sw));
       if (t->grad[u.pw]) {
-        CS_CUDA(cudaMemsetAsync(pl->dwp, 0, (size_t)4 * u.cin * u.cout * sizeof(float), s));
-        CS_CUDA(timed(pl, wgrad_class(u.bn_w), u.flops, s, [&] { return launch_wgrad_gemm(u.wg, u.bn_w, s); }));
-        CS_CUDA(launch_unpack_pairs(pl->dwp, u.cin, u.cout, 4, kTapIdent, t->grad[u.pw], s));
+        CS_CUDA(cudaMemsetAsync(pl->dwp, 0, (size_t)4 * u.cin * u.cout * sizeof(float), sw));
+        CS_CUDA(timed(pl, wgrad_class(u.bn_w), u.flops, sw, [&] { return launch_wgrad_gemm(u.wg, u.bn_w, sw); }));
+        CS_CUDA(launch_unpack_pairs(pl->dwp, u.cin, u.cout, 4, kTapIdent, t->grad[u.pw], sw));
       }
       CS_CUDA(timed(pl, pix_class(u.bn_d), u.flops, s, [&] { return launch_pix_gemm(u.dg, u.bn_d, pl->num_sms, s); }));
     }
+  }
+  if (overlap) {                                          // join: the caller's stream continues after both
+    CS_CUDA(cudaEventRecord(pl->ev_hi, s));
+    CS_CUDA(cudaEventRecord(pl->ev_lo, sw));
+    CS_CUDA(cudaStreamWaitEvent(caller, pl->ev_hi, 0));
+    CS_CUDA(cudaStreamWaitEvent(caller, pl->ev_lo, 0));
   }
   return 0;
 }
@@ -696,6 +759,12 @@ int cs_unet_profile(cs_unet_plan* pl, int enable) {
   if (!pl) return fail("plan is null");
   pl->profiling = enable != 0;
   pl->prof_used = 0;
+  return 0;
+}
+
+int cs_unet_set_overlap(cs_unet_plan* pl, int enable) {
+  if (!pl) return fail("plan is null");
+  pl->no_overlap = enable == 0;
   return 0;
 }
 

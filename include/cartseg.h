@@ -84,6 +84,10 @@ int cs_unet_backward(cs_unet_plan* plan, const cs_unet_tensors* t, const float* 
  * cs_unet_forward / cs_unet_backward is bracketed by CUDA events on the launch stream.  cs_unet_profile_read waits for
  * the recorded events and returns, per kernel class, the summed device time (ms), algorithmic FLOPs (2*MACs) and
  * launch count since the last read.  Classes: 0 pixel GEMM N=256, 1 N=128, 2 N=64, 3 weight-gradient GEMM N=128, 4 N=64. */
+/* cs_unet_backward runs the weight-gradient GEMMs on an internal lower-priority stream so that they overlap the
+ * HBM-bound BatchNorm-backward passes of the following layers (forked from / joined into `stream` with events).
+ * cs_unet_set_overlap(plan, 0) serialises everything on the caller's stream (used for per-kernel timing). */
+int cs_unet_set_overlap(cs_unet_plan* plan, int enable);
 #define CS_UNET_NUM_PROFILE_CLASSES 5
 int cs_unet_profile(cs_unet_plan* plan, int enable);
 int cs_unet_profile_read(cs_unet_plan* plan, int n_classes, double* ms, double* flops, long long* launches);
