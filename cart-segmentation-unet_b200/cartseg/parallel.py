@@ -107,3 +107,43 @@ def shard_batch(x: torch.Tensor, rank: int, world: int) -> torch.Tensor:
         raise ValueError(f"global batch {x.shape[0]} is not divisible by world size {world}")
     per = x.shape[0] // world
     return x[rank * per:(rank + 1) * per]
+
+
+class CudaPrefetcher:
+    """Wraps an iterable of (pinned) host batches — e.g. ``DataLoader(..., pin_memory=True)`` as every training script
+    of the reference builds it (train_bce_dice.py:284-287) — and stages batch i+1 on the device with a side stream
+    while step i computes, so the host->device copy of ``data.to(DEVICE)`` (train_bce_dice.py:329) leaves the
+    critical path.  Yields tuples of CUDA tensors that are safe to use on the current stream."""
+
+    def __init__(self, loader, device=None):
+        self.loader = loader
+        self.device = torch.device(device if device is not None else "cuda")
+        self.stream = torch.cuda.Stream(device=self.device)
+
+    def _stage(self, batch):
+        with torch.cuda.stream(self.stream):
+            out = tuple(t.to(self.device, non_blocking=True) if torch.is_tensor(t) else t for t in batch)
+        ev = torch.cuda.Event()
+        ev.record(self.stream)
+        return out, ev
+
+    def __iter__(self):
+        it = iter(self.loader)
+        try:
+            nxt = self._stage(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            cur, ev = nxt
+            try:
+                nxt = self._stage(next(it))
+            except StopIteration:
+                nxt = None
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            for t in cur:
+                if torch.is_tensor(t):
+                    t.record_stream(torch.cuda.current_stream(self.device))
+            yield cur
+
+    def __len__(self):
+        return len(self.loader)

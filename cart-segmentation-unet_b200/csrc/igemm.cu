@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) pix_gemm2_kernel(const __gri
     else tmem_alloc<L::kTmemCols>(tmem_ptr);
   }
   {
-    const int nvec = p.o_blocks_per_map * BLOCK_N;           // <= 1024
+    const int nvec = p.cols_per_map;                         // <= 1024
     for (int i = threadIdx.x; i < 1024; i += L::kThreadsTotal) {
       float a = 0.f, b = 0.f;
       if (!want_stats && i < nvec) {
@@ -513,14 +513,16 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) pix_gemm2_kernel(const __gri
       }
       int nb, b, w0, h0;
       const bool valid = decode(u, nb, b, w0, h0);
-      const int omap = nb / p.o_blocks_per_map;
-      const int n_in_map0 = (nb - omap * p.o_blocks_per_map) * BLOCK_N;
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
       for (int cb = 0; cb < BLOCK_N / 64; ++cb) {
+        // an n-block may span several output maps (conv-transpose: one map per (i,j) of the 2x2 kernel)
+        const int col0 = nb * BLOCK_N + cb * 64;
+        const int omap = col0 / p.cols_per_map;
+        const int nin = col0 - omap * p.cols_per_map;     // first channel of this 64-wide chunk inside its map
         uint8_t* sbuf = smem + L::kStage + (EG == 2 ? eg : (NSTG == 2 ? (int)(buf_ctr & 1) : 0)) * kStageBytes;
         ++buf_ctr;
         if (et == 0) {                                   // the store that last used this buffer has drained
@@ -542,8 +544,8 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) pix_gemm2_kernel(const __gri
         }
         uint32_t packed[32];
         if (affine) {
-          const float* sc = vec + n_in_map0 + cb * 64;
-          const float* sh = vec + 1024 + n_in_map0 + cb * 64;
+          const float* sc = vec + nin;
+          const float* sh = vec + 1024 + nin;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             float a = __uint_as_float(v[2 * i]) * sc[2 * i] + sh[2 * i];
@@ -566,7 +568,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) pix_gemm2_kernel(const __gri
         fence_proxy_async();
         bar_sync(2 + bar0, 128);
         if (et == 0 && valid) {
-          tma_store_4d(&p.tmapO[omap], sbuf, p.o_chan0 + n_in_map0 + cb * 64, w0, h0, b);
+          tma_store_4d(&p.tmapO[omap], sbuf, p.o_chan0 + nin, w0, h0, b);
           tma_store_commit();
         }
         if (want_stats) {
@@ -593,7 +595,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) pix_gemm2_kernel(const __gri
           float tot = 0.f;
 #pragma unroll
           for (int w4 = 0; w4 < 4; ++w4) tot += red[(w4 * 64 + c) * 2 + which];
-          gvec[which * 1024 + n_in_map0 + cb * 64 + c] += tot;
+          gvec[which * 1024 + nin + c] += tot;
         }
       }
       if (EG == 1) {
@@ -604,7 +606,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) pix_gemm2_kernel(const __gri
     if (et == 0) tma_store_wait_all<0>();
     if (want_stats) {
       bar_sync(1 + bar0, 128);
-      const int nvec = p.o_blocks_per_map * BLOCK_N;
+      const int nvec = p.cols_per_map;
       for (int i = et; i < nvec; i += 128) {
         const float s = gvec[i], q = gvec[1024 + i];
         if (q != 0.f) {

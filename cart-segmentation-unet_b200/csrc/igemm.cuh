@@ -32,6 +32,7 @@ struct PixGemmParams {
   int n_blocks;         // Ntot / BLOCK_N
   int tiles_w, tiles_h, batch;
   int H, W;             // extent of the tile grid's image (pixels past it are excluded from statistics)
+  int cols_per_map;     // output channels written through one output map (pair kernel: an n-block may span maps)
   int o_blocks_per_map; // n-blocks written through one output map
   int o_chan0;          // first output channel (coordinate offset inside the O maps)
   const float* scale;   // per output channel (index inside its map), may be null

@@ -111,6 +111,7 @@ static void pix_common(PixGemmParams& p, int B, int H, int W, int K, int Ntot, i
   p.H = H;
   p.W = W;
   p.o_blocks_per_map = p.n_blocks;
+  p.cols_per_map = Ntot;
   p.pair = use_pair() ? 1 : 0;
 }
 
@@ -147,13 +148,15 @@ static int build_pointwise(PixGemmParams& p, int* block_n, View in, int K, View 
 // (H, W) = input extents; `out` has twice the resolution.  wpack = [4][Cout][Cin].
 static int build_convT_fprop(PixGemmParams& p, int* block_n, View in, int Cin, View out, int Cout, const bf16* wpack,
                              const float* bias, int B, int H, int W) {
-  *block_n = pick_block_n(Cout);
+  // the pair kernel lets one n-block span several (i,j) output maps: N = 256 even for Cout = 64
+  *block_n = use_pair() ? pick_block_n(4 * Cout) : pick_block_n(Cout);
   pix_common(p, B, H, W, Cin, 4 * Cout, *block_n);
   p.G = 1;
   p.R = 1;
   p.a_chan0 = in.c0;
   p.o_chan0 = out.c0;
   p.o_blocks_per_map = Cout / *block_n;
+  p.cols_per_map = Cout;
   p.shift = bias;
   CS_TRY(nhwc_map(&p.tmapA[0], in.p, in.pitch, B, H, W, 16));
   CS_TRY(weight_map(&p.tmapB, wpack, Cin, 4 * Cout, *block_n));
