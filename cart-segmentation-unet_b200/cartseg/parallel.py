@@ -113,37 +113,52 @@ class CudaPrefetcher:
     """Wraps an iterable of (pinned) host batches — e.g. ``DataLoader(..., pin_memory=True)`` as every training script
     of the reference builds it (train_bce_dice.py:284-287) — and stages batch i+1 on the device with a side stream
     while step i computes, so the host->device copy of ``data.to(DEVICE)`` (train_bce_dice.py:329) leaves the
-    critical path.  Yields tuples of CUDA tensors that are safe to use on the current stream."""
+    critical path.  Two sets of device buffers are reused in turn (no allocator traffic per step); a yielded batch
+    stays valid until the batch after the next one is requested."""
 
     def __init__(self, loader, device=None):
         self.loader = loader
         self.device = torch.device(device if device is not None else "cuda")
         self.stream = torch.cuda.Stream(device=self.device)
+        self._slots = [None, None]
+        self._free = [None, None]           # event: the consumer has finished with the slot's previous contents
 
-    def _stage(self, batch):
+    def _stage(self, batch, slot):
+        bufs = self._slots[slot]
+        if bufs is None or len(bufs) != len(batch) or any(
+                torch.is_tensor(t) and (b is None or b.shape != t.shape or b.dtype != t.dtype)
+                for t, b in zip(batch, bufs)):
+            bufs = [torch.empty(t.shape, dtype=t.dtype, device=self.device) if torch.is_tensor(t) else None for t in batch]
+            self._slots[slot] = bufs
+        if self._free[slot] is not None:
+            self.stream.wait_event(self._free[slot])
         with torch.cuda.stream(self.stream):
-            out = tuple(t.to(self.device, non_blocking=True) if torch.is_tensor(t) else t for t in batch)
+            out = tuple(b.copy_(t, non_blocking=True) if torch.is_tensor(t) else t for t, b in zip(batch, bufs))
         ev = torch.cuda.Event()
         ev.record(self.stream)
         return out, ev
 
     def __iter__(self):
         it = iter(self.loader)
+        slot = 0
         try:
-            nxt = self._stage(next(it))
+            nxt = self._stage(next(it), slot)
         except StopIteration:
             return
         while nxt is not None:
             cur, ev = nxt
+            cur_slot = slot
+            slot ^= 1
             try:
-                nxt = self._stage(next(it))
+                nxt = self._stage(next(it), slot)
             except StopIteration:
                 nxt = None
-            torch.cuda.current_stream(self.device).wait_event(ev)
-            for t in cur:
-                if torch.is_tensor(t):
-                    t.record_stream(torch.cuda.current_stream(self.device))
+            cs = torch.cuda.current_stream(self.device)
+            cs.wait_event(ev)
             yield cur
+            done = torch.cuda.Event()          # everything the consumer enqueued on its stream for this batch
+            done.record(torch.cuda.current_stream(self.device))
+            self._free[cur_slot] = done
 
     def __len__(self):
         return len(self.loader)

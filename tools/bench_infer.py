@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""Pseudo-label generation throughput (workload K5, BASELINE.json config 5): eval-mode forward (BatchNorm folded into
+the conv epilogues) + on-device `sigmoid(logits) >= 0.5` uint8 mask, 3x224x224 inputs, batch sweep.
+Reference path: src/data_preprocessing/create_pseudo_labels_gpu.py:201-215,294.  Prints one JSON line per batch size."""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "cart-segmentation-unet_b200"))
+import cartseg                                   # noqa: E402
+from oracle import unet_oracle as O              # noqa: E402  (synthetic inputs only)
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--size", type=int, default=224)
+ap.add_argument("--batches", default="1,2,4,8,16,32,64,128,256,512")
+ap.add_argument("--iters", type=int, default=10)
+args = ap.parse_args()
+GFLOP_FWD = {224: 73.756, 512: 385.339}[args.size]
+
+torch.manual_seed(0)
+model = cartseg.UNet().cuda().eval()
+peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"] \
+    if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1400.0
+for B in [int(b) for b in args.batches.split(",")]:
+    x, _ = O.synth_batch(min(B, 8), args.size, args.size, seed=0)
+    x = x.repeat((B + x.shape[0] - 1) // x.shape[0], 1, 1, 1)[:B].contiguous().cuda()
+    x_h = x.cpu().pin_memory()
+
+    def run(src):
+        with torch.no_grad():
+            return cartseg.pseudo_label_mask(model(src), 0.5)
+
+    for _ in range(3):
+        run(x)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.iters):
+        m = run(x)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.iters
+    # end to end: pinned host images in, uint8 masks out (1 B/px D2H instead of the reference's 4 B/px probabilities)
+    out_h = torch.empty((B, args.size, args.size), dtype=torch.uint8).pin_memory()
+    xd = torch.empty_like(x)
+    import time
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.iters):
+        xd.copy_(x_h, non_blocking=True)
+        out_h.copy_(run(xd), non_blocking=True)
+    torch.cuda.synchronize()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / args.iters
+    tf = B / (ms / 1e3) * GFLOP_FWD / 1e3
+    print(json.dumps({"workload": f"pseudo-label inference 3x{args.size}x{args.size}", "batch": B, "ms": ms,
+                      "img_per_s": B / (ms / 1e3), "tflops": tf, "frac_of_sustained_bf16_peak": tf / peak,
+                      "e2e_img_per_s": B / (e2e_ms / 1e3), "fg_fraction": float(m.float().mean().item())}), flush=True)
+    cartseg.ops.release_plans()
+    torch.cuda.empty_cache()

@@ -28,6 +28,8 @@ for part in "$@"; do
     bench3) run bench_k3 900 python bench.py --steps 3 --warmup 3 --workload k3 --no-cpu-baseline ;;
     bench4) run bench_k4 900 python bench.py --steps 5 --warmup 3 --workload k4 --no-cpu-baseline ;;
     bench2gpu) run bench_2gpu 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 ;;
+    infer)  run bench_infer 900 python tools/bench_infer.py ;;
+    bench20) run bench 900 python bench.py ;;
     benchref) run bench_ref 600 python bench.py --impl reference --steps 3 --warmup 1 ;;
     launches) run profile_plain 300 python tools/profile_step.py && \
             run ncu_launches 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none \
