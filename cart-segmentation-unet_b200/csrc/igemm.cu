@@ -8,6 +8,7 @@
 // double-buffered accumulators), persistent static tile schedule.
 #include "igemm.cuh"
 
+#include <atomic>
 #include <mutex>
 
 #include "common.cuh"
@@ -18,6 +19,19 @@ static constexpr int kThreads = 192;
 static constexpr int kAtomBytes = 1024;            // 8 rows x 128 B: one 128B-swizzle atom
 static constexpr int kASlotBytes = 18 * kAtomBytes; // (16 + 2 halo) image rows of 8 pixels x 64 ch
 static constexpr int kStageBytes = 128 * 128;      // epilogue staging: 128 pixels x 64 ch bf16
+
+// Opt a kernel in to > 48 KB of dynamic shared memory once per device (bit mask of devices already done).
+template <typename K>
+static cudaError_t ensure_dynamic_smem(K kern, int bytes, std::atomic<unsigned long long>& done) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+  return e;
+}
 
 CS_DEVINL void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
@@ -631,12 +645,11 @@ static cudaError_t launch_pix2(const PixGemmParams& p, int num_sms, cudaStream_t
   using L = Pix2Layout<BLOCK_N, S, NSTG, EG>;
   static_assert(L::kDyn <= 232448, "shared memory budget exceeded");
   auto kern = pix_gemm2_kernel<BLOCK_N, S, NSTG, EG>;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDyn);
-  });
-  if (attr_err != cudaSuccess) return attr_err;
+  static std::atomic<unsigned long long> attr_done{0};   // per device: function attributes belong to the context
+  {
+    cudaError_t ae = ensure_dynamic_smem(kern, L::kDyn, attr_done);
+    if (ae != cudaSuccess) return ae;
+  }
   const int m_tiles = p.tiles_w * p.tiles_h * p.batch;
   const int units = ((m_tiles + 1) / 2) * p.n_blocks;
   if (units <= 0) return cudaSuccess;
@@ -663,12 +676,11 @@ static cudaError_t launch_pix(const PixGemmParams& p, int num_sms, cudaStream_t 
   using L = PixLayout<BLOCK_N, SA, SB, PAIR>;
   static_assert(L::kDyn <= 232448, "shared memory budget exceeded");
   auto kern = pix_gemm_kernel<BLOCK_N, SA, SB, PAIR>;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDyn);
-  });
-  if (attr_err != cudaSuccess) return attr_err;
+  static std::atomic<unsigned long long> attr_done{0};   // per device: function attributes belong to the context
+  {
+    cudaError_t ae = ensure_dynamic_smem(kern, L::kDyn, attr_done);
+    if (ae != cudaSuccess) return ae;
+  }
   const int m_tiles = p.tiles_w * p.tiles_h * p.batch;
   const int units = (PAIR ? (m_tiles + 1) / 2 : m_tiles) * p.n_blocks;
   if (units <= 0) return cudaSuccess;
@@ -860,12 +872,11 @@ static cudaError_t launch_wg(const WgradParams& p, cudaStream_t stream) {
   using L = WgLayout<BLOCK_N, STAGES>;
   static_assert(L::kDyn <= 232448, "shared memory budget exceeded");
   auto kern = wgrad_gemm_kernel<BLOCK_N, STAGES>;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDyn);
-  });
-  if (attr_err != cudaSuccess) return attr_err;
+  static std::atomic<unsigned long long> attr_done{0};   // per device: function attributes belong to the context
+  {
+    cudaError_t ae = ensure_dynamic_smem(kern, L::kDyn, attr_done);
+    if (ae != cudaSuccess) return ae;
+  }
   const int grid = p.m_blocks * p.n_blocks * p.G * p.splits;
   if (grid <= 0) return cudaSuccess;
   kern<<<grid, kThreads, L::kDyn, stream>>>(p);

@@ -1,0 +1,98 @@
+"""GPU parity at BASELINE.json's full sizes (K2: B=64 @224^2, K3: B=32 @512^2), where the CPU oracle cannot run the
+whole batch in seconds: per-sample comparisons where the computation is per-sample (eval-mode forward, EDT), and
+size-independent properties elsewhere (exact linearity of the backward pass in dlogits for power-of-two scalings,
+run-to-run reproducibility, Dice of thresholded masks)."""
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch_init_model(seed):
+    import cartseg
+    torch.manual_seed(seed)
+    return cartseg.UNet()
+
+
+@pytest.mark.parametrize("B,S,check", [(64, 224, (0, 37, 63)), (8, 512, (5,))])
+def test_eval_forward_full_batch_matches_oracle_per_sample(B, S, check):
+    """Eval-mode forward is per-sample independent (running statistics): samples of a full-size batch are compared
+    with the oracle one at a time; masks of those samples agree to Dice >= 0.999."""
+    import cartseg
+    from oracle import unet_oracle as O
+    x, _ = O.synth_batch(B, S, S, seed=11)
+    m = _torch_init_model(0)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m = m.cuda().eval()
+    with torch.no_grad():
+        z = m(x.cuda())
+        mask = cartseg.pseudo_label_mask(z, 0.5).cpu()
+        z = z.cpu()
+    for b in check:
+        with torch.no_grad():
+            ref = O.unet_logits(x[b:b + 1], {k: v.clone() for k, v in sd.items()}, training=False)
+        assert rel_l2(z[b:b + 1], ref) < 1e-2, b
+        rm = O.pseudo_label_mask(ref, 0.5)[0].bool()
+        gm = mask[b].bool()
+        if rm.any():
+            dice = 2.0 * (rm & gm).sum().item() / (rm.sum().item() + gm.sum().item())
+            assert dice >= 0.999, (b, dice)
+
+
+@pytest.mark.parametrize("B,S", [(64, 224), (32, 512)])
+def test_sdf_full_batch(B, S):
+    """EDT of a full K4-sized batch: a few images bit-exact against the oracle, and for every image the properties
+    that define a signed distance map (sign == class, zero only for degenerate images, |sdf| >= 1/max(H,W))."""
+    import cartseg
+    from oracle import unet_oracle as O
+    _, masks = O.synth_batch(B, S, S, seed=21)
+    masks[1] = 0.0
+    masks[2] = 1.0
+    got = cartseg.batch_sdf_from_masks(masks.cuda()).cpu()
+    for b in (0, 1, 2, B - 1):
+        ref = O.batch_sdf_from_masks(masks[b:b + 1])
+        assert np.array_equal(got[b:b + 1].numpy().view(np.uint32), ref.numpy().view(np.uint32)), b
+    fg = masks > 0.5
+    regular = torch.ones(B, dtype=torch.bool)
+    regular[1] = regular[2] = False
+    g = got[regular]
+    f = fg[regular]
+    assert (g[f] < 0).all() and (g[~f] > 0).all()
+    assert (g.abs() >= 1.0 / S - 1e-9).all()
+    assert (got[~regular] == 0).all()
+
+
+def test_train_step_full_k2_properties():
+    """K2 (B=64 @224^2, focal-Dice): the loss equals the oracle's loss on the GPU's own logits; the backward pass is
+    exactly linear in dlogits for a power-of-two scaling (bf16 and fp32 roundings commute with it — this is what makes
+    GradScaler's 2^16 safe); a repeated step reproduces the activation-gradient chain bit for bit."""
+    import cartseg
+    from oracle import unet_oracle as O
+    B, S = 64, 224
+    x, tgt = O.synth_batch(B, S, S, seed=31)
+    m = _torch_init_model(1).cuda().train()
+    crit = cartseg.FocalDiceLoss(0.5, 2.0, 1.0, 0.7)
+    xg, tg = x.cuda(), tgt.cuda()
+
+    def grads(scale):
+        m.zero_grad(set_to_none=True)
+        z = m(xg)
+        loss = crit(z, tg)
+        (loss * scale).backward()
+        return z.detach(), loss.item(), {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+
+    z1, l1, g1 = grads(1.0)
+    z2, l2, g2 = grads(1.0)
+    z3, l3, g3 = grads(65536.0)
+    assert torch.equal(z1, z2) and l1 == l2                              # forward bit-reproducible
+    ref_loss = O.focal_dice_loss(z1.cpu(), tgt, 0.5, 2.0, 1.0, 0.7).item()
+    assert abs(l1 - ref_loss) / ref_loss < 1e-5
+    for k in g1:
+        if g1[k].abs().max() == 0:
+            continue
+        assert rel_l2(g2[k], g1[k]) < 1e-4, k                             # fp32 atomic ordering only
+        assert rel_l2(g3[k] / 65536.0, g1[k]) < 1e-4, k                   # exact linearity in the loss scale
+        assert torch.isfinite(g3[k]).all(), k
