@@ -114,6 +114,7 @@ class UNet(nn.Module):
         self.final_conv = nn.Conv2d(64, out_channels, 1)
         self._dp_handle = 0
         self._weights_epoch = 0          # advanced by every training-mode forward (see ops._ensure_packed)
+        self._reserve_sms = 0            # SMs left to the NCCL kernels in data-parallel runs (parallel.init_data_parallel)
 
     # ---- groups the training scripts address (smp.Unet naming) --------------------------------
     @property
@@ -181,6 +182,8 @@ class UNet(nn.Module):
         plan = ops.get_plan(B, C, H, W, x.device, inference_only=not self.training)
         if self.training:
             self._weights_epoch += 1
+        if self._reserve_sms != plan.reserved_sms:
+            ops.set_plan_sm_reserve(plan, self._reserve_sms)
         if need_grad:
             frozen = self._frozen_encoder_convs(params)
             logits = ops.UNetFunction.apply(x, plan.id, True, frozen, self._dp_handle, self._weights_epoch,

@@ -36,6 +36,7 @@ class Plan:
         self.inference_only = inference_only
         self.generation = 0               # bumped by every training-mode forward
         self.pack_key = None              # identity + version of the weights currently packed
+        self.reserved_sms = 0
         self.handle = C.c_void_p()
         L = _lib.lib()
         check(L.cs_unet_plan_create(C.byref(self.handle), B, Cin, H, W, int(inference_only)), "cs_unet_plan_create")
@@ -85,6 +86,15 @@ def get_plan(B: int, Cin: int, H: int, W: int, device: torch.device, inference_o
     _PLANS[plan.id] = plan
     _PLAN_BY_KEY[key] = plan.id
     return plan
+
+
+def set_plan_sm_reserve(plan: Plan, reserve: int) -> None:
+    """Leave ``reserve`` SMs to other resident kernels (NCCL) by capping the persistent GEMM grids."""
+    n_sm = torch.cuda.get_device_properties(plan.device).multi_processor_count
+    with torch.cuda.device(plan.device):
+        check(_lib.lib().cs_unet_plan_set_sm_limit(plan.handle, n_sm - reserve if reserve > 0 else 0),
+              "cs_unet_plan_set_sm_limit")
+    plan.reserved_sms = reserve
 
 
 def release_plans() -> None:
@@ -237,10 +247,19 @@ def unet_backward(dlogits: Tensor, params: List[Tensor], plan_id: int, generatio
             check(L.cs_unet_backward(plan.handle, C.byref(t), ptr(dlogits), 0, _lib.NUM_BWD_STAGES,
                                      frozen_encoder_convs, stream), "cs_unet_backward")
         else:
-            for (s0, s1) in sync.stage_buckets(stage_off):
-                check(L.cs_unet_backward(plan.handle, C.byref(t), ptr(dlogits), s0, s1, frozen_encoder_convs, stream),
-                      "cs_unet_backward")
-                sync.reduce_async(flat[stage_off[s0]:stage_off[s1]])
+            # bucket by bucket; the join with the library's internal streams is deferred: only the communication
+            # stream waits per bucket, the compute stream once at the end
+            check(L.cs_unet_set_deferred_join(plan.handle, 1), "cs_unet_set_deferred_join")
+            try:
+                for (s0, s1) in sync.stage_buckets(stage_off):
+                    check(L.cs_unet_backward(plan.handle, C.byref(t), ptr(dlogits), s0, s1, frozen_encoder_convs,
+                                             stream), "cs_unet_backward")
+                    sync.reduce_async(flat[stage_off[s0]:stage_off[s1]],
+                                      wait=lambda cuda_stream: check(L.cs_unet_backward_wait(plan.handle, cuda_stream),
+                                                                     "cs_unet_backward_wait"))
+                check(L.cs_unet_backward_wait(plan.handle, stream), "cs_unet_backward_wait")
+            finally:
+                L.cs_unet_set_deferred_join(plan.handle, 0)
             sync.finish()
     return flat
 

@@ -295,7 +295,7 @@ struct cs_unet_plan {
   // internal streams of the backward pass (see cs_unet_backward)
   cudaStream_t s_hi, s_lo;
   cudaEvent_t ev_fork, ev_hi, ev_lo, ev_stage[CS_UNET_NUM_BWD_STAGES];
-  bool profiling, no_overlap;
+  bool profiling, no_overlap, deferred_join, join_pending;
   std::vector<cudaEvent_t> prof_events;   // pairs (begin, end)
   std::vector<int> prof_class;
   std::vector<double> prof_flops;
@@ -752,9 +752,34 @@ int cs_unet_backward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* dl
   if (overlap) {                                          // join: the caller's stream continues after both
     CS_CUDA(cudaEventRecord(pl->ev_hi, s));
     CS_CUDA(cudaEventRecord(pl->ev_lo, sw));
-    CS_CUDA(cudaStreamWaitEvent(caller, pl->ev_hi, 0));
-    CS_CUDA(cudaStreamWaitEvent(caller, pl->ev_lo, 0));
+    pl->join_pending = true;
+    if (!pl->deferred_join) CS_TRY(cs_unet_backward_wait(pl, stream));
   }
+  return 0;
+}
+
+int cs_unet_plan_set_sm_limit(cs_unet_plan* pl, int sms) {
+  if (!pl || !pl->bound) return fail("plan is not bound to a workspace");
+  int all = 0;
+  CS_TRY(device_sm_count(&all));
+  if (sms <= 0 || sms > all) sms = all;
+  pl->num_sms = sms & ~1;                                 // CTA pairs
+  if (pl->num_sms < 2) pl->num_sms = 2;
+  return 0;
+}
+
+int cs_unet_set_deferred_join(cs_unet_plan* pl, int enable) {
+  if (!pl) return fail("plan is null");
+  pl->deferred_join = enable != 0;
+  return 0;
+}
+
+int cs_unet_backward_wait(cs_unet_plan* pl, cs_stream_t stream) {
+  if (!pl) return fail("plan is null");
+  if (!pl->join_pending) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CS_CUDA(cudaStreamWaitEvent(st, pl->ev_hi, 0));
+  CS_CUDA(cudaStreamWaitEvent(st, pl->ev_lo, 0));
   return 0;
 }
 

@@ -88,6 +88,17 @@ int cs_unet_backward(cs_unet_plan* plan, const cs_unet_tensors* t, const float* 
  * HBM-bound BatchNorm-backward passes of the following layers (forked from / joined into `stream` with events).
  * cs_unet_set_overlap(plan, 0) serialises everything on the caller's stream (used for per-kernel timing). */
 int cs_unet_set_overlap(cs_unet_plan* plan, int enable);
+/* By default every cs_unet_backward call makes `stream` wait for its internal streams before returning.  A data-parallel
+ * caller that runs the stages bucket by bucket can defer that join (enable = 1): the calls then only enqueue work, and
+ * cs_unet_backward_wait(plan, some_stream) makes `some_stream` wait for everything enqueued so far — the communication
+ * stream waits per bucket, the caller's stream once after the last stage, so the weight-gradient overlap is not cut at
+ * bucket boundaries. */
+int cs_unet_set_deferred_join(cs_unet_plan* plan, int enable);
+/* The persistent implicit-GEMM kernels launch one CTA per SM and assume a single wave.  When another kernel (an NCCL
+ * all-reduce of the data-parallel path) holds some SMs for the whole step, cap the persistent grids at `sms` so that no
+ * CTA has to wait for a second wave (sms <= 0 restores the full device). */
+int cs_unet_plan_set_sm_limit(cs_unet_plan* plan, int sms);
+int cs_unet_backward_wait(cs_unet_plan* plan, cs_stream_t stream);
 #define CS_UNET_NUM_PROFILE_CLASSES 5
 int cs_unet_profile(cs_unet_plan* plan, int enable);
 int cs_unet_profile_read(cs_unet_plan* plan, int n_classes, double* ms, double* flops, long long* launches);
