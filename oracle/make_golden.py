@@ -68,6 +68,96 @@ def edge_masks(H, W, seed=0):
     return ms
 
 
+def load_reference_abl():
+    """Import the reference's ABL module (src/training/losses/{abl,label_smooth}.py) unchanged, on the CPU.
+    Three shims make that possible without touching its arithmetic: ``np.bool`` (removed from numpy, used at
+    abl.py:20) is aliased to ``np.bool_``; ``Tensor.cuda()`` (abl.py:87,134-135,193) returns the tensor itself;
+    the two files are loaded as a synthetic package so that the relative import at abl.py:8 resolves."""
+    import importlib.util
+    import types
+    import scipy.ndimage  # noqa: F401  (must be imported before np.bool is aliased)
+    import torchvision  # noqa: F401
+    if not hasattr(np, "bool"):
+        np.bool = np.bool_
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    base = os.path.join(REF, "src", "training", "losses")
+    pkg = types.ModuleType("ref_losses")
+    pkg.__path__ = [base]
+    sys.modules["ref_losses"] = pkg
+    mods = {}
+    for name in ("label_smooth", "abl"):
+        spec = importlib.util.spec_from_file_location("ref_losses." + name, os.path.join(base, name + ".py"))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules["ref_losses." + name] = m
+        spec.loader.exec_module(m)
+        mods[name] = m
+    return mods["abl"]
+
+
+def abl_cases():
+    """name -> (logits [B,1,H,W] fp32, targets [B,1,H,W] fp32 {0,1})"""
+    cases = {}
+    rng = np.random.Generator(np.random.PCG64(23))
+
+    def noisy(tgt, scale=2.0, gain=4.0):
+        z = rng.standard_normal(tgt.shape).astype(np.float32) * scale
+        return torch.from_numpy(z) + gain * (tgt - 0.5)
+
+    def shifted(tgt, dy, dx, scale=0.3, gain=6.0):
+        """logits of a prediction whose boundary lies (dy, dx) pixels away from the GT boundary"""
+        return noisy(torch.roll(tgt, shifts=(dy, dx), dims=(2, 3)), scale, gain)
+
+    _, t = O.synth_batch(1, 48, 64, seed=11)
+    cases["b1_48x64"] = (shifted(t, 3, -2), t)
+    _, t = O.synth_batch(2, 32, 48, seed=12)
+    cases["b2_32x48"] = (shifted(t, -2, 4), t)
+    _, t = O.synth_batch(3, 40, 40, seed=13)
+    cases["b3_40x40"] = (shifted(t, 5, 5, 0.1, 8.0), t)
+    _, t = O.synth_batch(4, 64, 64, seed=14)
+    t[1] = 0.0                                             # an image without any GT boundary (empty mask)
+    cases["b4_64x64_empty_gt"] = (shifted(t, 4, 0, 0.5, 5.0), t)
+    _, t = O.synth_batch(2, 64, 64, seed=16)
+    cases["b2_64x64_noisy"] = (noisy(t, 2.0, 4.0), t)     # heavy noise: the threshold ladder climbs far
+    _, d = O.synth_batch(1, 64, 64, seed=17)               # no GT boundary at all, B = 1 (scipy's no-zero EDT)
+    cases["b1_64x64_no_boundary"] = (noisy(d, 0.2, 6.0), torch.zeros_like(d))
+    t = torch.zeros(1, 1, 100, 100); t[0, 0, 5] = 1; t[0, 0, 50] = 1      # abl.py:232-236 smoke shape
+    cases["b1_100x100_lines"] = (noisy(t, 1.0, 0.0), t)
+    _, t = O.synth_batch(2, 32, 32, seed=15)
+    cases["b2_32x32_flat_logits"] = (torch.full_like(t, 0.3), t)          # empty predicted boundary -> None
+    return cases
+
+
+def make_abl():
+    import contextlib
+    import io
+    ref = load_reference_abl()
+    out = {}
+    for name, (logits, tgt) in abl_cases().items():
+        x = logits.clone().requires_grad_(True)
+        crit = ref.ABL()
+        with contextlib.redirect_stdout(io.StringIO()):
+            loss = crit(x, tgt)
+            p = torch.sigmoid(x.detach())
+            pb = crit.logits2boundary(torch.cat([1 - p, p], 1))
+            gb = crit.gt2boundary(tgt[:, 0].long(), ignore_label=crit.ignore_label)
+            dm = crit.get_dist_maps(gb)
+        out[name + "_logits"] = logits.numpy()
+        out[name + "_targets"] = np.packbits(tgt.numpy().astype(bool))
+        out[name + "_shape"] = np.array(logits.shape)
+        out[name + "_pred_boundary"] = np.packbits(pb.numpy())
+        out[name + "_gt_boundary"] = np.packbits(gb.numpy())
+        out[name + "_dist_maps"] = dm.numpy().astype(np.int16)            # [2B,H,W], integral values
+        if loss is None:
+            out[name + "_none"] = np.array(1)
+            continue
+        out[name + "_none"] = np.array(0)
+        out[name + "_value"] = np.float64(loss.item())
+        if torch.isfinite(loss):
+            loss.backward()
+            out[name + "_grad"] = x.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "abl.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
@@ -181,9 +271,14 @@ def main():
         model[f"{tag}_shape"] = np.array([B, 3, H, W])
     model["n_params"] = np.int64(sum(p.numel() for p in net.parameters()))
     np.savez_compressed(os.path.join(OUT, "model.npz"), **model)
+    make_abl()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1:                       # e.g. `make_golden.py abl`: regenerate one file only
+        for part in sys.argv[1:]:
+            globals()["make_" + part]()
+    else:
+        main()
