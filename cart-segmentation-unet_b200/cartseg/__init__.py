@@ -5,7 +5,7 @@ the ``cartseg::`` torch.library ops.  There is no CPU or PyTorch fallback: a mis
 """
 from ._lib import CartsegError, LIB_PATH, lib
 from . import ops
-from .modules import (BCEDiceLoss, BCEDiceLossPerSample, CompositeSegLoss, DoubleConv, FocalDiceLoss, FocalLoss,
+from .modules import (ABL, BCEDiceABL, BCEDiceLoss, BCEDiceLossPerSample, CompositeSegLoss, DoubleConv, FocalDiceLoss, FocalLoss,
                       SymmetricBoundaryLoss, UNet, batch_sdf_from_masks)
 from .metrics import (dice_iou_at_t, dice_metric, find_best_threshold, hard_dice_metric, hard_iou_metric, iou_metric,
                       precision_recall_f1, pseudo_label_mask, sweep_thresholds, threshold_sums)
@@ -16,7 +16,7 @@ lib()   # fail loudly at import time if the extension has not been built
 __all__ = [
     "CartsegError", "LIB_PATH", "lib", "ops", "parallel",
     "UNet", "DoubleConv", "BCEDiceLoss", "BCEDiceLossPerSample", "FocalLoss", "FocalDiceLoss",
-    "SymmetricBoundaryLoss", "CompositeSegLoss", "batch_sdf_from_masks",
+    "SymmetricBoundaryLoss", "CompositeSegLoss", "batch_sdf_from_masks", "ABL", "BCEDiceABL",
     "dice_metric", "iou_metric", "precision_recall_f1", "dice_iou_at_t", "hard_dice_metric", "hard_iou_metric",
     "sweep_thresholds", "threshold_sums", "find_best_threshold", "pseudo_label_mask",
 ]

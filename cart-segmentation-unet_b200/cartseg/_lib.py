@@ -40,6 +40,19 @@ class LossDesc(C.Structure):
     ]
 
 
+ABL_LADDER = 80
+
+
+class AblDesc(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int), ("height", C.c_int), ("width", C.c_int),
+        ("max_n", C.c_float), ("label_smoothing", C.c_float), ("max_clip_dist", C.c_float),
+        ("ignore_label", C.c_longlong),
+        ("per_image_maps", C.c_int),
+        ("eps_ladder", C.c_float * ABL_LADDER),
+    ]
+
+
 _P = C.c_void_p
 _SIGNATURES = {
     # name: (restype, argtypes)
@@ -68,6 +81,11 @@ _SIGNATURES = {
     "cs_loss_backward": (C.c_int, [C.POINTER(LossDesc), _P, _P, _P, _P, _P, _P, _P, _P]),
     "cs_threshold_stats": (C.c_int, [_P, _P, C.c_int, C.c_longlong, _P, C.c_int, _P, _P, _P]),
     "cs_threshold_mask": (C.c_int, [_P, C.c_longlong, C.c_float, _P, _P]),
+    "cs_abl_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "cs_abl_forward": (C.c_int, [C.POINTER(AblDesc), _P, _P, _P, _P, _P]),
+    "cs_abl_backward": (C.c_int, [C.POINTER(AblDesc), _P, _P, _P, _P, _P]),
+    "cs_abl_debug_read": (C.c_int, [C.POINTER(AblDesc), _P, C.POINTER(C.c_float), C.POINTER(C.c_int),
+                                    C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), _P, _P, _P]),
     "cs_layer_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "cs_conv3x3_fprop": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P, _P, _P]),
     "cs_conv3x3_dgrad": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P]),

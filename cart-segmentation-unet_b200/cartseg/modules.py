@@ -340,3 +340,76 @@ class CompositeSegLoss(nn.Module):
                          w_elem=(1 - w) * r.w, alpha=1.0, gamma=0.0,
                          w_dice=(1 - w) * (1 - r.w), smooth=r.smooth,
                          w_bgt=w * b.scale * b.w_gt, w_bpred=w * b.scale * b.w_pred, use_abs=b.use_abs)
+
+
+# =============================================================================================
+# Active Boundary Loss ("next" row N1): src/training/losses/abl.py, src/training/train_BCEDice_ABL.py
+# =============================================================================================
+class ABL(nn.Module):
+    """Drop-in for ``ABL`` (src/training/losses/abl.py:32-212), binary case ([B,1,H,W] logits, {0,1} targets).
+
+    Same constructor arguments.  ``forward`` returns the loss tensor, or ``None`` when the predicted boundary is empty
+    (abl.py:197-198) — deciding that costs one host read, exactly one where the reference has a dozen (its threshold
+    loop, ``nonzero`` and per-image scipy EDTs).  ``forward_with_valid`` returns ``(loss, valid)`` without any host
+    synchronisation; :class:`BCEDiceABL` uses it.  ``per_image_maps=True`` looks the GT distance up in image n's own
+    map instead of reproducing the reference's batch indexing (behaviour 3).
+    """
+
+    def __init__(self, isdetach: bool = True, max_N_ratio: float = 1 / 100, ignore_label: int = 255,
+                 label_smoothing: float = 0.2, weight=None, max_clip_dist: float = 20.0,
+                 per_image_maps: bool = False):
+        super().__init__()
+        if not isdetach:
+            raise NotImplementedError("ABL(isdetach=False): the reference never trains with attached neighbours")
+        if weight is not None:
+            raise NotImplementedError("ABL(weight=...) is only read by the label_smoothing == 0 branch of the reference")
+        self.isdetach = isdetach
+        self.max_N_ratio = max_N_ratio
+        self.ignore_label = ignore_label
+        self.label_smoothing = label_smoothing
+        self.max_clip_dist = max_clip_dist
+        self.per_image_maps = per_image_maps
+
+    def forward_with_valid(self, logits: Tensor, target: Tensor) -> Tuple[Tensor, Tensor]:
+        if target.dim() == 3:
+            target = target[:, None]
+        logits, target = _prep(logits, target)
+        loss, valid, _ = ops.abl_loss(logits, target, float(self.label_smoothing), float(self.max_N_ratio),
+                                      float(self.max_clip_dist), int(self.ignore_label), bool(self.per_image_maps))
+        return loss, valid
+
+    def forward(self, logits: Tensor, target: Tensor) -> Optional[Tensor]:
+        loss, valid = self.forward_with_valid(logits, target)
+        return loss if bool(valid.item()) else None
+
+
+class BCEDiceABL(nn.Module):
+    """Drop-in for ``BCEDiceABL`` (src/training/train_BCEDice_ABL.py:264-302): region (BCE+Dice) + abl_weight * ABL,
+    the region term alone when ABL has no valid boundary.  No host synchronisation in ``forward``; the
+    ``boundary_none_count`` / ``total_calls`` counters of the reference are kept as device tensors."""
+
+    def __init__(self, bce_weight: float = 0.5, smooth: float = 1.0, abl_weight: float = 0.1):
+        super().__init__()
+        self.region_loss = BCEDiceLoss(bce_weight=bce_weight, smooth=smooth)
+        self.boundary_loss = ABL()
+        self.abl_weight = abl_weight
+        self.total_calls = 0
+        self._none_count: Optional[Tensor] = None
+
+    @property
+    def boundary_none_count(self) -> int:
+        return 0 if self._none_count is None else int(self._none_count.item())
+
+    def components(self, logits: Tensor, targets: Tensor) -> dict:
+        region = self.region_loss(logits, targets)
+        boundary, valid = self.boundary_loss.forward_with_valid(logits, targets)
+        self.total_calls += 1
+        with torch.no_grad():
+            miss = 1.0 - valid
+            self._none_count = miss if self._none_count is None else self._none_count + miss
+        # valid == 0: boundary is 0 with a zero gradient, so the sum is the region term alone
+        total = region + self.abl_weight * boundary
+        return {"total": total, "region": region.detach(), "boundary": boundary.detach()}
+
+    def forward(self, logits: Tensor, targets: Tensor) -> Tensor:
+        return self.components(logits, targets)["total"]

@@ -398,6 +398,121 @@ def _seg_loss_bwd(ctx, grad_loss, grad_scratch):
 
 
 seg_loss.register_autograd(_seg_loss_bwd, setup_context=_seg_loss_setup)
+# under torch.autocast the loss takes float32 like the reference's native op (label_smooth.py:63 custom_fwd(cast_inputs=float32))
+seg_loss.register_autocast("cuda", torch.float32)
+
+
+# =============================================================================================
+# Active Boundary Loss (src/training/losses/abl.py:66-212)
+# =============================================================================================
+def abl_eps_ladder() -> List[float]:
+    """The thresholds the reference's ``while True: eps *= 1.2`` loop (abl.py:78-83) visits, computed the way Python
+    does (float64 products); the C side rounds them to float32, which is what the tensor comparison sees."""
+    out, e = [], 1e-5
+    for _ in range(_lib.ABL_LADDER):
+        out.append(e)
+        e *= 1.2
+    return out
+
+
+def _abl_desc(B: int, H: int, W: int, label_smoothing: float, max_n_ratio: float, max_clip_dist: float,
+              ignore_label: int, per_image_maps: bool) -> "_lib.AblDesc":
+    import numpy as np
+    d = _lib.AblDesc()
+    d.batch, d.height, d.width = B, H, W
+    d.max_n = float(np.float32((H * W) * max_n_ratio))        # abl.py:69; compared in float32 by torch
+    d.label_smoothing, d.max_clip_dist = label_smoothing, max_clip_dist
+    d.ignore_label, d.per_image_maps = ignore_label, int(per_image_maps)
+    for i, e in enumerate(abl_eps_ladder()):
+        d.eps_ladder[i] = e
+    return d
+
+
+def _check_abl_inputs(logits: Tensor, targets: Tensor) -> Tuple[int, int, int]:
+    if not (logits.is_cuda and targets.is_cuda):
+        raise CartsegError("cartseg::abl_loss takes CUDA tensors only (no CPU fallback)")
+    if logits.dim() != 4 or logits.shape[1] != 1:
+        raise CartsegError("abl_loss: logits must be [B,1,H,W] (the binary case the reference trains)")
+    if logits.dtype != torch.float32 or targets.dtype != torch.float32:
+        raise CartsegError("abl_loss: logits and targets must be float32")
+    if not (logits.is_contiguous() and targets.is_contiguous()) or targets.numel() != logits.numel():
+        raise CartsegError("abl_loss: logits / targets must be contiguous and of the same size")
+    return logits.shape[0], logits.shape[2], logits.shape[3]
+
+
+def _abl_scratch(B: int, H: int, W: int, device) -> Tensor:
+    n = int(_lib.lib().cs_abl_scratch_bytes(B, H, W))
+    return torch.empty(n, dtype=torch.uint8, device=device)       # torch's caching allocator aligns to 512 B
+
+
+@torch.library.custom_op("cartseg::abl_loss", mutates_args=(), device_types="cuda")
+def abl_loss(logits: Tensor, targets: Tensor, label_smoothing: float, max_n_ratio: float, max_clip_dist: float,
+             ignore_label: int, per_image_maps: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    """Returns (loss [], valid [] (1.0 / 0.0: the reference returns None when 0), scratch)."""
+    B, H, W = _check_abl_inputs(logits, targets)
+    scratch = _abl_scratch(B, H, W, logits.device)
+    out = torch.empty(2, dtype=torch.float32, device=logits.device)
+    d = _abl_desc(B, H, W, label_smoothing, max_n_ratio, max_clip_dist, ignore_label, per_image_maps)
+    with torch.cuda.device(logits.device):
+        check(_lib.lib().cs_abl_forward(C.byref(d), ptr(logits), ptr(targets), ptr(scratch), ptr(out),
+                                        _lib.current_stream()), "cs_abl_forward")
+    return out[0].clone(), out[1].clone(), scratch
+
+
+@abl_loss.register_fake
+def _(logits, targets, label_smoothing, max_n_ratio, max_clip_dist, ignore_label, per_image_maps):
+    B, H, W = logits.shape[0], logits.shape[2], logits.shape[3]
+    return (logits.new_empty(()), logits.new_empty(()),
+            logits.new_empty(B * H * W * 10 + 4096, dtype=torch.uint8))
+
+
+@torch.library.custom_op("cartseg::abl_loss_backward", mutates_args=(), device_types="cuda")
+def abl_loss_backward(grad_out: Tensor, logits: Tensor, scratch: Tensor, label_smoothing: float, max_n_ratio: float,
+                      max_clip_dist: float, ignore_label: int, per_image_maps: bool) -> Tensor:
+    B, H, W = logits.shape[0], logits.shape[2], logits.shape[3]
+    go = grad_out.to(torch.float32).contiguous().reshape(-1)
+    dlogits = torch.empty_like(logits)
+    d = _abl_desc(B, H, W, label_smoothing, max_n_ratio, max_clip_dist, ignore_label, per_image_maps)
+    with torch.cuda.device(logits.device):
+        check(_lib.lib().cs_abl_backward(C.byref(d), ptr(logits), ptr(scratch), ptr(go), ptr(dlogits),
+                                         _lib.current_stream()), "cs_abl_backward")
+    return dlogits
+
+
+@abl_loss_backward.register_fake
+def _(grad_out, logits, *args):
+    return torch.empty_like(logits)
+
+
+def _abl_setup(ctx, inputs, output):
+    ctx.scalars = inputs[2:]
+    ctx.save_for_backward(inputs[0], output[2])
+
+
+def _abl_bwd(ctx, grad_loss, grad_valid, grad_scratch):
+    logits, scratch = ctx.saved_tensors
+    return (torch.ops.cartseg.abl_loss_backward(grad_loss, logits, scratch, *ctx.scalars),) + (None,) * 6
+
+
+abl_loss.register_autograd(_abl_bwd, setup_context=_abl_setup)
+abl_loss.register_autocast("cuda", torch.float32)
+
+
+def abl_debug(logits: Tensor, scratch: Tensor, per_image_maps: bool = False):
+    """Test hook: (eps, ladder index, kept pixels, predicted-boundary pixels, distance map [B,H,W] uint16 (numpy),
+    kl map [B,H,W] float32 (numpy)) of the forward call that filled ``scratch``.  Synchronises."""
+    import numpy as np
+    B, H, W = logits.shape[0], logits.shape[2], logits.shape[3]
+    d = _abl_desc(B, H, W, 0.2, 0.01, 20.0, 255, per_image_maps)
+    eps, k = C.c_float(), C.c_int()
+    kept, nb = C.c_ulonglong(), C.c_ulonglong()
+    dm = np.empty((B, H, W), np.uint16)
+    kl = np.empty((B, H, W), np.float32)
+    with torch.cuda.device(logits.device):
+        check(_lib.lib().cs_abl_debug_read(C.byref(d), ptr(scratch), C.byref(eps), C.byref(k), C.byref(kept),
+                                           C.byref(nb), dm.ctypes.data, kl.ctypes.data, _lib.current_stream()),
+              "cs_abl_debug_read")
+    return eps.value, k.value, kept.value, nb.value, dm, kl
 
 
 # =============================================================================================

@@ -110,4 +110,19 @@ cudaError_t launch_threshold_stats(const float* logits, const float* targets, in
                                    int K, double* counts, double* soft, cudaStream_t s);
 cudaError_t launch_threshold_mask(const float* logits, long long n, float xstar, uint8_t* mask, cudaStream_t s);
 
+// ---- Active Boundary Loss (binary case) ------------------------------------------------------
+// src/training/losses/abl.py:66-212 + label_smooth.py:14-57.  ladder: the thresholds the reference's adaptive
+// loop can visit (host-computed so that they are the same float32 values); loss_out = {loss, valid}.
+static constexpr int kAblLadder = 80;
+struct AblLadder { float v[kAblLadder]; };
+size_t abl_scratch_bytes(int B, int H, int W);
+cudaError_t launch_abl_forward(const float* logits, const float* targets, int B, int H, int W, const AblLadder& ladder,
+                               float max_n, float smoothing, float max_clip, long long ignore_label, int faithful,
+                               void* scratch, float* loss_out, cudaStream_t s);
+cudaError_t launch_abl_backward(const float* logits, int B, int H, int W, float smoothing, float max_clip,
+                                const void* scratch, const float* grad_out, float* dlogits, cudaStream_t s);
+// test hook (synchronises): threshold chosen, counters, the distance map and the KL map of the last forward
+cudaError_t abl_debug_read(const void* scratch, int B, int H, int W, float* eps, int* k, unsigned long long* kept,
+                           unsigned long long* pred_boundary, unsigned short* dmap_out, float* kl_out, cudaStream_t s);
+
 }  // namespace cs

@@ -915,6 +915,53 @@ int cs_threshold_mask(const float* logits, long long n, float xstar, uint8_t* ma
 }
 
 // ---------------------------------------------------------------------------------------------
+// Active Boundary Loss
+// ---------------------------------------------------------------------------------------------
+size_t cs_abl_scratch_bytes(int batch, int height, int width) { return abl_scratch_bytes(batch, height, width); }
+
+static int abl_check(const cs_abl_desc* d) {
+  if (!d) return fail("abl descriptor is null");
+  if (d->batch < 1 || d->height < 2 || d->width < 2) return fail("abl: batch >= 1 and H, W >= 2 required");
+  if (!(d->max_clip_dist > 0.f)) return fail("abl: max_clip_dist must be positive");
+  if (d->label_smoothing < 0.f || d->label_smoothing >= 1.f) return fail("abl: label_smoothing must be in [0, 1)");
+  return 0;
+}
+
+int cs_abl_forward(const cs_abl_desc* d, const float* logits, const float* targets, void* scratch, float* loss_out,
+                   cs_stream_t stream) {
+  CS_TRY(abl_check(d));
+  if (!logits || !targets || !scratch || !loss_out) return fail("cs_abl_forward: null pointer");
+  if ((uintptr_t)scratch & 255) return fail("cs_abl_forward: scratch must be 256-byte aligned");
+  AblLadder lad;
+  for (int i = 0; i < kAblLadder; ++i) lad.v[i] = d->eps_ladder[i];
+  for (int i = 1; i < kAblLadder; ++i)
+    if (!(lad.v[i] > lad.v[i - 1])) return fail("abl: eps_ladder must be strictly increasing");
+  CS_CUDA(launch_abl_forward(logits, targets, d->batch, d->height, d->width, lad, d->max_n, d->label_smoothing,
+                             d->max_clip_dist, d->ignore_label, d->per_image_maps ? 0 : 1, scratch, loss_out,
+                             static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int cs_abl_backward(const cs_abl_desc* d, const float* logits, const void* scratch, const float* grad_out,
+                    float* dlogits, cs_stream_t stream) {
+  CS_TRY(abl_check(d));
+  if (!logits || !scratch || !dlogits) return fail("cs_abl_backward: null pointer");
+  CS_CUDA(launch_abl_backward(logits, d->batch, d->height, d->width, d->label_smoothing, d->max_clip_dist, scratch,
+                              grad_out, dlogits, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int cs_abl_debug_read(const cs_abl_desc* d, const void* scratch, float* eps, int* ladder_index, unsigned long long* kept,
+                      unsigned long long* pred_boundary, uint16_t* dist_map_host, float* kl_map_host,
+                      cs_stream_t stream) {
+  CS_TRY(abl_check(d));
+  if (!scratch) return fail("cs_abl_debug_read: null pointer");
+  CS_CUDA(abl_debug_read(scratch, d->batch, d->height, d->width, eps, ladder_index, kept, pred_boundary, dist_map_host,
+                         kl_map_host, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Single-layer entry points (tests / micro-benchmarks).  scratch = [fprop pack | dgrad pack | fp32 dW pack]
 // ---------------------------------------------------------------------------------------------
 size_t cs_layer_scratch_bytes(int cin, int cout) {

@@ -160,6 +160,41 @@ int cs_threshold_stats(const float* logits, const float* targets, int rows, long
 int cs_threshold_mask(const float* logits, long long n, float xstar, uint8_t* mask, cs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Active Boundary Loss, binary case.  Replaces ABL.forward
+ * (src/training/losses/abl.py:66-212) with its LabelSmoothSoftmaxCEV1 criterion
+ * (src/training/losses/label_smooth.py:14-57): the latest training recipe of the reference,
+ * src/training/train_BCEDice_ABL.py:264-302.  No host synchronisation: the adaptive KL threshold of
+ * abl.py:78-83 is found on the device from a histogram over `eps_ladder` (the float32 values
+ * 1e-5 * 1.2^k the reference's loop visits, computed by the host in float64 exactly as Python does),
+ * and the scipy EDT of abl.py:16-24 runs as an exact integer EDT on the device.
+ *   loss_out[0] = mean over kept boundary pixels of weight * CE (NaN when none is kept, as torch.mean of
+ *                 an empty tensor), loss_out[1] = 1 if the predicted boundary is non-empty, else 0 — the case
+ *                 in which the reference returns None (abl.py:197-198) and the caller skips the term.
+ * per_image_maps == 0 reproduces the reference's distance-map indexing (map of batch entry n = channel n%2
+ * of image n/2, abl.py:166-167 + 121); != 0 uses image n's own map.
+ * ---------------------------------------------------------------------------------------------- */
+#define CS_ABL_LADDER 80
+typedef struct cs_abl_desc {
+  int batch, height, width;
+  float max_n;                 /* float32(H*W*max_N_ratio), abl.py:69 */
+  float label_smoothing;       /* 0.2 */
+  float max_clip_dist;         /* 20 */
+  long long ignore_label;      /* 255 */
+  int per_image_maps;
+  float eps_ladder[CS_ABL_LADDER];
+} cs_abl_desc;
+size_t cs_abl_scratch_bytes(int batch, int height, int width);
+/* logits, targets: fp32 [B,1,H,W] (targets are truncated to integers like target.long()); scratch 256-byte aligned. */
+int cs_abl_forward(const cs_abl_desc* d, const float* logits, const float* targets, void* scratch, float* loss_out,
+                   cs_stream_t stream);
+/* dlogits = grad_out[0] * d loss / d logits (zero when the loss was invalid); scratch from the forward call. */
+int cs_abl_backward(const cs_abl_desc* d, const float* logits, const void* scratch, const float* grad_out,
+                    float* dlogits, cs_stream_t stream);
+/* Test hook (synchronises `stream`): chosen threshold, counters, and the [B,H,W] distance / KL maps copied to HOST. */
+int cs_abl_debug_read(const cs_abl_desc* d, const void* scratch, float* eps, int* ladder_index, unsigned long long* kept,
+                      unsigned long long* pred_boundary, uint16_t* dist_map_host, float* kl_map_host, cs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Single-layer entry points (unit tests / micro-benchmarks of the tcgen05 kernels).  Activations
  * are NHWC bf16; weights fp32 in the reference layout; `scratch` must hold the packed copies
  * (cs_layer_scratch_bytes).  dw is fp32 in the reference layout.

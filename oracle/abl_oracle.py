@@ -108,7 +108,7 @@ def pred_boundary(probs2: Tensor, max_n_ratio: float = 0.01) -> Tuple[Tensor, in
     kl_lr = torch.zeros(B, H, W, dtype=probs2.dtype)
     kl_lr[:, :, :-1] = _kl(probs2[:, :, :, 1:], probs2[:, :, :, :-1])
     kl = kl_lr + kl                                        # reference adds lr + ud in this order
-    max_n = H * W * max_n_ratio
+    max_n = float(np.float32(H * W * max_n_ratio))        # torch compares a float32 tensor with a Python scalar in float32
     ladder = eps_ladder()
     k = 0
     while float((kl > float(ladder[k])).sum()) > max_n:
