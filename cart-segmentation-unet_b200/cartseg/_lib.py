@@ -86,6 +86,10 @@ _SIGNATURES = {
     "cs_abl_backward": (C.c_int, [C.POINTER(AblDesc), _P, _P, _P, _P, _P]),
     "cs_abl_debug_read": (C.c_int, [C.POINTER(AblDesc), _P, C.POINTER(C.c_float), C.POINTER(C.c_int),
                                     C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), _P, _P, _P]),
+    "cs_ensemble_accumulate": (C.c_int, [_P, C.c_float, C.c_longlong, C.c_int, _P, _P]),
+    "cs_pseudo_qc": (C.c_int, [_P, C.c_int, C.c_longlong, C.c_float, C.c_int, _P, _P, _P]),
+    "cs_mask_cleanup_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "cs_mask_cleanup": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "cs_layer_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "cs_conv3x3_fprop": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P, _P, _P]),
     "cs_conv3x3_dgrad": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P]),

@@ -125,4 +125,16 @@ cudaError_t launch_abl_backward(const float* logits, int B, int H, int W, float 
 cudaError_t abl_debug_read(const void* scratch, int B, int H, int W, float* eps, int* k, unsigned long long* kept,
                            unsigned long long* pred_boundary, unsigned short* dmap_out, float* kl_out, cudaStream_t s);
 
+// ---- pseudo-label post-processing -------------------------------------------------------------
+// probs = (first ? 0 : probs) + w * sigmoid(logits)      (create_pseudo_labels_gpu.py:201-215)
+cudaError_t launch_ensemble_accumulate(const float* logits, float w, long long n, int first, float* probs, cudaStream_t s);
+// per image: mask = probs >= thr (written as mask_value / 0, may be NULL); stats[b] = {fg pixels, median(|p-0.5|*2),
+// mean entropy, n}   (create_pseudo_labels_gpu.py:294-300)
+cudaError_t launch_pseudo_qc(const float* probs, int B, long long n, float thr, int mask_value, uint8_t* mask,
+                             double* stats, cudaStream_t s);
+// fg = mask > bin_thr; optional corner flood-fill hole filling; optional largest 8-connected component; out {0,255}
+size_t mask_cleanup_scratch_bytes(int B, int H, int W);
+cudaError_t launch_mask_cleanup(const uint8_t* mask, int B, int H, int W, int bin_thr, int fill_holes, int keep_largest,
+                                uint8_t* out, void* scratch, cudaStream_t s);
+
 }  // namespace cs

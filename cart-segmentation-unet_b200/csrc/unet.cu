@@ -962,6 +962,40 @@ int cs_abl_debug_read(const cs_abl_desc* d, const void* scratch, float* eps, int
 }
 
 // ---------------------------------------------------------------------------------------------
+// Pseudo-label post-processing
+// ---------------------------------------------------------------------------------------------
+int cs_ensemble_accumulate(const float* logits, float weight, long long n, int first, float* probs, cs_stream_t stream) {
+  if (!logits || !probs) return fail("cs_ensemble_accumulate: null pointer");
+  if (n < 1) return fail("cs_ensemble_accumulate: empty input");
+  CS_CUDA(launch_ensemble_accumulate(logits, weight, n, first, probs, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int cs_pseudo_qc(const float* probs, int batch, long long n, float threshold, int mask_value, uint8_t* mask,
+                 double* stats, cs_stream_t stream) {
+  if (!probs || !stats) return fail("cs_pseudo_qc: null pointer");
+  if (batch < 1 || n < 1) return fail("cs_pseudo_qc: empty input");
+  if (mask_value < 1 || mask_value > 255) return fail("cs_pseudo_qc: mask_value must be in 1..255");
+  CS_CUDA(launch_pseudo_qc(probs, batch, n, threshold, mask_value, mask, stats, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+size_t cs_mask_cleanup_scratch_bytes(int batch, int height, int width) {
+  return mask_cleanup_scratch_bytes(batch, height, width);
+}
+
+int cs_mask_cleanup(const uint8_t* mask, int batch, int height, int width, int bin_threshold, int fill_holes,
+                    int keep_largest, uint8_t* out, void* scratch, cs_stream_t stream) {
+  if (!mask || !out || !scratch) return fail("cs_mask_cleanup: null pointer");
+  if (batch < 1 || height < 1 || width < 1) return fail("cs_mask_cleanup: empty input");
+  if ((long long)batch * height * width >= 0x7fffffffLL) return fail("cs_mask_cleanup: more than 2^31 pixels per call");
+  if ((uintptr_t)scratch & 255) return fail("cs_mask_cleanup: scratch must be 256-byte aligned");
+  CS_CUDA(launch_mask_cleanup(mask, batch, height, width, bin_threshold, fill_holes, keep_largest, out, scratch,
+                              static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Single-layer entry points (tests / micro-benchmarks).  scratch = [fprop pack | dgrad pack | fp32 dW pack]
 // ---------------------------------------------------------------------------------------------
 size_t cs_layer_scratch_bytes(int cin, int cout) {

@@ -195,6 +195,26 @@ int cs_abl_debug_read(const cs_abl_desc* d, const void* scratch, float* eps, int
                       unsigned long long* pred_boundary, uint16_t* dist_map_host, float* kl_map_host, cs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Pseudo-label post-processing: what the reference does on the HOST with the
+ * probabilities it copies back at 4 B/px (src/data_preprocessing/create_pseudo_labels_gpu.py:201-215,
+ * 294-300) and in its mask clean-up tools (src/data_preprocessing/clean_masks.py:12-32,
+ * src/data_preprocessing/remove_blops.py:14-33).
+ * ---------------------------------------------------------------------------------------------- */
+/* probs[i] = (first ? 0 : probs[i]) + weight * sigmoid(logits[i])   — ensemble_forward, one call per model. */
+int cs_ensemble_accumulate(const float* logits, float weight, long long n, int first, float* probs, cs_stream_t stream);
+/* Per image b of n pixels: mask = (probs >= threshold) written as mask_value/0 (mask may be NULL), and
+ * stats[b] = { foreground pixel count, median(|p - 0.5| * 2) (exact, numpy's even-count rule),
+ *              mean binary entropy of clip(p, 1e-6, 1 - 1e-6), n }. */
+int cs_pseudo_qc(const float* probs, int batch, long long n, float threshold, int mask_value, uint8_t* mask,
+                 double* stats, cs_stream_t stream);
+/* fg = mask > bin_threshold.  fill_holes: background the 4-connected flood fill from pixel (0,0) cannot reach becomes
+ * foreground (a foreground (0,0) makes everything foreground — cv2.floodFill semantics of clean_masks.py:16-22).
+ * keep_largest: only the largest 8-connected component survives (ties: OpenCV's lowest label).  out is {0,255}. */
+size_t cs_mask_cleanup_scratch_bytes(int batch, int height, int width);
+int cs_mask_cleanup(const uint8_t* mask, int batch, int height, int width, int bin_threshold, int fill_holes,
+                    int keep_largest, uint8_t* out, void* scratch, cs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Single-layer entry points (unit tests / micro-benchmarks of the tcgen05 kernels).  Activations
  * are NHWC bf16; weights fp32 in the reference layout; `scratch` must hold the packed copies
  * (cs_layer_scratch_bytes).  dw is fp32 in the reference layout.

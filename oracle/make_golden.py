@@ -27,10 +27,11 @@ REF = "/root/reference"
 OUT = os.path.join(ROOT, "tests", "golden")
 
 
-def lift(relpath: str, names):
+def lift(relpath: str, names, extra=None):
     src = open(os.path.join(REF, relpath)).read()
     tree = ast.parse(src)
     ns = {"torch": torch, "nn": nn, "np": np, "F": torch.nn.functional}
+    ns.update(extra or {})
     from scipy.ndimage import distance_transform_edt
     ns["distance_transform_edt"] = distance_transform_edt
     got = []
@@ -42,6 +43,10 @@ def lift(relpath: str, names):
     missing = set(names) - set(got)
     assert not missing, f"{relpath}: missing {missing}"
     return ns
+
+
+def lift_with(relpath, names, extra):
+    return lift(relpath, names, extra)
 
 
 def edge_masks(H, W, seed=0):
@@ -158,6 +163,71 @@ def make_abl():
     np.savez_compressed(os.path.join(OUT, "abl.npz"), **out)
 
 
+def postproc_masks():
+    """name -> uint8 {0,255} masks exercising holes, ties, a foreground corner, enclosed background, emptiness"""
+    rng = np.random.Generator(np.random.PCG64(77))
+    out = {}
+    m = np.zeros((32, 48), np.uint8); m[4:20, 6:30] = 255; m[8:12, 10:16] = 0; m[14, 20] = 0; m[25:29, 38:44] = 255
+    out["holes_and_blob"] = m
+    m = np.zeros((16, 24), np.uint8); m[1, 0] = m[2, 0] = 255; m[0, 5] = m[0, 6] = 255; m[9:11, 9] = 255
+    out["three_way_tie"] = m
+    m = np.zeros((16, 24), np.uint8); m[1, 4] = m[2, 4] = 255; m[0, 9] = m[0, 10] = 255
+    out["tie_block_order"] = m
+    m = np.zeros((24, 24), np.uint8); m[0:6, 0:6] = 255; m[12:20, 12:20] = 255
+    out["fg_corner"] = m
+    m = np.zeros((24, 32), np.uint8); m[:, 14:17] = 255; m[5:9, 22:28] = 255; m[6:8, 24:26] = 0
+    out["stripe_cuts_background"] = m
+    out["empty"] = np.zeros((16, 16), np.uint8)
+    out["full"] = np.full((16, 16), 255, np.uint8)
+    m = np.zeros((20, 20), np.uint8); m[3:9, 3:9] = 255; m[9, 9] = 255; m[10:15, 10:15] = 255; m[11:14, 11:14] = 0
+    out["diagonal_touch"] = m                  # 8-connected through one corner; hole closed only 4-connectedly
+    m = np.zeros((20, 20), np.uint8); m[2:12, 2:12] = 255; m[4:10, 4:10] = 0; m[10, 10] = 0; m[11, 11] = 0
+    out["hole_leaks_diagonally"] = m           # background escapes only through a diagonal: stays a hole (4-conn fill)
+    for i, p in enumerate((0.35, 0.5, 0.62)):
+        out[f"bernoulli_{i}"] = ((rng.random((64, 64)) < p) * 255).astype(np.uint8)
+    yy, xx = np.mgrid[0:224, 0:224]
+    blobs = np.zeros((224, 224), bool)
+    for _ in range(9):
+        cy, cx, r = rng.integers(10, 214), rng.integers(10, 214), rng.integers(4, 40)
+        blobs |= (yy - cy) ** 2 + (xx - cx) ** 2 <= r * r
+    blobs &= rng.random((224, 224)) > 0.03
+    out["blobs_224"] = (blobs * 255).astype(np.uint8)
+    m = out["blobs_224"].copy(); m[m == 255] = 200; m[5:9, 5:9] = 100      # grey levels: > 127 vs > 0 binarisation
+    out["grey_levels_224"] = m
+    return out
+
+
+def make_postproc():
+    import cv2
+    cm = lift_with("src/data_preprocessing/clean_masks.py", ["clean_mask"], {"cv2": cv2})
+    rb = lift_with("src/data_preprocessing/remove_blops.py", ["clean_mask_largest_component"], {"cv2": cv2})
+    pl = lift_with("src/data_preprocessing/create_pseudo_labels_gpu.py", ["entropy_map"], {})
+    out = {}
+    for name, m in postproc_masks().items():
+        out[name + "_mask"] = m
+        out[name + "_clean"] = cm["clean_mask"](m.copy())
+        out[name + "_largest"] = rb["clean_mask_largest_component"](m.copy())
+    # QC scores: the expressions of create_pseudo_labels_gpu.py:294-299 evaluated with the reference's entropy_map
+    rng = np.random.Generator(np.random.PCG64(78))
+    for name, (H, W) in {"qc_a": (64, 64), "qc_b": (37, 51), "qc_c": (96, 128)}.items():
+        _, t = O.synth_batch(1, H if H % 2 == 0 else H + 1, W if W % 2 == 0 else W + 1, seed=H)
+        t = t[0, 0, :H, :W].numpy()
+        z1 = (rng.standard_normal((H, W)) * 1.5 + 5.0 * (t - 0.5)).astype(np.float32)
+        z2 = (rng.standard_normal((H, W)) * 2.5 + 3.0 * (t - 0.4)).astype(np.float32)
+        z1[0, :4] = [0.0, 40.0, -40.0, 1e-7]
+        w = np.array([0.7, 0.3], dtype=np.float32); w = (w / w.sum()).tolist()             # :167-171
+        p = [torch.sigmoid(torch.from_numpy(z)) for z in (z1, z2)]
+        probs = (p[0].mul_(w[0])).add_(p[1], alpha=w[1]).numpy()                          # :211-214 (fp32 on the CPU)
+        pred01 = (probs >= 0.5).astype(np.uint8)                                          # :294
+        out[name + "_logits"] = np.stack([z1, z2])
+        out[name + "_probs"] = probs
+        out[name + "_pred01"] = np.packbits(pred01)
+        out[name + "_fg_area"] = np.float64(float(pred01.mean()))                         # :298
+        out[name + "_fg_conf"] = np.float64(float(np.median(np.abs(probs - 0.5) * 2.0)))  # :299
+        out[name + "_mean_ent"] = np.float64(float(pl["entropy_map"](probs).mean()))      # :300
+    np.savez_compressed(os.path.join(OUT, "postproc.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
@@ -272,6 +342,7 @@ def main():
     model["n_params"] = np.int64(sum(p.numel() for p in net.parameters()))
     np.savez_compressed(os.path.join(OUT, "model.npz"), **model)
     make_abl()
+    make_postproc()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
