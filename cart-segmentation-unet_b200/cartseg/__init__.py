@@ -11,6 +11,8 @@ from .metrics import (dice_iou_at_t, dice_metric, find_best_threshold, hard_dice
                       precision_recall_f1, pseudo_label_mask, sweep_thresholds, threshold_sums)
 from . import parallel
 from . import postproc
+from . import preproc
+from .preproc import letterbox_resize_normalize, resize_masks
 from .postproc import (clean_mask, clean_mask_largest_component, ensemble_forward, pseudo_label_qc, should_accept)
 
 lib()   # fail loudly at import time if the extension has not been built
@@ -21,5 +23,6 @@ __all__ = [
     "SymmetricBoundaryLoss", "CompositeSegLoss", "batch_sdf_from_masks", "ABL", "BCEDiceABL",
     "dice_metric", "iou_metric", "precision_recall_f1", "dice_iou_at_t", "hard_dice_metric", "hard_iou_metric",
     "sweep_thresholds", "threshold_sums", "find_best_threshold", "pseudo_label_mask",
+    "preproc", "letterbox_resize_normalize", "resize_masks",
     "postproc", "ensemble_forward", "pseudo_label_qc", "should_accept", "clean_mask", "clean_mask_largest_component",
 ]

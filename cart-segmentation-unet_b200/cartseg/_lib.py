@@ -53,6 +53,16 @@ class AblDesc(C.Structure):
     ]
 
 
+class ImageDesc(C.Structure):
+    _fields_ = [
+        ("data", C.c_void_p),
+        ("height", C.c_int), ("width", C.c_int), ("pitch", C.c_int),
+        ("canvas_h", C.c_int), ("canvas_w", C.c_int),
+        ("x0", C.c_int), ("y0", C.c_int),
+        ("reserved", C.c_int),
+    ]
+
+
 _P = C.c_void_p
 _SIGNATURES = {
     # name: (restype, argtypes)
@@ -90,6 +100,10 @@ _SIGNATURES = {
     "cs_pseudo_qc": (C.c_int, [_P, C.c_int, C.c_longlong, C.c_float, C.c_int, _P, _P, _P]),
     "cs_mask_cleanup_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "cs_mask_cleanup": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "cs_letterbox_geometry": (C.c_int, [C.c_int, C.c_int, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                        C.POINTER(C.c_int)]),
+    "cs_preproc_images": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, _P, _P]),
+    "cs_preproc_masks": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "cs_layer_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "cs_conv3x3_fprop": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P, _P, _P]),
     "cs_conv3x3_dgrad": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P]),

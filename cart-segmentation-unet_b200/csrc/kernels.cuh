@@ -137,4 +137,18 @@ size_t mask_cleanup_scratch_bytes(int B, int H, int W);
 cudaError_t launch_mask_cleanup(const uint8_t* mask, int B, int H, int W, int bin_thr, int fill_holes, int keep_largest,
                                 uint8_t* out, void* scratch, cudaStream_t s);
 
+// ---- input side: letterbox + resize + normalise ------------------------------------------------
+// One descriptor per image (array in DEVICE memory; same layout as cs_image_desc of include/cartseg.h).
+struct ImageDesc {
+  const uint8_t* data;          // HWC uint8 (3 channels) or HW uint8 (masks)
+  int height, width, pitch;     // pitch in bytes
+  int canvas_h, canvas_w;       // size of the (virtual) letterboxed canvas the resize reads
+  int x0, y0;                   // position of the image inside the canvas
+  int reserved;
+};
+struct Norm3 { float mean255[3]; float inv_std255[3]; };
+cudaError_t launch_preproc_images(const ImageDesc* descs, int B, int S, const Norm3& nrm, int bgr, float* out,
+                                  cudaStream_t s);
+cudaError_t launch_preproc_masks(const ImageDesc* descs, int B, int S, float* out, cudaStream_t s);
+
 }  // namespace cs

@@ -17,6 +17,8 @@
 #include <new>
 #include <vector>
 
+#include <cmath>
+
 #include "../../include/cartseg.h"
 #include "igemm.cuh"
 #include "kernels.cuh"
@@ -992,6 +994,45 @@ int cs_mask_cleanup(const uint8_t* mask, int batch, int height, int width, int b
   if ((uintptr_t)scratch & 255) return fail("cs_mask_cleanup: scratch must be 256-byte aligned");
   CS_CUDA(launch_mask_cleanup(mask, batch, height, width, bin_threshold, fill_holes, keep_largest, out, scratch,
                               static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Input side
+// ---------------------------------------------------------------------------------------------
+static_assert(sizeof(cs_image_desc) == sizeof(ImageDesc), "cs_image_desc and ImageDesc must have the same layout");
+
+int cs_letterbox_geometry(int height, int width, double side_padding_ratio, int* canvas, int* x0, int* y0) {
+  if (height < 1 || width < 1 || !canvas || !x0 || !y0) return fail("cs_letterbox_geometry: bad arguments");
+  const int side = (int)nearbyint((double)width * side_padding_ratio);   // Python round(): half to even
+  const int pw = width + 2 * side;
+  const int L = pw > height ? pw : height;
+  *canvas = L;
+  *x0 = (L - pw) / 2 + side;
+  *y0 = (L - height) / 2;
+  return 0;
+}
+
+int cs_preproc_images(const cs_image_desc* descs_device, int batch, int out_size, const float mean[3],
+                      const float std_[3], int bgr, float* out_nchw, cs_stream_t stream) {
+  if (!descs_device || !mean || !std_ || !out_nchw) return fail("cs_preproc_images: null pointer");
+  if (batch < 1 || batch > 65535 || out_size < 1 || out_size > 65535) return fail("cs_preproc_images: bad batch / size");
+  Norm3 n;
+  for (int c = 0; c < 3; ++c) {
+    if (!(std_[c] > 0.f)) return fail("cs_preproc_images: std must be positive");
+    n.mean255[c] = (float)((double)mean[c] * 255.0);
+    n.inv_std255[c] = (float)(1.0 / ((double)std_[c] * 255.0));
+  }
+  CS_CUDA(launch_preproc_images(reinterpret_cast<const ImageDesc*>(descs_device), batch, out_size, n, bgr, out_nchw,
+                                static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int cs_preproc_masks(const cs_image_desc* descs_device, int batch, int out_size, float* out, cs_stream_t stream) {
+  if (!descs_device || !out) return fail("cs_preproc_masks: null pointer");
+  if (batch < 1 || batch > 65535 || out_size < 1 || out_size > 65535) return fail("cs_preproc_masks: bad batch / size");
+  CS_CUDA(launch_preproc_masks(reinterpret_cast<const ImageDesc*>(descs_device), batch, out_size, out,
+                               static_cast<cudaStream_t>(stream)));
   return 0;
 }
 

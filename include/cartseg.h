@@ -215,6 +215,29 @@ int cs_mask_cleanup(const uint8_t* mask, int batch, int height, int width, int b
                     int keep_largest, uint8_t* out, void* scratch, cs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Input side: what the reference's Dataset does per image on the CPU —
+ * letterbox_image_with_side_padding (train_bce_dice.py:42-85), cv2.resize INTER_LINEAR / INTER_NEAREST
+ * (:147-148), A.Resize + A.Normalize + ToTensorV2 (:171-176; create_pseudo_labels_gpu.py:113-117) — for a
+ * whole batch of variable-size uint8 images in one launch.  The resize is OpenCV's 8-bit bilinear kernel
+ * bit for bit; the letterboxed canvas is virtual (taps outside the image read black).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cs_image_desc {
+  const uint8_t* data;       /* device pointer: HWC uint8 with 3 channels (images) or HW uint8 (masks) */
+  int height, width, pitch;  /* pitch = bytes per row */
+  int canvas_h, canvas_w;    /* size of the letterboxed canvas (= height, width when there is none) */
+  int x0, y0;                /* where the image sits inside the canvas */
+  int reserved;
+} cs_image_desc;
+/* Host helper: canvas side and offsets of train_bce_dice.py:56-80 (side padding = Python round(width * ratio)). */
+int cs_letterbox_geometry(int height, int width, double side_padding_ratio, int* canvas, int* x0, int* y0);
+/* descs_device: `batch` descriptors in DEVICE memory.  out_nchw: fp32 [batch,3,out_size,out_size] =
+ * (resized - mean*255) * (1/(std*255)); bgr != 0 reverses the channel order first (cv2.imread -> RGB). */
+int cs_preproc_images(const cs_image_desc* descs_device, int batch, int out_size, const float mean[3],
+                      const float std_[3], int bgr, float* out_nchw, cs_stream_t stream);
+/* Masks: nearest-neighbour resize of each HW uint8 image to out_size^2, divided by 255 -> fp32 [batch,1,S,S]. */
+int cs_preproc_masks(const cs_image_desc* descs_device, int batch, int out_size, float* out, cs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Single-layer entry points (unit tests / micro-benchmarks of the tcgen05 kernels).  Activations
  * are NHWC bf16; weights fp32 in the reference layout; `scratch` must hold the packed copies
  * (cs_layer_scratch_bytes).  dw is fp32 in the reference layout.

@@ -228,6 +228,34 @@ def make_postproc():
     np.savez_compressed(os.path.join(OUT, "postproc.npz"), **out)
 
 
+def make_preproc():
+    """Run the reference's letterbox function and OpenCV's resize on seeded uint8 images; store inputs compactly
+    (small images) and the resized uint8 outputs."""
+    import cv2
+    tb = lift_with("train_bce_dice.py", ["letterbox_image_with_side_padding"], {"SIDE_PADDING_RATIO": 0.1})
+    rng = np.random.Generator(np.random.PCG64(91))
+    out = {}
+    shapes = {"wide": (60, 96), "tall": (120, 50), "square": (64, 64), "tiny_up": (20, 30), "odd": (75, 101),
+              "x2": (112, 93)}
+    sizes = {"tiny_up": (56, 224), "odd": (56, 224)}
+    for name, (H, W) in shapes.items():
+        base = rng.integers(0, 256, (H // 4 + 2, W // 4 + 2, 3)).astype(np.uint8)          # smooth-ish content
+        img = cv2.resize(base, (W, H), interpolation=cv2.INTER_CUBIC)
+        img = np.clip(img.astype(int) + rng.integers(-20, 21, img.shape), 0, 255).astype(np.uint8)
+        if name == "x2":                                   # letterboxed side 112 = 2 * 56: the area fast path
+            assert tb["letterbox_image_with_side_padding"](img, (0, 0, 0), 0.1).shape[0] == 112
+        lb = tb["letterbox_image_with_side_padding"](img, padding_color=(0, 0, 0), side_padding_ratio=0.1)
+        out[name + "_image"] = img
+        out[name + "_letterbox_side"] = np.array(lb.shape[0])
+        for S in sizes.get(name, (56,)):
+            out[f"{name}_resized_{S}"] = cv2.resize(lb, (S, S), interpolation=cv2.INTER_LINEAR)
+        m = ((rng.random((H, W)) < 0.4) * 255).astype(np.uint8)
+        out[name + "_mask"] = np.packbits(m > 0)
+        for S in sizes.get(name, (56,)):
+            out[f"{name}_mask_{S}"] = np.packbits(cv2.resize(m, (S, S), interpolation=cv2.INTER_NEAREST) > 0)
+    np.savez_compressed(os.path.join(OUT, "preproc.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
@@ -343,6 +371,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "model.npz"), **model)
     make_abl()
     make_postproc()
+    make_preproc()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -21,6 +21,7 @@ for part in "$@"; do
     sdf)    run test_gpu_sdf 600 python -m pytest tests/test_gpu_sdf.py -m gpu -q --tb=short -s --timeout 300 ;;
     abl)    run test_gpu_abl 600 python -m pytest tests/test_gpu_abl.py -m gpu -q --tb=short -s --timeout 300 ;;
     postproc) run test_gpu_postproc 600 python -m pytest tests/test_gpu_postproc.py -m gpu -q --tb=short -s --timeout 300 ;;
+    preproc) run test_gpu_preproc 600 python -m pytest tests/test_gpu_preproc.py -m gpu -q --tb=short -s --timeout 300 ;;
     losses) run test_gpu_losses 600 python -m pytest tests/test_gpu_losses.py -m gpu -q --tb=short -s --timeout 300 ;;
     layers) run test_gpu_layers 900 python -m pytest tests/test_gpu_layers.py -m gpu -q --tb=short -s --timeout 300 ;;
     stages) run test_gpu_unet_stages 1200 python -m pytest tests/test_gpu_unet_stages.py -m gpu -q --tb=short -s --timeout 600 ;;
