@@ -17,13 +17,11 @@
 //                         neighbours are detached: abl.py:144-145).
 // Reference behaviours kept on purpose are listed in oracle/abl_oracle.py (distance-map batch indexing, scipy's
 // EDT of an input without zeros, label smoothing mass 1 - s/8).
-#include "common.cuh"
-#include "kernels.cuh"
+#include "edt.cuh"
 
 namespace cs {
 
 static constexpr int kLadder = kAblLadder;      // thresholds 1e-5 * 1.2^k, k < 80 (the last ones exceed any KL)
-static constexpr int kInfD = 30000;
 static constexpr int kPadDist = 100000;         // abl.py:116 max_dis
 
 struct AblResult {                              // lives at the start of the scratch buffer
@@ -127,38 +125,17 @@ __global__ void __launch_bounds__(256) abl_kl_kernel(const float* __restrict__ l
 // ------------------------------------------------------------------------------------------------ 2. distance maps
 CS_DEVINL long long label_of(float t) { return (long long)t; }      // target.long(): truncation (abl.py:177)
 
-// One thread per column of one source image: vertical distance to the nearest boundary / non-boundary pixel.
-__global__ void abl_columns_kernel(const float* __restrict__ targets, int nimg, int H, int W, long long ignore_label,
-                                   ushort2* __restrict__ g, int* __restrict__ flags) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= nimg * W) return;
-  const int b = idx / W, x = idx - b * W;
-  const float* col = targets + (size_t)b * H * W + x;
-  ushort2* gc = g + (size_t)b * H * W + x;
-  int any_b = 0, any_n = 0;
-  int db = kInfD, dn = kInfD;
-  long long cur = label_of(__ldg(col));
-  for (int y = 0; y < H; ++y) {
-    const long long below = y + 1 < H ? label_of(__ldg(col + (size_t)(y + 1) * W)) : cur;
-    const long long right = x + 1 < W ? label_of(__ldg(col + (size_t)y * W + 1)) : cur;
-    const bool bnd = (below != cur) || (right != cur) || (cur == ignore_label);    // abl.py:94-107
-    db = bnd ? 0 : min(db + 1, kInfD);
-    dn = bnd ? min(dn + 1, kInfD) : 0;
-    any_b |= bnd; any_n |= !bnd;
-    gc[(size_t)y * W] = make_ushort2((unsigned short)db, (unsigned short)dn);
-    cur = below;
+// GT boundary (abl.py:94-107): the label differs from the pixel below or the pixel to the right, or is the ignore label.
+struct BoundaryPred {
+  const float* targets; long long ignore_label; int H, W;
+  __device__ bool operator()(int img, int y, int x) const {
+    const float* p = targets + ((size_t)img * H + y) * W + x;
+    const long long cur = label_of(__ldg(p));
+    const long long below = y + 1 < H ? label_of(__ldg(p + W)) : cur;
+    const long long right = x + 1 < W ? label_of(__ldg(p + 1)) : cur;
+    return below != cur || right != cur || cur == ignore_label;
   }
-  db = kInfD; dn = kInfD;
-  for (int y = H - 1; y >= 0; --y) {
-    const ushort2 d = gc[(size_t)y * W];
-    const bool bnd = d.x == 0;
-    db = bnd ? 0 : min(db + 1, kInfD);
-    dn = bnd ? min(dn + 1, kInfD) : 0;
-    gc[(size_t)y * W] = make_ushort2((unsigned short)min((int)d.x, db), (unsigned short)min((int)d.y, dn));
-  }
-  if (any_b) atomicOr(&flags[2 * b], 1);
-  if (any_n) atomicOr(&flags[2 * b + 1], 1);
-}
+};
 
 CS_DEVINL int isqrt_floor(int v) {
   int r = (int)sqrtf((float)v);
@@ -167,41 +144,46 @@ CS_DEVINL int isqrt_floor(int v) {
   return r;
 }
 
-// One block per row of a source image.  faithful: image i feeds map 2i (channel 0: non-boundary pixels get
-// floor(dist to boundary) - 1) and map 2i+1 (channel 1: boundary pixels get floor(dist to non-boundary) - 1), the
-// layout the reference's torch.cat over [2,H,W] maps produces (abl.py:166-167).  Otherwise map i = channel 0 of image i.
-__global__ void abl_rows_kernel(const ushort2* __restrict__ g, const int* __restrict__ flags, int B, int H, int W,
-                                int faithful, unsigned short* __restrict__ dmap) {
-  extern __shared__ int srow[];                 // [2][W]
-  const int row = blockIdx.x;                   // img*H + y
-  const int img = row / H, y = row - img * H;
-  const ushort2* gr = g + (size_t)row * W;
-  for (int x = threadIdx.x; x < W; x += blockDim.x) {
-    const ushort2 d = gr[x];
-    srow[x] = (int)d.x * (int)d.x;
-    srow[W + x] = (int)d.y * (int)d.y;
-  }
-  __syncthreads();
-  const bool has_b = flags[2 * img] != 0, has_n = flags[2 * img + 1] != 0;
-  const int n0 = faithful ? 2 * img : img, n1 = faithful ? 2 * img + 1 : -1;
-  for (int x = threadIdx.x; x < W; x += blockDim.x) {
-    const bool bnd = srow[x] == 0;
-    const int* opp = bnd ? (srow + W) : srow;
-    int best;
-    if (bnd ? has_n : has_b) {
-      best = opp[x];
-      for (int d = 1; d < W && d * d < best; ++d) {
-        const int d2 = d * d;
-        if (x - d >= 0) best = min(best, d2 + opp[x - d]);
-        if (x + d < W) best = min(best, d2 + opp[x + d]);
-      }
-    } else {
-      best = (y + 1) * (y + 1) + x * x;         // scipy's EDT of an input without any zero pixel
-    }
+// faithful: image i feeds map 2i (channel 0: non-boundary pixels get floor(dist to boundary) - 1) and map 2i+1
+// (channel 1: boundary pixels get floor(dist to non-boundary) - 1), the layout the reference's torch.cat over [2,H,W]
+// maps produces (abl.py:166-167).  Otherwise map i = channel 0 of image i.
+struct AblDistEpilogue {
+  unsigned short* dmap; int B, H, W, faithful;
+  __device__ void operator()(int img, int y, int x, bool bnd, int best_sq, bool has_b, bool has_n) const {
+    // scipy's EDT of an input without any zero pixel measures from (row -1, column 0)
+    const int best = (bnd ? has_n : has_b) ? best_sq : (y + 1) * (y + 1) + x * x;
     const int v = max(isqrt_floor(best) - 1, 0);
+    const int n0 = faithful ? 2 * img : img, n1 = faithful ? 2 * img + 1 : -1;
     if (n0 < B) dmap[((size_t)n0 * H + y) * W + x] = bnd ? 0 : (unsigned short)v;
     if (n1 >= 0 && n1 < B) dmap[((size_t)n1 * H + y) * W + x] = bnd ? (unsigned short)v : 0;
   }
+};
+
+// Fallback for images taller than the segmented column pass supports.
+__global__ void abl_columns_serial_kernel(BoundaryPred pred, int nimg, int H, int W, ushort2* __restrict__ g,
+                                          int* __restrict__ flags) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nimg * W) return;
+  const int b = idx / W, x = idx - b * W;
+  ushort2* gc = g + (size_t)b * H * W + x;
+  int any_b = 0, any_n = 0, db = kEdtInf, dn = kEdtInf;
+  for (int y = 0; y < H; ++y) {
+    const bool bnd = pred(b, y, x);
+    db = bnd ? 0 : min(db + 1, kEdtInf);
+    dn = bnd ? min(dn + 1, kEdtInf) : 0;
+    any_b |= bnd; any_n |= !bnd;
+    gc[(size_t)y * W] = make_ushort2((unsigned short)db, (unsigned short)dn);
+  }
+  db = kEdtInf; dn = kEdtInf;
+  for (int y = H - 1; y >= 0; --y) {
+    const ushort2 d = gc[(size_t)y * W];
+    const bool bnd = d.x == 0;
+    db = bnd ? 0 : min(db + 1, kEdtInf);
+    dn = bnd ? min(dn + 1, kEdtInf) : 0;
+    gc[(size_t)y * W] = make_ushort2((unsigned short)min((int)d.x, db), (unsigned short)min((int)d.y, dn));
+  }
+  if (any_b) atomicOr(&flags[2 * b], 1);
+  if (any_n) atomicOr(&flags[2 * b + 1], 1);
 }
 
 // ------------------------------------------------------------------------------------------------ 3./4. loss
@@ -357,7 +339,7 @@ static int grid_1d(long long work, int per_block) {
 cudaError_t launch_abl_forward(const float* logits, const float* targets, int B, int H, int W, const AblLadder& ladder,
                                float max_n, float smoothing, float max_clip, long long ignore_label, int faithful,
                                void* scratch, float* loss_out, cudaStream_t s) {
-  if (H >= kInfD || W >= kInfD) return cudaErrorInvalidValue;
+  if (H >= kEdtInf || W >= kEdtInf) return cudaErrorInvalidValue;
   const AblBuffers a = carve(scratch, B, H, W);
   cudaError_t e = cudaMemsetAsync(a.res, 0, sizeof(AblResult), s);
   if (e != cudaSuccess) return e;
@@ -367,10 +349,18 @@ cudaError_t launch_abl_forward(const float* logits, const float* targets, int B,
   const int nimg = faithful ? (B + 1) / 2 : B;
   e = cudaMemsetAsync(a.flags, 0, (size_t)nimg * 8, s);
   if (e != cudaSuccess) return e;
-  abl_columns_kernel<<<(nimg * W + 63) / 64, 64, 0, s>>>(targets, nimg, H, W, ignore_label, a.g, a.flags);
+  const BoundaryPred pred{targets, ignore_label, H, W};
+  int nseg = 0, rps = 0;
+  if (edt_column_geometry(H, &nseg, &rps)) {
+    edt_columns_kernel<<<nimg * ((W + 31) / 32), dim3(32, nseg), 0, s>>>(pred, nimg, H, W, rps, a.g, a.flags);
+  } else {
+    abl_columns_serial_kernel<<<(nimg * W + 63) / 64, 64, 0, s>>>(pred, nimg, H, W, a.g, a.flags);
+  }
   if ((e = launched()) != cudaSuccess) return e;
+  const AblDistEpilogue epi{a.dmap, B, H, W, faithful};
   const int threads = W >= 256 ? 256 : ((W + 31) / 32) * 32;
-  abl_rows_kernel<<<nimg * H, threads, 2 * W * sizeof(int), s>>>(a.g, a.flags, B, H, W, faithful, a.dmap);
+  if (W <= kEdtMaxPaddedW) edt_rows_kernel<true><<<nimg * H, threads, edt_rows_smem(W, true), s>>>(epi, a.g, a.flags, H, W);
+  else edt_rows_kernel<false><<<nimg * H, threads, edt_rows_smem(W, false), s>>>(epi, a.g, a.flags, H, W);
   if ((e = launched()) != cudaSuccess) return e;
   abl_forward_kernel<<<grid_1d(px, 256), 256, 0, s>>>(logits, a.kl, a.dmap, B, H, W, smoothing, max_clip, a.res, loss_out);
   return launched();

@@ -13,98 +13,81 @@
 // and sqrtf / division are IEEE-rounded (this file must not be built with -use_fast_math); that
 // equals the reference's float64 sqrt rounded to float32 for every reachable value
 // (tests/test_oracle_golden.py::test_sqrt_f32_equals_f64_path_for_all_reachable_values).
-#include "common.cuh"
-#include "kernels.cuh"
+#include "edt.cuh"
 
 namespace cs {
 
-static constexpr int kInf = 30000;   // > any in-image distance (H, W <= 16384); kInf^2 fits int32
-
 size_t sdf_scratch_bytes(int B, int H, int W) { return (size_t)B * H * W * 4 + (size_t)B * 8; }
 
-// One thread per column.  g[(b,y,x)] = {dist to nearest fg in column, dist to nearest bg in column}.
-__global__ void sdf_columns_kernel(const float* __restrict__ src, float thr, int ge, int B, int H, int W,
-                                   ushort2* __restrict__ g, int* __restrict__ flags) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = idx < B * W;
-  const int b = active ? idx / W : 0, x = active ? idx - b * W : 0;
-  const float* col = src + (size_t)b * H * W + x;
-  ushort2* gc = g + (size_t)b * H * W + x;
-  int any_fg = 0, any_bg = 0;
-  if (active) {
-    int df = kInf, db = kInf;
-#pragma unroll 4
-    for (int y = 0; y < H; ++y) {
-      const float v = __ldg(col + (size_t)y * W);
-      const bool fg = ge ? (v >= thr) : (v > thr);
-      df = fg ? 0 : min(df + 1, kInf);
-      db = fg ? min(db + 1, kInf) : 0;
-      any_fg |= fg;
-      any_bg |= !fg;
-      gc[(size_t)y * W] = make_ushort2((unsigned short)df, (unsigned short)db);
-    }
-    df = kInf; db = kInf;
-    for (int y = H - 1; y >= 0; --y) {
-      const ushort2 d = gc[(size_t)y * W];
-      const bool fg = d.x == 0;
-      df = fg ? 0 : min(df + 1, kInf);
-      db = fg ? min(db + 1, kInf) : 0;
-      gc[(size_t)y * W] = make_ushort2((unsigned short)min((int)d.x, df), (unsigned short)min((int)d.y, db));
-    }
+struct ThresholdPred {
+  const float* src; float thr; int ge, H, W;
+  __device__ bool operator()(int img, int y, int x) const {
+    const float v = __ldg(src + ((size_t)img * H + y) * W + x);
+    return ge ? (v >= thr) : (v > thr);
   }
-  // per-image "has fg" / "has bg" flags (a warp may straddle two images: reduce per lane's own image)
-  if (active) {
-    if (any_fg) atomicOr(&flags[2 * b], 1);
-    if (any_bg) atomicOr(&flags[2 * b + 1], 1);
-  }
-}
+};
 
-// One block per image row.  Each thread owns pixels x = tid, tid + blockDim, ... and scans outwards from
-// x; the scan stops as soon as dx^2 alone can no longer beat the best candidate (exact pruning).
-__global__ void sdf_rows_kernel(const ushort2* __restrict__ g, const int* __restrict__ flags, int H, int W, float norm,
-                                float* __restrict__ sdf) {
-  extern __shared__ int srow[];                 // [2][W]: squared column distances to fg / to bg
-  const int row = blockIdx.x;                   // b*H + y
-  const int b = row / H;
-  const ushort2* gr = g + (size_t)row * W;
-  for (int x = threadIdx.x; x < W; x += blockDim.x) {
-    const ushort2 d = gr[x];
-    srow[x] = (int)d.x * (int)d.x;
-    srow[W + x] = (int)d.y * (int)d.y;
-  }
-  __syncthreads();
-  const bool degenerate = !(flags[2 * b] && flags[2 * b + 1]);
-  for (int x = threadIdx.x; x < W; x += blockDim.x) {
+// sdf = +dist(nearest fg) on background pixels, -dist(nearest bg) on foreground pixels, / norm; zeros when the image
+// is all-fg or all-bg (src/train_with_boundary_loss.py:193-195).
+struct SdfEpilogue {
+  float* sdf; float norm; int H, W;
+  __device__ void operator()(int img, int y, int x, bool fg, int best_sq, bool has_fg, bool has_bg) const {
     float out = 0.f;
-    if (!degenerate) {
-      const bool fg = srow[x] == 0;             // distance to nearest fg is 0 <=> the pixel is fg
-      const int* opp = fg ? (srow + W) : srow;  // fg pixels look for bg, bg pixels look for fg
-      int best = opp[x];
-      for (int d = 1; d < W && d * d < best; ++d) {
-        const int d2 = d * d;
-        if (x - d >= 0) best = min(best, d2 + opp[x - d]);
-        if (x + d < W) best = min(best, d2 + opp[x + d]);
-      }
-      const float dist = __fdiv_rn(__fsqrt_rn((float)best), norm);
+    if (has_fg && has_bg) {
+      const float dist = __fdiv_rn(__fsqrt_rn((float)best_sq), norm);
       out = fg ? -dist : dist;
     }
-    sdf[(size_t)row * W + x] = out;
+    sdf[((size_t)img * H + y) * W + x] = out;
   }
+};
+
+// Fallback for images taller than the segmented pass supports: one thread walks one column.
+__global__ void sdf_columns_serial_kernel(ThresholdPred pred, int B, int H, int W, ushort2* __restrict__ g,
+                                          int* __restrict__ flags) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * W) return;
+  const int b = idx / W, x = idx - b * W;
+  ushort2* gc = g + (size_t)b * H * W + x;
+  int any_fg = 0, any_bg = 0, df = kEdtInf, db = kEdtInf;
+  for (int y = 0; y < H; ++y) {
+    const bool fg = pred(b, y, x);
+    df = fg ? 0 : min(df + 1, kEdtInf);
+    db = fg ? min(db + 1, kEdtInf) : 0;
+    any_fg |= fg;
+    any_bg |= !fg;
+    gc[(size_t)y * W] = make_ushort2((unsigned short)df, (unsigned short)db);
+  }
+  df = kEdtInf; db = kEdtInf;
+  for (int y = H - 1; y >= 0; --y) {
+    const ushort2 d = gc[(size_t)y * W];
+    const bool fg = d.x == 0;
+    df = fg ? 0 : min(df + 1, kEdtInf);
+    db = fg ? min(db + 1, kEdtInf) : 0;
+    gc[(size_t)y * W] = make_ushort2((unsigned short)min((int)d.x, df), (unsigned short)min((int)d.y, db));
+  }
+  if (any_fg) atomicOr(&flags[2 * b], 1);
+  if (any_bg) atomicOr(&flags[2 * b + 1], 1);
 }
 
 cudaError_t launch_sdf(const float* src, float thr, int ge, int B, int H, int W, float norm, float* sdf,
                        void* scratch, cudaStream_t s) {
-  if (H >= kInf || W >= kInf) return cudaErrorInvalidValue;
+  if (H >= kEdtInf || W >= kEdtInf) return cudaErrorInvalidValue;
   ushort2* g = reinterpret_cast<ushort2*>(scratch);
   int* flags = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(scratch) + (size_t)B * H * W * 4);
   cudaError_t e = cudaMemsetAsync(flags, 0, (size_t)B * 8, s);
   if (e != cudaSuccess) return e;
-  const int cols = B * W;
-  sdf_columns_kernel<<<(cols + 63) / 64, 64, 0, s>>>(src, thr, ge, B, H, W, g, flags);
-  e = launched();
-  if (e != cudaSuccess) return e;
+  const ThresholdPred pred{src, thr, ge, H, W};
+  int nseg = 0, rps = 0;
+  if (edt_column_geometry(H, &nseg, &rps)) {
+    edt_columns_kernel<<<B * ((W + 31) / 32), dim3(32, nseg), 0, s>>>(pred, B, H, W, rps, g, flags);
+  } else {
+    sdf_columns_serial_kernel<<<(B * W + 63) / 64, 64, 0, s>>>(pred, B, H, W, g, flags);
+  }
+  if ((e = launched()) != cudaSuccess) return e;
+  const SdfEpilogue epi{sdf, norm, H, W};
   const int threads = W >= 256 ? 256 : ((W + 31) / 32) * 32;
-  sdf_rows_kernel<<<B * H, threads, 2 * W * sizeof(int), s>>>(g, flags, H, W, norm, sdf);
+  if (W <= kEdtMaxPaddedW) edt_rows_kernel<true><<<B * H, threads, edt_rows_smem(W, true), s>>>(epi, g, flags, H, W);
+  else edt_rows_kernel<false><<<B * H, threads, edt_rows_smem(W, false), s>>>(epi, g, flags, H, W);
   return launched();
 }
 

@@ -30,35 +30,49 @@ CS_DEVINL Vec8 ld8(const bf16* p) { return *reinterpret_cast<const Vec8*>(p); }
 CS_DEVINL void st8(bf16* p, const Vec8& v) { *reinterpret_cast<Vec8*>(p) = v; }
 
 // ============================================================================ weight packing
-// Tile of 32 (a) x 32 (b) pairs, T taps each; reads are contiguous in (b, t), the two outputs are
-// written contiguous in b (out_ab) and in a (out_ba) through a shared-memory transpose.
-__global__ void pack_pairs_kernel(const float* __restrict__ in, int Na, int Nb, int T, bf16* __restrict__ out_ab,
-                                  TapMap map_ab, bf16* __restrict__ out_ba, TapMap map_ba) {
-  __shared__ float tile[9][32][33];
+// Tile of 32 (a) x 32 (b) pairs, T <= 9 taps each.  Thread (b, a) reads the T contiguous taps of its pair (a warp
+// covers 32*T contiguous floats), writes out_ab directly (64-byte runs of b) and stages bf16 values in shared memory
+// for the transposed copy out_ba (64-byte runs of a).
+template <int T>
+__global__ void __launch_bounds__(256) pack_pairs_kernel(const float* __restrict__ in, int Na, int Nb,
+                                                         bf16* __restrict__ out_ab, TapMap map_ab,
+                                                         bf16* __restrict__ out_ba, TapMap map_ba) {
+  __shared__ bf16 tile[T][32][34];                       // [t][b][a], padded: conflict-free both ways
   const int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
-  const int nb = min(32, Nb - b0), na = min(32, Na - a0);
-  for (int ai = threadIdx.y; ai < na; ai += blockDim.y) {
-    const float* src = in + ((size_t)(a0 + ai) * Nb + b0) * T;
-    for (int i = threadIdx.x; i < nb * T; i += 32) tile[i % T][ai][i / T] = src[i];
-  }
-  __syncthreads();
-  for (int t = 0; t < T; ++t) {
-    if (out_ab) {
-      for (int ai = threadIdx.y; ai < na; ai += blockDim.y)
-        if ((int)threadIdx.x < nb)
-          out_ab[((size_t)map_ab.v[t] * Na + a0 + ai) * Nb + b0 + threadIdx.x] = __float2bfloat16(tile[t][ai][threadIdx.x]);
+  const int b = b0 + threadIdx.x;
+#pragma unroll
+  for (int ai = threadIdx.y; ai < 32; ai += 8) {
+    const int a = a0 + ai;
+    if (a < Na && b < Nb) {
+      const float* src = in + ((size_t)a * Nb + b) * T;
+      float v[T];
+#pragma unroll
+      for (int t = 0; t < T; ++t) v[t] = __ldg(src + t);
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const bf16 h = __float2bfloat16(v[t]);
+        if (out_ab) out_ab[((size_t)map_ab.v[t] * Na + a) * Nb + b] = h;
+        tile[t][threadIdx.x][ai] = h;
+      }
     }
-    if (out_ba) {
-      for (int bi = threadIdx.y; bi < nb; bi += blockDim.y)
-        if ((int)threadIdx.x < na)
-          out_ba[((size_t)map_ba.v[t] * Nb + b0 + bi) * Na + a0 + threadIdx.x] = __float2bfloat16(tile[t][threadIdx.x][bi]);
+  }
+  if (!out_ba) return;
+  __syncthreads();
+  const int a = a0 + threadIdx.x;
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+#pragma unroll
+    for (int bi = threadIdx.y; bi < 32; bi += 8) {
+      if (a < Na && b0 + bi < Nb) out_ba[((size_t)map_ba.v[t] * Nb + b0 + bi) * Na + a] = tile[t][bi][threadIdx.x];
     }
   }
 }
 cudaError_t launch_pack_pairs(const float* in, int Na, int Nb, int T, bf16* out_ab, TapMap map_ab, bf16* out_ba,
                               TapMap map_ba, cudaStream_t s) {
   dim3 grid((Nb + 31) / 32, (Na + 31) / 32), block(32, 8);
-  pack_pairs_kernel<<<grid, block, 0, s>>>(in, Na, Nb, T, out_ab, map_ab, out_ba, map_ba);
+  if (T == 9) pack_pairs_kernel<9><<<grid, block, 0, s>>>(in, Na, Nb, out_ab, map_ab, out_ba, map_ba);
+  else if (T == 4) pack_pairs_kernel<4><<<grid, block, 0, s>>>(in, Na, Nb, out_ab, map_ab, out_ba, map_ba);
+  else return cudaErrorInvalidValue;
   return launched();
 }
 
@@ -78,15 +92,30 @@ cudaError_t launch_pack_first(const float* in, int Cout, int Cin, bf16* out, cud
   return launched();
 }
 
-__global__ void unpack_pairs_kernel(const float* __restrict__ dwp, int Na, int Nb, int T, TapMap map,
-                                    float* __restrict__ grad) {
-  const size_t pairs = (size_t)Na * Nb;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < pairs; i += (size_t)gridDim.x * blockDim.x) {
-    for (int t = 0; t < T; ++t) grad[i * T + map.v[t]] = dwp[(size_t)t * pairs + i];
+// dwp[t][pair] -> grad[pair*T + map[t]]: 256 pairs per block staged through shared memory so that both the reads
+// (runs of pairs) and the writes (256*T contiguous floats) are coalesced.
+template <int T>
+__global__ void __launch_bounds__(256) unpack_pairs_kernel(const float* __restrict__ dwp, size_t pairs, TapMap map,
+                                                           float* __restrict__ grad) {
+  __shared__ float st[256 * T];
+  for (size_t p0 = (size_t)blockIdx.x * 256; p0 < pairs; p0 += (size_t)gridDim.x * 256) {
+    const size_t p = p0 + threadIdx.x;
+    if (p < pairs) {
+#pragma unroll
+      for (int t = 0; t < T; ++t) st[threadIdx.x * T + map.v[t]] = __ldg(dwp + (size_t)t * pairs + p);
+    }
+    __syncthreads();
+    const size_t n = (pairs - p0 < 256 ? pairs - p0 : 256) * T;
+    for (size_t i = threadIdx.x; i < n; i += 256) grad[p0 * T + i] = st[i];
+    __syncthreads();
   }
 }
 cudaError_t launch_unpack_pairs(const float* dwp, int Na, int Nb, int T, TapMap map, float* grad, cudaStream_t s) {
-  unpack_pairs_kernel<<<grid_for((long long)Na * Nb, 256), 256, 0, s>>>(dwp, Na, Nb, T, map, grad);
+  const size_t pairs = (size_t)Na * Nb;
+  const int grid = grid_for((long long)pairs, 256);
+  if (T == 9) unpack_pairs_kernel<9><<<grid, 256, 0, s>>>(dwp, pairs, map, grad);
+  else if (T == 4) unpack_pairs_kernel<4><<<grid, 256, 0, s>>>(dwp, pairs, map, grad);
+  else return cudaErrorInvalidValue;
   return launched();
 }
 

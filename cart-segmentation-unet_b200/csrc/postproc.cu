@@ -31,60 +31,90 @@ cudaError_t launch_ensemble_accumulate(const float* logits, float w, long long n
 }
 
 // ------------------------------------------------------------------------------------------------ QC scores
-// One block per image.  conf = |p - 0.5| * 2 is non-negative, so its float bit pattern orders like an unsigned int.
+// One block per image, three passes over its probabilities (L2-resident): conf = |p - 0.5| * 2 lies in [0, 1], so its
+// float bit pattern is < 2^30 and orders like an unsigned int; the two middle order statistics (numpy's median rule
+// for even counts) are found together by an 11 + 11 + 8 bit radix select.  The first pass also produces the mask, the
+// foreground count and the entropy sum.  Histogram updates are aggregated per warp (__match_any_sync): confident
+// predictions put most pixels into a handful of bins.
 static constexpr int kQcThreads = 1024;
+static constexpr int kQcBins = 2048;
 
 CS_DEVINL unsigned int conf_bits(float p) { return __float_as_uint(__fmul_rn(fabsf(__fsub_rn(p, 0.5f)), 2.0f)); }
 
-// k-th smallest (0-based) of conf_bits over one image: 11 + 11 + 10 bit radix passes with a shared histogram.
-__device__ unsigned int select_kth(const float* __restrict__ p, long long n, unsigned long long k, unsigned int* hist) {
-  __shared__ unsigned int s_prefix, s_mask;
-  __shared__ unsigned long long s_k;
-  if (threadIdx.x == 0) { s_prefix = 0; s_mask = 0; s_k = k; }
-  const int shifts[3] = {21, 10, 0}, widths[3] = {11, 11, 10};
-  for (int pass = 0; pass < 3; ++pass) {
-    const int bins = 1 << widths[pass];
-    for (int i = threadIdx.x; i < bins; i += blockDim.x) hist[i] = 0;
-    __syncthreads();
-    const unsigned int prefix = s_prefix, mask = s_mask;
-    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-      const unsigned int b = conf_bits(__ldg(p + i));
-      if ((b & mask) == prefix) atomicAdd(&hist[(b >> shifts[pass]) & (bins - 1)], 1u);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned long long kk = s_k;
-      int bin = 0;
-      while (bin < bins - 1 && kk >= hist[bin]) { kk -= hist[bin]; ++bin; }
-      s_k = kk;
-      s_prefix = prefix | ((unsigned int)bin << shifts[pass]);
-      s_mask = mask | ((unsigned int)(bins - 1) << shifts[pass]);
-    }
-    __syncthreads();
+// Run-length aggregation in registers: a thread walks consecutive pixels, whose confidences mostly share their leading
+// bits, and touches the shared histogram only when the bin changes.
+struct BinRun {
+  unsigned int bin, count;
+  CS_DEVINL void add(unsigned int* hist, unsigned int b) {
+    if (count && b == bin) { ++count; return; }
+    if (count) atomicAdd(&hist[bin], count);
+    bin = b; count = 1;
   }
-  const unsigned int r = s_prefix;
-  __syncthreads();                                    // the next call resets s_prefix
-  return r;
-}
+  CS_DEVINL void flush(unsigned int* hist) {
+    if (count) atomicAdd(&hist[bin], count);
+    count = 0;
+  }
+};
 
 __global__ void __launch_bounds__(kQcThreads) pseudo_qc_kernel(const float* __restrict__ probs, long long n, float thr,
                                                               int mask_value, uint8_t* __restrict__ mask,
                                                               double* __restrict__ stats) {
-  __shared__ unsigned int hist[2048];
+  __shared__ unsigned int hist[2][kQcBins];                  // [0]: selection of the lower middle rank, [1]: upper
   __shared__ double s_ent[kQcThreads / 32];
   __shared__ unsigned int s_cnt[kQcThreads / 32];
+  __shared__ unsigned int s_prefix[2], s_maskbits;
+  __shared__ unsigned long long s_k[2];
   const float* p = probs + (size_t)blockIdx.x * n;
   uint8_t* m = mask ? mask + (size_t)blockIdx.x * n : nullptr;
+  if (threadIdx.x == 0) {
+    s_prefix[0] = s_prefix[1] = 0; s_maskbits = 0;
+    s_k[0] = (unsigned long long)((n - 1) / 2);              // np.median: ranks (n-1)/2 and n/2 (0-based)
+    s_k[1] = (unsigned long long)(n / 2);
+  }
+  constexpr int kRun = 8;                                    // consecutive pixels per thread and step
   unsigned int cnt = 0;
   double ent = 0.0;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-    const float v = __ldg(p + i);
-    const bool fg = v >= thr;                                        // create_pseudo_labels_gpu.py:294
-    cnt += fg ? 1u : 0u;
-    if (m) m[i] = fg ? (uint8_t)mask_value : (uint8_t)0;
-    const float c = fminf(fmaxf(v, 1e-6f), 0.999999f);               // np.clip(p, eps, 1 - eps) in float32 (:129)
-    const float e = -(__fadd_rn(__fmul_rn(c, logf(c)), __fmul_rn(__fsub_rn(1.0f, c), logf(__fsub_rn(1.0f, c)))));
-    ent += (double)e;
+  for (int pass = 0; pass < 3; ++pass) {
+    const int shift = pass == 0 ? 19 : (pass == 1 ? 8 : 0);
+    const unsigned int bins = pass == 2 ? 256u : 2048u;
+    for (int i = threadIdx.x; i < 2 * kQcBins; i += blockDim.x) (&hist[0][0])[i] = 0;
+    __syncthreads();
+    const unsigned int pre0 = s_prefix[0], pre1 = s_prefix[1], mb = s_maskbits;
+    const bool split = pre0 != pre1;                         // the two ranks fell into different bins earlier
+    BinRun r0{0, 0}, r1{0, 0};
+    for (long long i0 = (long long)threadIdx.x * kRun; i0 < n; i0 += (long long)blockDim.x * kRun) {
+      const int m_end = (int)min((long long)kRun, n - i0);
+      for (int j = 0; j < m_end; ++j) {
+        const long long i = i0 + j;
+        const float v = __ldg(p + i);
+        if (pass == 0) {
+          const bool fg = v >= thr;                                      // create_pseudo_labels_gpu.py:294
+          cnt += fg ? 1u : 0u;
+          if (m) m[i] = fg ? (uint8_t)mask_value : (uint8_t)0;
+          const float c = fminf(fmaxf(v, 1e-6f), 0.999999f);             // np.clip(p, eps, 1 - eps) in float32 (:129)
+          ent += (double)(-(__fadd_rn(__fmul_rn(c, logf(c)), __fmul_rn(__fsub_rn(1.0f, c), logf(__fsub_rn(1.0f, c))))));
+        }
+        const unsigned int b = conf_bits(v);
+        const unsigned int bin = (b >> shift) & (bins - 1);
+        if ((b & mb) == pre0) r0.add(hist[0], bin);
+        if (split && (b & mb) == pre1) r1.add(hist[1], bin);
+      }
+    }
+    r0.flush(hist[0]);
+    r1.flush(hist[1]);
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      const int w = threadIdx.x;
+      const unsigned int* h = hist[(split && w == 1) ? 1 : 0];
+      unsigned long long kk = s_k[w];
+      unsigned int bin = 0;
+      while (bin < bins - 1 && kk >= h[bin]) { kk -= h[bin]; ++bin; }
+      s_k[w] = kk;
+      s_prefix[w] |= bin << shift;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_maskbits |= (bins - 1) << shift;
+    __syncthreads();
   }
   cnt = __reduce_add_sync(0xffffffffu, cnt);
 #pragma unroll
@@ -94,18 +124,11 @@ __global__ void __launch_bounds__(kQcThreads) pseudo_qc_kernel(const float* __re
   if (threadIdx.x == 0) {
     unsigned long long c = 0; double e = 0.0;
     for (int w = 0; w < kQcThreads / 32; ++w) { c += s_cnt[w]; e += s_ent[w]; }
+    const float a = __uint_as_float(s_prefix[0]), b = __uint_as_float(s_prefix[1]);
     stats[(size_t)blockIdx.x * 4 + 0] = (double)c;                   // foreground pixels (area = count / n)
+    stats[(size_t)blockIdx.x * 4 + 1] = (double)__fmul_rn(__fadd_rn(a, b), 0.5f);   // float32 mean of the two middles
     stats[(size_t)blockIdx.x * 4 + 2] = e / (double)n;               // mean entropy
     stats[(size_t)blockIdx.x * 4 + 3] = (double)n;
-  }
-  __syncthreads();
-  // np.median: middle element, or the float32 mean of the two middle elements
-  const unsigned int lo = select_kth(p, n, (unsigned long long)((n - 1) / 2), hist);
-  unsigned int hi = lo;
-  if ((n & 1) == 0) hi = select_kth(p, n, (unsigned long long)(n / 2), hist);
-  if (threadIdx.x == 0) {
-    const float a = __uint_as_float(lo), b = __uint_as_float(hi);
-    stats[(size_t)blockIdx.x * 4 + 1] = (double)((n & 1) ? a : __fmul_rn(__fadd_rn(a, b), 0.5f));
   }
 }
 cudaError_t launch_pseudo_qc(const float* probs, int B, long long n, float thr, int mask_value, uint8_t* mask,
@@ -132,27 +155,51 @@ CS_DEVINL void uf_union(int* L, int a, int b) {
   }
 }
 
-// cls[i] = 1 foreground / 0 background; L[i] = i
-__global__ void cc_init_kernel(const uint8_t* __restrict__ in, int thr, long long total, uint8_t* __restrict__ cls,
-                               int* __restrict__ L) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    if (in) cls[i] = (int)in[i] > thr ? 1 : 0;
-    L[i] = (int)i;
+// cls[i] = 1 foreground / 0 background (written when `in` is given).  L[i] = leftmost pixel of i's horizontal run of
+// class `want` inside its 32-pixel lane group (ballot scan), so horizontal connectivity costs no union at all except at
+// group boundaries.  The grid-stride loop keeps warps on 32 consecutive flat indices; runs break at row starts.
+__global__ void cc_init_kernel(const uint8_t* __restrict__ in, int thr, int want, int W, long long total,
+                               uint8_t* __restrict__ cls, int* __restrict__ L) {
+  const long long total_ceil = (total + 31) / 32 * 32;
+  const unsigned int lane = threadIdx.x & 31;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_ceil; i += (long long)gridDim.x * blockDim.x) {
+    const bool inb = i < total;
+    int c = 0;
+    if (inb) {
+      c = in ? ((int)in[i] > thr ? 1 : 0) : (int)cls[i];
+      if (in) cls[i] = (uint8_t)c;
+    }
+    const unsigned int m = __ballot_sync(0xffffffffu, inb && c == want);
+    const unsigned int rs = __ballot_sync(0xffffffffu, inb && (i % W) == 0);
+    if (!inb) continue;
+    int label = (int)i;
+    if (c == want) {
+      const unsigned int starts = m & (~(m << 1) | rs | 1u);
+      const unsigned int upto = starts & (0xffffffffu >> (31 - lane));
+      label = (int)(i - (lane - (31 - __clz(upto))));
+    }
+    L[i] = label;
   }
 }
-// unions between pixels of class `want`; conn8: W, NW, N, NE neighbours, else W, N
+// Unions between pixels of class `want`, only where connectivity is new: a pixel whose left neighbour already links the
+// same two runs leaves the work to that neighbour.  conn8 adds the two upper diagonals.
 __global__ void cc_merge_kernel(const uint8_t* __restrict__ cls, int want, int conn8, int H, int W, long long total,
                                 int* __restrict__ L) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     if (cls[i] != want) continue;
     const int x = (int)(i % W), y = (int)((i / W) % H);
-    if (x > 0 && cls[i - 1] == want) uf_union(L, (int)i, (int)i - 1);
-    if (y > 0) {
-      if (cls[i - W] == want) uf_union(L, (int)i, (int)(i - W));
-      if (conn8) {
-        if (x > 0 && cls[i - W - 1] == want) uf_union(L, (int)i, (int)(i - W - 1));
-        if (x + 1 < W && cls[i - W + 1] == want) uf_union(L, (int)i, (int)(i - W + 1));
-      }
+    const bool left = x > 0 && cls[i - 1] == want;
+    if (left && (i & 31) == 0) uf_union(L, (int)i, (int)i - 1);          // runs continue across lane groups
+    if (y == 0) continue;
+    const bool up = cls[i - W] == want;
+    const bool upleft = x > 0 && cls[i - W - 1] == want;
+    if (up) {
+      if (!(left && upleft)) uf_union(L, (int)i, (int)(i - W));
+    } else if (conn8) {
+      if (upleft && !left) uf_union(L, (int)i, (int)(i - W - 1));
+      const bool upright = x + 1 < W && cls[i - W + 1] == want;
+      const bool right = x + 1 < W && cls[i + 1] == want;
+      if (upright && !right) uf_union(L, (int)i, (int)(i - W + 1));
     }
   }
 }
@@ -238,12 +285,12 @@ cudaError_t launch_mask_cleanup(const uint8_t* mask, int B, int H, int W, int bi
     __VA_ARGS__;                                    \
     if ((e = launched()) != cudaSuccess) return e;  \
   } while (0)
-  PP_LAUNCH(cc_init_kernel<<<grid, 256, 0, s>>>(mask, bin_thr, px, cls, L));
+  PP_LAUNCH(cc_init_kernel<<<grid, 256, 0, s>>>(mask, bin_thr, fill_holes ? 0 : 1, W, px, cls, L));
   if (fill_holes) {
     PP_LAUNCH(cc_merge_kernel<<<grid, 256, 0, s>>>(cls, 0, 0, H, W, px, L));          // background, 4-connected
     PP_LAUNCH(cc_compress_kernel<<<grid, 256, 0, s>>>(px, L));
     PP_LAUNCH(cc_fill_holes_kernel<<<grid, 256, 0, s>>>(L, hw, px, cls));
-    PP_LAUNCH(cc_init_kernel<<<grid, 256, 0, s>>>(nullptr, 0, px, cls, L));
+    PP_LAUNCH(cc_init_kernel<<<grid, 256, 0, s>>>(nullptr, 0, 1, W, px, cls, L));
   }
   if (keep_largest) {
     PP_LAUNCH(cc_merge_kernel<<<grid, 256, 0, s>>>(cls, 1, 1, H, W, px, L));          // foreground, 8-connected

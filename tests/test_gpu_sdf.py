@@ -32,7 +32,10 @@ def test_golden_masks_bit_exact():
     assert not bad, bad
 
 
-@pytest.mark.parametrize("H,W,B", [(224, 224, 6), (512, 512, 2), (96, 160, 3), (16, 16, 5)])
+# (1040, 48): taller than the segmented column pass (serial fallback); (8, 2112): wider than the padded row pass;
+# (257, 33) / (300, 250): segment counts 16 with ragged last segments and ragged 32-column groups
+@pytest.mark.parametrize("H,W,B", [(224, 224, 6), (512, 512, 2), (96, 160, 3), (16, 16, 5), (1040, 48, 2),
+                                   (8, 2112, 2), (257, 33, 5), (300, 250, 3), (1024, 64, 2)])
 def test_batches_bit_exact_vs_oracle(H, W, B):
     from oracle import unet_oracle as O
     rng = np.random.default_rng(H * 7 + W)

@@ -33,6 +33,9 @@ for part in "$@"; do
     bench8gpu) run bench_8gpu 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --steps 10 --warmup 3 ;;
     bench4gpu) run bench_4gpu 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29522 bench.py --gpus 4 --steps 10 --warmup 3 ;;
     bench2gpu) run bench_2gpu 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 ;;
+    aux)    run bench_aux 900 python tools/bench_aux.py ;;
+    aux512) run bench_aux512 900 python tools/bench_aux.py --batch 32 --size 512 --no-cpu ;;
+    auxncu) run ncu_aux 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/aux_launches.csv python tools/bench_aux.py --iters 1 --no-cpu ;;
     infer)  run bench_infer 900 python tools/bench_infer.py ;;
     bench20) run bench 900 python bench.py ;;
     benchref) run bench_ref 600 python bench.py --impl reference --steps 3 --warmup 1 ;;
