@@ -42,6 +42,20 @@ WORKLOADS = {
 }
 
 
+def step_traffic(kernel_label: str):
+    """DRAM bytes per launch of a kernel class from the committed ncu pass over one k2 step (profiles/, written by
+    tools/step_traffic.py); None when no capture is committed."""
+    path = os.path.join(ROOT, "profiles", "r1_step_traffic.json")
+    if not os.path.exists(path):
+        return None, None
+    data = json.load(open(path))
+    key = kernel_label.split(" ")[0].rstrip(">")            # e.g. "pix_gemm2_kernel<256"
+    for name, k in data["kernels"].items():
+        if name.replace("cs::", "").startswith(key + ",") or name.replace("cs::", "").startswith(key + ">"):
+            return k["avg_dram_bytes"], path.replace(ROOT + os.sep, "") + ": " + name
+    return None, None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -305,6 +319,7 @@ def run_ours(args, wl):
         pk = peaks()
         per_gpu_tflops = (value / world) * GFLOP_TRAIN[S] / 1e3
         dom = max(kernels, key=lambda k: k["ms_per_step"])
+        traffic, traffic_src = step_traffic(dom["kernel"]) if args.workload in ("k2", "k4") else (None, None)
         gemm_ms = sum(k["ms_per_step"] for k in kernels)
         gemm_tflops = sum(k_fl) / max(1e-9, sum(k_ms)) / 1e9
         line = {
@@ -320,7 +335,8 @@ def run_ours(args, wl):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": dom["tflops"], "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                         "frac": dom["tflops"] / pk["tf_sust"], "traffic": None,
+                         "frac": dom["tflops"] / pk["tf_sust"], "traffic": traffic,
+                         "traffic_source": traffic_src,
                          "kernel": dom["kernel"],
                          "how": "algorithmic FLOPs (2*MACs) of this kernel's launches / their summed CUDA-event durations "
                                 "on the launch stream, over the same K steps repeated right after the timed region with "

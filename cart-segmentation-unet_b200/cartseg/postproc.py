@@ -93,6 +93,8 @@ def ensemble_forward(models: Sequence, weights: Sequence[float], tens: Tensor) -
     probs = None
     for i, (m, w) in enumerate(zip(models, weights)):
         logits = m(tens)
+        if not logits.is_cuda:
+            raise CartsegError("ensemble_forward takes CUDA tensors only (no CPU fallback)")
         if logits.dim() != 4 or logits.shape[1] != 1:
             raise CartsegError("ensemble_forward: models must return [B,1,H,W] logits")
         lg = _f32c(logits)
@@ -114,6 +116,8 @@ def pseudo_label_qc(probs: Tensor, threshold: float = 0.5, mask_value: int = 1):
     """create_pseudo_labels_gpu.py:294-300 for a whole batch.  Returns ``(pred01, fg_area, fg_conf, mean_entropy)``:
     the uint8 mask [B,H,W] and three float64 [B] tensors, all on the device (one D2H of 3 numbers per image instead
     of 4 B/px)."""
+    if not probs.is_cuda:
+        raise CartsegError("pseudo_label_qc takes CUDA tensors only (no CPU fallback)")
     if probs.dim() == 4 and probs.shape[1] == 1:
         probs = probs[:, 0]
     mask, stats = torch.ops.cartseg.pseudo_qc(_f32c(probs), float(threshold), int(mask_value))

@@ -103,14 +103,30 @@ __global__ void __launch_bounds__(kQcThreads) pseudo_qc_kernel(const float* __re
     r0.flush(hist[0]);
     r1.flush(hist[1]);
     __syncthreads();
-    if (threadIdx.x < 2) {
-      const int w = threadIdx.x;
+    if (threadIdx.x < 64) {                                  // warp w locates the bin of rank w: 32 partial sums,
+      const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;        // a warp scan, then <= 64 serial steps
       const unsigned int* h = hist[(split && w == 1) ? 1 : 0];
-      unsigned long long kk = s_k[w];
-      unsigned int bin = 0;
-      while (bin < bins - 1 && kk >= h[bin]) { kk -= h[bin]; ++bin; }
-      s_k[w] = kk;
-      s_prefix[w] |= bin << shift;
+      const unsigned int per = bins >> 5;
+      unsigned int part = 0;
+      for (unsigned int j = 0; j < per; ++j) part += h[lane * per + j];
+      unsigned int incl = part;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const unsigned long long kk0 = s_k[w];
+      // first lane whose inclusive count exceeds the rank (the last lane if none does: rank beyond the data)
+      const unsigned int hit = __ballot_sync(0xffffffffu, (unsigned long long)incl > kk0);
+      const int owner = hit ? __ffs(hit) - 1 : 31;
+      if (lane == owner) {
+        unsigned long long kk = kk0 - (unsigned long long)(incl - part);
+        unsigned int bin = lane * per;
+        const unsigned int last = bin + per - 1;
+        while (bin < last && kk >= h[bin]) { kk -= h[bin]; ++bin; }
+        s_k[w] = kk;
+        s_prefix[w] |= bin << shift;
+      }
     }
     __syncthreads();
     if (threadIdx.x == 0) s_maskbits |= (bins - 1) << shift;

@@ -90,6 +90,40 @@ def test_no_cpu_fallback():
         cartseg.dice_metric(torch.zeros(1, 1, 16, 16), torch.zeros(1, 1, 16, 16))
 
 
+def test_no_cpu_fallback_next_rows():
+    import cartseg
+    z, t = torch.zeros(1, 1, 16, 16), torch.zeros(1, 1, 16, 16)
+    for fn in (lambda: cartseg.ABL()(z, t), lambda: cartseg.BCEDiceABL()(z, t),
+               lambda: cartseg.pseudo_label_qc(torch.zeros(1, 16, 16)),
+               lambda: cartseg.clean_mask(torch.zeros(16, 16, dtype=torch.uint8)),
+               lambda: cartseg.clean_mask_largest_component(torch.zeros(16, 16, dtype=torch.uint8)),
+               lambda: cartseg.letterbox_resize_normalize([torch.zeros(8, 8, 3, dtype=torch.uint8)], 16),
+               lambda: cartseg.resize_masks([torch.zeros(8, 8, dtype=torch.uint8)], 16),
+               lambda: cartseg.ensemble_forward([lambda x: z], [1.0], torch.zeros(1, 3, 16, 16))):
+        with pytest.raises(cartseg.CartsegError):
+            fn()
+
+
+def test_host_helpers_of_the_next_rows_match_the_oracle():
+    """Host-side pieces that need no GPU: the C letterbox geometry (Python round() semantics), the ABL threshold ladder,
+    the ensemble weight normalisation, should_accept."""
+    import cartseg
+    from cartseg import ops
+    from oracle import abl_oracle as A
+    from oracle import postproc_oracle as P
+    from oracle import preproc_oracle as R
+    for h, w in [(10, 25), (10, 35), (120, 50), (60, 96), (1080, 1920), (75, 101), (5, 5), (480, 645)]:
+        for ratio in (0.1, 0.0, 0.25):
+            assert cartseg.preproc.letterbox_geometry(h, w, ratio) == R.letterbox_geometry(h, w, ratio), (h, w, ratio)
+    import numpy as np
+    lad = np.asarray(ops.abl_eps_ladder(), dtype=np.float64).astype(np.float32)
+    assert np.array_equal(lad, A.eps_ladder(len(lad)))
+    w = cartseg.postproc.normalize_weights([0.7, 0.3, 2.0])
+    assert w == (np.array([0.7, 0.3, 2.0], np.float32) / np.array([0.7, 0.3, 2.0], np.float32).sum()).tolist()
+    for args in [(0.2, 0.9, 0.1), (0.004, 0.9, 0.1), (0.61, 0.9, 0.1), (0.2, 0.64, 0.1), (0.2, 0.9, 0.36)]:
+        assert cartseg.should_accept(*args) == P.should_accept(*args)
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "cart-segmentation-unet_b200", "cartseg")
     for f in os.listdir(pkg):

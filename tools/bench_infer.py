@@ -49,6 +49,8 @@ for B in [int(b) for b in args.batches.split(",")]:
     out_h = torch.empty((B, args.size, args.size), dtype=torch.uint8).pin_memory()
     xd = torch.empty_like(x)
     import time
+    xd.copy_(x_h, non_blocking=True)                     # one untimed pass: first-use costs of the copy paths
+    out_h.copy_(run(xd), non_blocking=True)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(args.iters):

@@ -42,6 +42,7 @@ for part in "$@"; do
     launches) run profile_plain 300 python tools/profile_step.py && \
             run ncu_launches 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none \
                 --csv --log-file gpurun_out/launches.csv python tools/profile_step.py ;;
+    traffic) run ncu_traffic 900 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/step_traffic.csv python tools/profile_step.py ;;
     ncufull) run profile_plain 300 python tools/profile_step.py && \
             run ncu_pix 1500 ncu --profile-from-start off --set full --clock-control none --import-source on \
                 -k regex:pix_gemm -c 12 -f -o gpurun_out/prof_pix python tools/profile_step.py && \
