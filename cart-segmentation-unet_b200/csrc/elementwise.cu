@@ -401,21 +401,64 @@ CS_DEVINL void masked_grad(const BnBwdArgs& a, const BnCoef& k, int g, long long
       if (!(act[d][j] > 0.f)) gm[d][j] = 0.f;
 }
 
+// Pooled layers, register-lean formulation: the four pixels of a 2x2 window stay packed (bf16) and are unpacked one
+// channel at a time, so that a thread holds ~100 registers instead of ~170 and two blocks fit on an SM.  `f(d, j, gm,
+// xhat)` is called for every pixel d of the window and channel j in the same (j outer, d inner) order for both
+// passes; per-channel sums therefore see the pixels in the same order as the wide formulation (bit-identical).
+CS_DEVINL float bf16_elem(const Vec8& v, int j) { return (j & 1) ? bf16_hi(v.w[j >> 1]) : bf16_lo(v.w[j >> 1]); }
+template <class F>
+CS_DEVINL void pooled_unit(const BnBwdArgs& a, const BnCoef& k, int g, long long unit, long long pix[4], F&& f) {
+  const int H2 = a.H >> 1, W2 = a.W >> 1;
+  const int w2 = (int)(unit % W2);
+  const int h2 = (int)((unit / W2) % H2);
+  const int b = (int)(unit / ((long long)W2 * H2));
+  Vec8 yv8[4], gv8[4];
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+    pix[d] = ((long long)b * a.H + 2 * h2 + (d >> 1)) * a.W + 2 * w2 + (d & 1);
+    yv8[d] = ld8(a.y + pix[d] * a.C + g * 8);
+    gv8[d] = ld8(a.g + pix[d] * a.g_pitch + a.g_c0 + g * 8);
+  }
+  const Vec8 gp8 = ld8(a.g_pool + unit * a.C + g * 8);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float yv[4], gm[4], act[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      yv[d] = bf16_elem(yv8[d], j);
+      gm[d] = bf16_elem(gv8[d], j);
+      act[d] = __bfloat162float(__float2bfloat16(fmaxf(fmaf(yv[d], k.sc[j], k.sh[j]), 0.f)));   // as stored by the forward
+    }
+    int best = 0;
+    float bv = act[0];
+#pragma unroll
+    for (int d = 1; d < 4; ++d)
+      if (act[d] > bv) { bv = act[d]; best = d; }
+    const float gp = bf16_elem(gp8, j);
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      float gd = gm[d] + (d == best ? gp : 0.f);
+      if (!(act[d] > 0.f)) gd = 0.f;
+      f(d, j, gd, (yv[d] - k.mu[j]) * k.is[j]);
+    }
+  }
+}
+
 static constexpr int kBnBwdThreads = 256;
 static constexpr int kBnBwdMaxBlocks = 148 * 4;          // partials: [blocks][2*C] floats
 
 size_t bn_bwd_scratch_bytes(int maxC) { return (size_t)kBnBwdMaxBlocks * 2 * maxC * sizeof(float); }
 
-// One full wave of resident blocks (3 per SM without pooling, 1 with: see the launch bounds) — a partial second
+// One full wave of resident blocks (3 per SM without pooling, 2 with: see the launch bounds) — a partial second
 // wave costs these bandwidth-bound kernels its whole duration again.
 static int bn_bwd_grid(const BnBwdArgs& a) {
   const int rpb = kBnBwdThreads / (a.C / 8);
   const long long units = a.g_pool ? (long long)a.B * (a.H / 2) * (a.W / 2) : (long long)a.B * a.H * a.W;
-  return grid_for(units, rpb * 2, a.g_pool ? 148 : 148 * 3);
+  return grid_for(units, rpb * 2, a.g_pool ? 148 * 2 : 148 * 3);
 }
 
 template <bool POOL>
-__global__ void __launch_bounds__(kBnBwdThreads, POOL ? 1 : 3) bn_bwd_reduce_kernel(BnBwdArgs a) {
+__global__ void __launch_bounds__(kBnBwdThreads, POOL ? 2 : 3) bn_bwd_reduce_kernel(BnBwdArgs a) {
   constexpr int ND = POOL ? 4 : 1;
   __shared__ float sm[16 * kBnBwdThreads];               // [rows per block][2*C]  (rpb * 2C == 16 * threads)
   const int cg = a.C >> 3;
@@ -426,15 +469,22 @@ __global__ void __launch_bounds__(kBnBwdThreads, POOL ? 1 : 3) bn_bwd_reduce_ker
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
-#pragma unroll(POOL ? 1 : 2)
-  for (long long u = (long long)blockIdx.x * rpb + ri; u < units; u += (long long)gridDim.x * rpb) {
-    float gm[ND][8], xh[ND][8];
-    long long pix[ND];
-    masked_grad<POOL>(a, k, g, u, gm, xh, pix);
+  if (POOL) {
+    for (long long u = (long long)blockIdx.x * rpb + ri; u < units; u += (long long)gridDim.x * rpb) {
+      long long pix[4];
+      pooled_unit(a, k, g, u, pix, [&](int, int j, float gmv, float xhv) { s1[j] += gmv; s2[j] = fmaf(gmv, xhv, s2[j]); });
+    }
+  } else {
+#pragma unroll 2
+    for (long long u = (long long)blockIdx.x * rpb + ri; u < units; u += (long long)gridDim.x * rpb) {
+      float gm[ND][8], xh[ND][8];
+      long long pix[ND];
+      masked_grad<POOL>(a, k, g, u, gm, xh, pix);
 #pragma unroll
-    for (int d = 0; d < ND; ++d)
+      for (int d = 0; d < ND; ++d)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { s1[j] += gm[d][j]; s2[j] = fmaf(gm[d][j], xh[d][j], s2[j]); }
+        for (int j = 0; j < 8; ++j) { s1[j] += gm[d][j]; s2[j] = fmaf(gm[d][j], xh[d][j], s2[j]); }
+    }
   }
   float* row = sm + (size_t)ri * 2 * a.C;
 #pragma unroll
@@ -485,7 +535,7 @@ cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t s) {
 }
 
 template <bool POOL>
-__global__ void __launch_bounds__(kBnBwdThreads, POOL ? 1 : 3) bn_bwd_apply_kernel(BnBwdArgs a) {
+__global__ void __launch_bounds__(kBnBwdThreads, POOL ? 2 : 3) bn_bwd_apply_kernel(BnBwdArgs a) {
   constexpr int ND = POOL ? 4 : 1;
   const int cg = a.C >> 3;
   const int g = threadIdx.x % cg, ri = threadIdx.x / cg, rpb = kBnBwdThreads / cg;
@@ -495,17 +545,32 @@ __global__ void __launch_bounds__(kBnBwdThreads, POOL ? 1 : 3) bn_bwd_apply_kern
   float c1[8], c2[8];
   load8(a.c1 + g * 8, c1);
   load8(a.c2 + g * 8, c2);
-#pragma unroll(POOL ? 1 : 2)
-  for (long long u = (long long)blockIdx.x * rpb + ri; u < units; u += (long long)gridDim.x * rpb) {
-    float gm[ND][8], xh[ND][8];
-    long long pix[ND];
-    masked_grad<POOL>(a, k, g, u, gm, xh, pix);
+  if (POOL) {
+    for (long long u = (long long)blockIdx.x * rpb + ri; u < units; u += (long long)gridDim.x * rpb) {
+      long long pix[4];
+      float prev[4];                                     // the even channel of the pair being packed
+      Vec8 out[4];
+      pooled_unit(a, k, g, u, pix, [&](int d, int j, float gmv, float xhv) {
+        const float o = k.sc[j] * (gmv - c1[j] - xhv * c2[j]);
+        if (j & 1) out[d].w[j >> 1] = pack_bf16x2(prev[d], o);
+        else prev[d] = o;
+      });
 #pragma unroll
-    for (int d = 0; d < ND; ++d) {
-      float o[8];
+      for (int d = 0; d < 4; ++d) st8(a.dy + pix[d] * a.C + g * 8, out[d]);
+    }
+  } else {
+#pragma unroll 2
+    for (long long u = (long long)blockIdx.x * rpb + ri; u < units; u += (long long)gridDim.x * rpb) {
+      float gm[ND][8], xh[ND][8];
+      long long pix[ND];
+      masked_grad<POOL>(a, k, g, u, gm, xh, pix);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = k.sc[j] * (gm[d][j] - c1[j] - xh[d][j] * c2[j]);
-      st8(a.dy + pix[d] * a.C + g * 8, pack8(o));
+      for (int d = 0; d < ND; ++d) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = k.sc[j] * (gm[d][j] - c1[j] - xh[d][j] * c2[j]);
+        st8(a.dy + pix[d] * a.C + g * 8, pack8(o));
+      }
     }
   }
 }

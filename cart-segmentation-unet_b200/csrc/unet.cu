@@ -196,9 +196,21 @@ static void wgrad_common(WgradParams& p, int* block_n, int M, int N, int B, int 
   p.batch = B;
   const int tiles = p.tiles_w * p.tiles_h * B;
   const int base = p.m_blocks * p.n_blocks * G;
-  int splits = (148 * 4 + base - 1) / base;
-  if (splits > tiles / 16) splits = tiles / 16;
-  if (splits < 1) splits = 1;
+  // Split-K factor.  One CTA per SM is resident (shared memory), so the grid runs in waves of 148; a CTA costs its
+  // share of the pixel tiles plus a fixed prologue / accumulator drain worth ~6 tiles.  Pick the split count with the
+  // smallest waves x (tiles per CTA + overhead): 13 splits of a 48-item layer are 624 CTAs = five waves with the last
+  // one 22 % full, 12 splits are four full waves of slightly longer CTAs.
+  const int kSMs = 148, kOverheadTiles = 6;
+  int max_splits = tiles / 16;
+  if (max_splits < 1) max_splits = 1;
+  if (max_splits > 4 * kSMs) max_splits = 4 * kSMs;
+  int splits = 1;
+  long long best_cost = -1;
+  for (int sp = 1; sp <= max_splits; ++sp) {
+    const long long waves = ((long long)base * sp + kSMs - 1) / kSMs;
+    const long long cost = waves * ((tiles + sp - 1) / sp + kOverheadTiles);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; splits = sp; }
+  }
   p.splits = splits;
   p.dw = dw;
 }
