@@ -186,17 +186,20 @@ cudaError_t launch_im2col_first(const float* x, int B, int Cin, int H, int W, bf
 }
 
 // ============================================================================ batch norm: statistics -> affine
-__global__ void bn_finalize_train_kernel(BnFinalizeArgs a) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && a.num_batches_tracked) *a.num_batches_tracked += 1;
-  if (c >= a.C) return;
+// One channel: batch statistics -> (scale, shift); `publish` also stores the per-channel vectors the backward pass
+// reads and updates the running statistics (momentum, unbiased variance), exactly once per forward.
+CS_DEVINL void bn_channel_coef(const BnFinalizeArgs& a, int c, bool publish, float* sc_out, float* sh_out) {
   const double mean = a.sum[c] / a.count;
   double var = a.sq[c] / a.count - mean * mean;
   if (var < 0.0) var = 0.0;
   const double invstd = rsqrt(var + (double)a.eps);
   const float sc = (float)((double)a.gamma[c] * invstd);
+  const float sh = (float)((double)a.beta[c] - mean * (double)a.gamma[c] * invstd);
+  *sc_out = sc;
+  *sh_out = sh;
+  if (!publish) return;
   a.scale[c] = sc;
-  a.shift[c] = (float)((double)a.beta[c] - mean * (double)a.gamma[c] * invstd);
+  a.shift[c] = sh;
   a.mean[c] = (float)mean;
   a.invstd[c] = (float)invstd;
   if (a.running_mean) {
@@ -208,6 +211,13 @@ __global__ void bn_finalize_train_kernel(BnFinalizeArgs a) {
     const double unbiased = a.count > 1.0 ? var * a.count / (a.count - 1.0) : var;
     a.running_var[c] = (float)((1.0 - m) * (double)a.running_var[c] + m * unbiased);
   }
+}
+__global__ void bn_finalize_train_kernel(BnFinalizeArgs a) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && a.num_batches_tracked) *a.num_batches_tracked += 1;
+  if (c >= a.C) return;
+  float sc, sh;
+  bn_channel_coef(a, c, true, &sc, &sh);
 }
 cudaError_t launch_bn_finalize_train(const BnFinalizeArgs& a, cudaStream_t s) {
   bn_finalize_train_kernel<<<(a.C + 127) / 128, 128, 0, s>>>(a);
@@ -231,9 +241,17 @@ cudaError_t launch_bn_fold_eval(const float* gamma, const float* beta, const flo
 
 // ============================================================================ BN apply + ReLU (+ 2x2 max-pool)
 template <bool POOL>
-__global__ void bn_relu_kernel(const bf16* __restrict__ y, int B, int H, int W, int C, const float* __restrict__ scale,
-                               const float* __restrict__ shift, bf16* __restrict__ out, int out_pitch, int out_c0,
-                               bf16* __restrict__ pooled) {
+__global__ void bn_relu_kernel(const bf16* __restrict__ y, int B, int H, int W, int C, const BnFinalizeArgs fin,
+                               bf16* __restrict__ out, int out_pitch, int out_c0, bf16* __restrict__ pooled) {
+  // Fused statistics -> affine step (was a kernel of its own between the convolution and this pass): every block
+  // derives (scale, shift) of all C channels into shared memory; block 0 also publishes them for the backward pass
+  // and updates the running statistics.
+  extern __shared__ __align__(16) float s_coef[];          // [2][C]
+  const float* scale = s_coef;
+  const float* shift = s_coef + C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) bn_channel_coef(fin, c, blockIdx.x == 0, &s_coef[c], &s_coef[C + c]);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && fin.num_batches_tracked) *fin.num_batches_tracked += 1;
+  __syncthreads();
   const int cg = C >> 3;
   if (!POOL) {
     const long long total = (long long)B * H * W * cg;
@@ -243,10 +261,10 @@ __global__ void bn_relu_kernel(const bf16* __restrict__ y, int B, int H, int W, 
       const long long p = i / cg;
       float f[8], sc[8], sh[8];
       unpack8(ld8(y + p * C + g * 8), f);
-      *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(scale + g * 8));
-      *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(scale + g * 8 + 4));
-      *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(shift + g * 8));
-      *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(shift + g * 8 + 4));
+      *reinterpret_cast<float4*>(sc) = *reinterpret_cast<const float4*>(scale + g * 8);
+      *reinterpret_cast<float4*>(sc + 4) = *reinterpret_cast<const float4*>(scale + g * 8 + 4);
+      *reinterpret_cast<float4*>(sh) = *reinterpret_cast<const float4*>(shift + g * 8);
+      *reinterpret_cast<float4*>(sh + 4) = *reinterpret_cast<const float4*>(shift + g * 8 + 4);
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
       st8(out + p * out_pitch + out_c0 + g * 8, pack8(f));
@@ -262,10 +280,10 @@ __global__ void bn_relu_kernel(const bf16* __restrict__ y, int B, int H, int W, 
       const int h2 = (int)((q / W2) % H2);
       const int b = (int)(q / ((long long)W2 * H2));
       float sc[8], sh[8], mx[8];
-      *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(scale + g * 8));
-      *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(scale + g * 8 + 4));
-      *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(shift + g * 8));
-      *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(shift + g * 8 + 4));
+      *reinterpret_cast<float4*>(sc) = *reinterpret_cast<const float4*>(scale + g * 8);
+      *reinterpret_cast<float4*>(sc + 4) = *reinterpret_cast<const float4*>(scale + g * 8 + 4);
+      *reinterpret_cast<float4*>(sh) = *reinterpret_cast<const float4*>(shift + g * 8);
+      *reinterpret_cast<float4*>(sh + 4) = *reinterpret_cast<const float4*>(shift + g * 8 + 4);
 #pragma unroll
       for (int j = 0; j < 8; ++j) mx[j] = 0.f;          // post-ReLU values are >= 0
 #pragma unroll
@@ -286,14 +304,15 @@ __global__ void bn_relu_kernel(const bf16* __restrict__ y, int B, int H, int W, 
     }
   }
 }
-cudaError_t launch_bn_relu(const bf16* y, int B, int H, int W, int C, const float* scale, const float* shift,
-                           bf16* out, int out_pitch, int out_c0, bf16* pooled, cudaStream_t s) {
+cudaError_t launch_bn_relu(const bf16* y, int B, int H, int W, int C, const BnFinalizeArgs& fin, bf16* out,
+                           int out_pitch, int out_c0, bf16* pooled, cudaStream_t s) {
+  const size_t smem = (size_t)2 * C * sizeof(float);
   if (pooled) {
-    bn_relu_kernel<true><<<grid_for((long long)B * (H / 2) * (W / 2) * (C / 8), 256), 256, 0, s>>>(
-        y, B, H, W, C, scale, shift, out, out_pitch, out_c0, pooled);
+    bn_relu_kernel<true><<<grid_for((long long)B * (H / 2) * (W / 2) * (C / 8), 256), 256, smem, s>>>(
+        y, B, H, W, C, fin, out, out_pitch, out_c0, pooled);
   } else {
-    bn_relu_kernel<false><<<grid_for((long long)B * H * W * (C / 8), 256), 256, 0, s>>>(y, B, H, W, C, scale, shift,
-                                                                                         out, out_pitch, out_c0, pooled);
+    bn_relu_kernel<false><<<grid_for((long long)B * H * W * (C / 8), 256), 256, smem, s>>>(y, B, H, W, C, fin, out,
+                                                                                            out_pitch, out_c0, pooled);
   }
   return launched();
 }

@@ -359,7 +359,8 @@ template <int BLOCK_N, int S, int NSTG, int EG>
 __global__ void __launch_bounds__(64 + 128 * EG, 1) pix_gemm2_kernel(const __grid_constant__ PixGemmParams p) {
   using L = Pix2Layout<BLOCK_N, S, NSTG, EG>;
   constexpr bool PAIR = true;
-  static_assert(EG == 1 || NSTG == 2, "two epilogue groups use one staging buffer each");
+  static_assert(NSTG % EG == 0, "every epilogue group owns NSTG / EG staging buffers");
+  constexpr int BPG = NSTG / EG;                             // staging buffers per epilogue group (used round-robin)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
@@ -537,12 +538,9 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) pix_gemm2_kernel(const __gri
         const int col0 = nb * BLOCK_N + cb * 64;
         const int omap = col0 / p.cols_per_map;
         const int nin = col0 - omap * p.cols_per_map;     // first channel of this 64-wide chunk inside its map
-        uint8_t* sbuf = smem + L::kStage + (EG == 2 ? eg : (NSTG == 2 ? (int)(buf_ctr & 1) : 0)) * kStageBytes;
+        uint8_t* sbuf = smem + L::kStage + (eg * BPG + (int)(buf_ctr % BPG)) * kStageBytes;
         ++buf_ctr;
-        if (et == 0) {                                   // the store that last used this buffer has drained
-          if (EG == 2) tma_store_wait_read<0>();
-          else tma_store_wait_read<NSTG - 1>();
-        }
+        if (et == 0) tma_store_wait_read<BPG - 1>();     // the store that last used this buffer has drained
         bar_sync(1 + bar0, 128);
         uint32_t v[64];
         tmem_ld32(taddr + cb * 64, v);

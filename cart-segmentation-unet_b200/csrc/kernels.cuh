@@ -39,9 +39,11 @@ struct BnFinalizeArgs {
 cudaError_t launch_bn_finalize_train(const BnFinalizeArgs& a, cudaStream_t s);
 cudaError_t launch_bn_fold_eval(const float* gamma, const float* beta, const float* conv_bias, const float* rm,
                                 const float* rv, float eps, float* scale, float* shift, int C, cudaStream_t s);
+// Training forward: (scale, shift) are derived from the batch statistics inside the kernel (fused bn_finalize_train:
+// block 0 publishes scale/shift/mean/invstd and updates the running statistics), then
 // out[p][out_c0 + c] = relu(y[p][c]*scale[c] + shift[c]); optional 2x2 max-pooled copy (pitch C)
-cudaError_t launch_bn_relu(const bf16* y, int B, int H, int W, int C, const float* scale, const float* shift,
-                           bf16* out, int out_pitch, int out_c0, bf16* pooled, cudaStream_t s);
+cudaError_t launch_bn_relu(const bf16* y, int B, int H, int W, int C, const BnFinalizeArgs& fin, bf16* out,
+                           int out_pitch, int out_c0, bf16* pooled, cudaStream_t s);
 // relu/bn already applied (eval path): plain 2x2 max-pool of in[p][c0 + c] (pitch in_pitch) -> pooled (pitch C)
 cudaError_t launch_maxpool(const bf16* in, int in_pitch, int in_c0, int B, int H, int W, int C, bf16* pooled,
                            cudaStream_t s);

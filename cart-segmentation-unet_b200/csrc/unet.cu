@@ -152,6 +152,9 @@ static int build_convT_fprop(PixGemmParams& p, int* block_n, View in, int Cin, V
                              const float* bias, int B, int H, int W) {
   // the pair kernel lets one n-block span several (i,j) output maps: N = 256 even for Cout = 64
   *block_n = use_pair() ? pick_block_n(4 * Cout) : pick_block_n(Cout);
+  // short K (Cin <= 256): the launch is paced by its epilogue and by operand traffic from L2, not by the MMAs -> the
+  // N = 128 kernel with its two epilogue groups (up3 fprop 182 -> 134 us; Cin = 512 is slower that way: 75 -> 110 us)
+  if (use_pair() && Cin <= 256 && *block_n == 256) *block_n = 128;
   pix_common(p, B, H, W, Cin, 4 * Cout, *block_n);
   p.G = 1;
   p.R = 1;
@@ -615,8 +618,7 @@ int cs_unet_forward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* x, 
       f.num_batches_tracked = t->num_batches_tracked[i];
       f.momentum = 0.1f; f.eps = 1e-5f;
       f.scale = c.scale; f.shift = c.shift; f.mean = c.mean; f.invstd = c.invstd; f.C = c.cout;
-      CS_CUDA(launch_bn_finalize_train(f, s));
-      CS_CUDA(launch_bn_relu(c.y, B, c.H, c.W, c.cout, c.scale, c.shift, c.out.p, c.out.pitch, c.out.c0, c.pooled, s));
+      CS_CUDA(launch_bn_relu(c.y, B, c.H, c.W, c.cout, f, c.out.p, c.out.pitch, c.out.c0, c.pooled, s));
     } else {
       if (!t->running_mean[i] || !t->running_var[i]) return fail("running statistics of BN %d are null", i);
       CS_CUDA(launch_bn_fold_eval(t->param[c.pgamma], t->param[c.pbeta], t->param[c.pb], t->running_mean[i],
