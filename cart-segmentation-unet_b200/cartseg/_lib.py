@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcartseg.so")
+LIB_PATH = os.environ.get("CARTSEG_LIB_PATH") or os.path.join(_HERE, "libcartseg.so")   # override: A/B runs of two builds
 
 NUM_PARAMS = 82
 NUM_BN = 18
@@ -82,6 +82,8 @@ _SIGNATURES = {
     "cs_unet_backward_wait": (C.c_int, [_P, _P]),
     "cs_unet_profile": (C.c_int, [_P, C.c_int]),
     "cs_unet_profile_read": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    "cs_unet_trace": (C.c_int, [_P, C.c_int]),
+    "cs_unet_trace_read": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "cs_unet_debug_read": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_int), _P, _P]),
     "cs_unet_stage_params": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.c_int]),
     "cs_sdf_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
@@ -132,6 +134,8 @@ def lib() -> C.CDLL:
                 "(or __graft_entry__.build()).  cartseg has no CPU or PyTorch fallback.")
         handle = C.CDLL(LIB_PATH)
         for name, (res, args) in _SIGNATURES.items():
+            if os.environ.get("CARTSEG_LIB_PATH") and not hasattr(handle, name):
+                continue                        # an older build loaded for an A/B run may lack newer developer hooks
             fn = getattr(handle, name)          # AttributeError if the library does not export it
             fn.restype = res
             fn.argtypes = args

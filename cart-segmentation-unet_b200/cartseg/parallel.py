@@ -19,6 +19,9 @@ import torch
 import torch.distributed as dist
 
 
+DEFAULT_BUCKET_MB = 16.0
+
+
 def plan_buckets(stage_off: Sequence[int], bucket_elems: int) -> List[Tuple[int, int]]:
     """Group consecutive backward stages into buckets of at least ``bucket_elems`` gradient elements.
     ``stage_off[s]`` is the flat offset at which stage ``s`` starts (len = stages + 1).
@@ -88,7 +91,7 @@ class GradSync:
 _next_handle = 1
 
 
-def init_data_parallel(model, group: Optional[dist.ProcessGroup] = None, bucket_mb: float = 16.0,
+def init_data_parallel(model, group: Optional[dist.ProcessGroup] = None, bucket_mb: Optional[float] = None,
                        broadcast_from: int = 0, reserve_sms: int = 0):
     """Make ``model`` (a cartseg.UNet) data-parallel over ``group``: broadcast rank-``broadcast_from``'s
     parameters and BN buffers, and hook the bucketed gradient all-reduce into its backward.  Returns the model.
@@ -97,7 +100,10 @@ def init_data_parallel(model, group: Optional[dist.ProcessGroup] = None, bucket_
     not push GEMM CTAs into a second wave.  Measured on 8 x B200 (round 1) it did not pay: 21.3 ms per step with 4
     reserved SMs and NCCL_MAX_NCHANNELS=4 against 20.7 ms with the defaults, so the default is 0."""
     global _next_handle
+    import os
     from . import ops
+    if bucket_mb is None:
+        bucket_mb = float(os.environ.get("CARTSEG_DP_BUCKET_MB", DEFAULT_BUCKET_MB))
     sync = GradSync(group, bucket_mb)
     with torch.no_grad():
         for t in list(model.parameters()) + list(model.buffers()):

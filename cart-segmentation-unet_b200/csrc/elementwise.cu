@@ -242,7 +242,8 @@ cudaError_t launch_bn_fold_eval(const float* gamma, const float* beta, const flo
 // ============================================================================ BN apply + ReLU (+ 2x2 max-pool)
 template <bool POOL>
 __global__ void bn_relu_kernel(const bf16* __restrict__ y, int B, int H, int W, int C, const BnFinalizeArgs fin,
-                               bf16* __restrict__ out, int out_pitch, int out_c0, bf16* __restrict__ pooled) {
+                               bf16* __restrict__ out, int out_pitch, int out_c0, bf16* __restrict__ pooled,
+                               const HeadFwd head) {
   // Fused statistics -> affine step (was a kernel of its own between the convolution and this pass): every block
   // derives (scale, shift) of all C channels into shared memory; block 0 also publishes them for the backward pass
   // and updates the running statistics.
@@ -267,7 +268,20 @@ __global__ void bn_relu_kernel(const bf16* __restrict__ y, int B, int H, int W, 
       *reinterpret_cast<float4*>(sh + 4) = *reinterpret_cast<const float4*>(shift + g * 8 + 4);
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
-      st8(out + p * out_pitch + out_c0 + g * 8, pack8(f));
+      const Vec8 stored = pack8(f);
+      st8(out + p * out_pitch + out_c0 + g * 8, stored);
+      if (head.logits) {
+        // fused 1x1 head (C == 64: the 8 lanes holding one pixel are adjacent): logits = <stored activation, w> + b.
+        // total is a multiple of 32 (H, W multiples of 16), so whole warps are in range together.
+        float r[8], acc = 0.f;
+        unpack8(stored, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc = fmaf(r[j], __ldg(head.w + g * 8 + j), acc);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        if (g == 0) head.logits[p] = acc + (head.b ? __ldg(head.b) : 0.f);
+      }
     }
   } else {
     const int H2 = H >> 1, W2 = W >> 1;
@@ -305,14 +319,15 @@ __global__ void bn_relu_kernel(const bf16* __restrict__ y, int B, int H, int W, 
   }
 }
 cudaError_t launch_bn_relu(const bf16* y, int B, int H, int W, int C, const BnFinalizeArgs& fin, bf16* out,
-                           int out_pitch, int out_c0, bf16* pooled, cudaStream_t s) {
+                           int out_pitch, int out_c0, bf16* pooled, const HeadFwd& head, cudaStream_t s) {
   const size_t smem = (size_t)2 * C * sizeof(float);
+  if (head.logits && (pooled || C != 64 || ((long long)B * H * W) % 4 != 0)) return cudaErrorInvalidValue;
   if (pooled) {
     bn_relu_kernel<true><<<grid_for((long long)B * (H / 2) * (W / 2) * (C / 8), 256), 256, smem, s>>>(
-        y, B, H, W, C, fin, out, out_pitch, out_c0, pooled);
+        y, B, H, W, C, fin, out, out_pitch, out_c0, pooled, head);
   } else {
     bn_relu_kernel<false><<<grid_for((long long)B * H * W * (C / 8), 256), 256, smem, s>>>(y, B, H, W, C, fin, out,
-                                                                                            out_pitch, out_c0, pooled);
+                                                                                            out_pitch, out_c0, pooled, head);
   }
   return launched();
 }
@@ -354,7 +369,7 @@ cudaError_t launch_maxpool(const bf16* in, int in_pitch, int in_c0, int B, int H
 // over pixels (or 2x2 windows) with 16-byte loads.  Two passes over (g, y): pass 1 reduces sum(gm) and sum(gm*xhat)
 // per channel — per-block partials, combined in a fixed order, so the backward pass is run-to-run deterministic —
 // pass 2 writes dy.
-struct BnCoef { float sc[8], sh[8], mu[8], is[8]; };
+struct BnCoef { float sc[8], sh[8], mu[8], is[8], hw[8]; };   // hw: head weights (only when the gradient comes from the head)
 CS_DEVINL void load8(const float* p, float* d) {
   *reinterpret_cast<float4*>(d) = __ldg(reinterpret_cast<const float4*>(p));
   *reinterpret_cast<float4*>(d + 4) = __ldg(reinterpret_cast<const float4*>(p + 4));
@@ -364,6 +379,7 @@ CS_DEVINL void load_coef(const BnBwdArgs& a, int g, BnCoef& k) {
   load8(a.shift + g * 8, k.sh);
   load8(a.mean + g * 8, k.mu);
   load8(a.invstd + g * 8, k.is);
+  if (a.head_dlogits) load8(a.head_w + g * 8, k.hw);
 }
 // Computes, for one pixel (no pool) or one 2x2 window (pool), the masked gradient gm[d][8] and xhat[d][8].
 template <bool POOL>
@@ -385,7 +401,17 @@ CS_DEVINL void masked_grad(const BnBwdArgs& a, const BnCoef& k, int g, long long
 #pragma unroll
   for (int d = 0; d < ND; ++d) {                         // issue every load before the first use
     yv8[d] = ld8(a.y + pix[d] * a.C + g * 8);
-    gv8[d] = ld8(a.g + pix[d] * a.g_pitch + a.g_c0 + g * 8);
+    if (!POOL && a.head_dlogits) {
+      // the layer feeds the 1x1 head: its activation gradient dlogits[p] * w[c] (rounded to bf16, as the stand-alone
+      // head backward used to store it) is formed here instead of being written to and read back from HBM twice
+      const float dl = __ldg(a.head_dlogits + pix[d]);
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = dl * k.hw[j];
+      gv8[d] = pack8(o);
+    } else {
+      gv8[d] = ld8(a.g + pix[d] * a.g_pitch + a.g_c0 + g * 8);
+    }
   }
 #pragma unroll
   for (int d = 0; d < ND; ++d) {
@@ -418,6 +444,44 @@ CS_DEVINL void masked_grad(const BnBwdArgs& a, const BnCoef& k, int g, long long
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       if (!(act[d][j] > 0.f)) gm[d][j] = 0.f;
+}
+
+// Non-pooled layers, split into a load phase and a compute phase so that a thread can have several units' loads in
+// flight before the first use (the kernels run at two blocks per SM: memory parallelism has to come from the thread).
+struct PlainUnit { Vec8 y, g; };
+CS_DEVINL Vec8 ld8_nc(const bf16* p) {
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+  Vec8 r;
+  r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
+  return r;
+}
+CS_DEVINL void plain_load(const BnBwdArgs& a, const BnCoef& k, int g, long long pix, PlainUnit& u) {
+  u.y = ld8_nc(a.y + pix * a.C + g * 8);
+  if (a.head_dlogits) {
+    // the layer feeds the 1x1 head: its activation gradient dlogits[p] * w[c] (rounded to bf16, as the stand-alone
+    // head backward used to store it) is formed here instead of being written to and read back from HBM twice
+    const float dl = __ldg(a.head_dlogits + pix);
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = dl * k.hw[j];
+    u.g = pack8(o);
+  } else {
+    u.g = ld8_nc(a.g + pix * a.g_pitch + a.g_c0 + g * 8);
+  }
+}
+// gm[j] = g[j] where the stored (bf16-rounded) activation is positive, else 0;  xh[j] = (y - mean) * invstd
+CS_DEVINL void plain_compute(const BnCoef& k, const PlainUnit& u, float gm[8], float xh[8]) {
+  float yv[8], t[8], act[8];
+  unpack8(u.y, yv);
+  unpack8(u.g, gm);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) t[j] = fmaxf(fmaf(yv[j], k.sc[j], k.sh[j]), 0.f);
+  unpack8(pack8(t), act);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    xh[j] = (yv[j] - k.mu[j]) * k.is[j];
+    if (!(act[j] > 0.f)) gm[j] = 0.f;
+  }
 }
 
 // Pooled layers, register-lean formulation: the four pixels of a 2x2 window stay packed (bf16) and are unpacked one
@@ -464,22 +528,27 @@ CS_DEVINL void pooled_unit(const BnBwdArgs& a, const BnCoef& k, int g, long long
 }
 
 static constexpr int kBnBwdThreads = 256;
-static constexpr int kBnBwdMaxBlocks = 148 * 4;          // partials: [blocks][2*C] floats
+static constexpr int kBnBwdMaxBlocks = 148 * 4;
 
-size_t bn_bwd_scratch_bytes(int maxC) { return (size_t)kBnBwdMaxBlocks * 2 * maxC * sizeof(float); }
+// Partial sums: one row of 2*C floats per (block, row group).  Row groups per block: 8 (one per warp) when a warp
+// holds whole pixel rows (C <= 256), else 256 / (C/8) pixel rows of several warps each.  Rows x 2C <= 4096 floats.
+static int bn_bwd_rows_per_block(int C) { return C <= 256 ? 8 : kBnBwdThreads / (C / 8); }
+size_t bn_bwd_scratch_bytes(int maxC) { return (size_t)kBnBwdMaxBlocks * 4 * maxC * sizeof(float); }
 
-// One full wave of resident blocks (3 per SM without pooling, 2 with: see the launch bounds) — a partial second
-// wave costs these bandwidth-bound kernels its whole duration again.
+// Grid: two blocks per SM without pooling.  These kernels use no shared memory and <= 85 registers per thread so that
+// two of their blocks fit on an SM NEXT TO a resident weight-gradient CTA (192 threads x 49 registers, ~210 KB of
+// shared memory): the HBM-bound BN backward of layer L-1 then really runs under the tensor-bound wgrad of layer L
+// (cs_unet_backward issues them on two streams).  With three blocks per SM the register file is full and the wgrad
+// CTAs cannot be placed until the BN kernel has drained, which serialises the two.
 static int bn_bwd_grid(const BnBwdArgs& a) {
   const int rpb = kBnBwdThreads / (a.C / 8);
   const long long units = a.g_pool ? (long long)a.B * (a.H / 2) * (a.W / 2) : (long long)a.B * a.H * a.W;
-  return grid_for(units, rpb * 2, a.g_pool ? 148 * 2 : 148 * 3);
+  return grid_for(units, rpb * 2, 148 * 2);
 }
 
 template <bool POOL>
-__global__ void __launch_bounds__(kBnBwdThreads, POOL ? 2 : 3) bn_bwd_reduce_kernel(BnBwdArgs a) {
+__global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(POOL ? 128 : 104) bn_bwd_reduce_kernel(BnBwdArgs a) {
   constexpr int ND = POOL ? 4 : 1;
-  __shared__ float sm[16 * kBnBwdThreads];               // [rows per block][2*C]  (rpb * 2C == 16 * threads)
   const int cg = a.C >> 3;
   const int g = threadIdx.x % cg, ri = threadIdx.x / cg, rpb = kBnBwdThreads / cg;
   const long long units = POOL ? (long long)a.B * (a.H >> 1) * (a.W >> 1) : (long long)a.B * a.H * a.W;
@@ -494,25 +563,52 @@ __global__ void __launch_bounds__(kBnBwdThreads, POOL ? 2 : 3) bn_bwd_reduce_ker
       pooled_unit(a, k, g, u, pix, [&](int, int j, float gmv, float xhv) { s1[j] += gmv; s2[j] = fmaf(gmv, xhv, s2[j]); });
     }
   } else {
-#pragma unroll 2
-    for (long long u = (long long)blockIdx.x * rpb + ri; u < units; u += (long long)gridDim.x * rpb) {
-      float gm[ND][8], xh[ND][8];
-      long long pix[ND];
-      masked_grad<POOL>(a, k, g, u, gm, xh, pix);
+    constexpr int U = 4;
+    const long long stride = (long long)gridDim.x * rpb;
+    for (long long u0 = (long long)blockIdx.x * rpb + ri; u0 < units; u0 += U * stride) {
+      PlainUnit pu[U];
 #pragma unroll
-      for (int d = 0; d < ND; ++d)
+      for (int i = 0; i < U; ++i)
+        if (u0 + i * stride < units) plain_load(a, k, g, u0 + i * stride, pu[i]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { s1[j] += gm[d][j]; s2[j] = fmaf(gm[d][j], xh[d][j], s2[j]); }
+      for (int i = 0; i < U; ++i) {
+        if (u0 + i * stride >= units) break;
+        float gm[8], xh[8];
+        plain_compute(k, pu[i], gm, xh);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s1[j] += gm[j]; s2[j] = fmaf(gm[j], xh[j], s2[j]); }
+      }
     }
   }
-  float* row = sm + (size_t)ri * 2 * a.C;
+  // Combine the pixel rows that share a warp with a fixed shuffle pattern (deterministic), then one partial row per
+  // row group goes straight to global memory: no shared memory, see bn_bwd_grid.
+  int rows_per_block, my_row;
+  bool writer;
+  if (cg <= 32) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { row[g * 8 + j] = s1[j]; row[a.C + g * 8 + j] = s2[j]; }
-  __syncthreads();
-  for (int c = threadIdx.x; c < 2 * a.C; c += kBnBwdThreads) {   // fixed-order combine over the block's rows
-    float t = 0.f;
-    for (int r = 0; r < rpb; ++r) t += sm[(size_t)r * 2 * a.C + c];
-    a.partial[(size_t)blockIdx.x * 2 * a.C + c] = t;
+    for (int o = 16; o >= 8; o >>= 1) {
+      if (o >= cg) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
+          s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
+        }
+      }
+    }
+    rows_per_block = kBnBwdThreads / 32;
+    my_row = threadIdx.x >> 5;
+    writer = (threadIdx.x & 31) < cg;
+  } else {
+    rows_per_block = rpb;
+    my_row = ri;
+    writer = true;
+  }
+  if (writer) {
+    float* row = a.partial + ((size_t)blockIdx.x * rows_per_block + my_row) * 2 * a.C;
+    *reinterpret_cast<float4*>(row + g * 8) = make_float4(s1[0], s1[1], s1[2], s1[3]);
+    *reinterpret_cast<float4*>(row + g * 8 + 4) = make_float4(s1[4], s1[5], s1[6], s1[7]);
+    *reinterpret_cast<float4*>(row + a.C + g * 8) = make_float4(s2[0], s2[1], s2[2], s2[3]);
+    *reinterpret_cast<float4*>(row + a.C + g * 8 + 4) = make_float4(s2[4], s2[5], s2[6], s2[7]);
   }
 }
 
@@ -549,12 +645,12 @@ cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t s) {
   else bn_bwd_reduce_kernel<false><<<grid, kBnBwdThreads, 0, s>>>(a);
   cudaError_t e = launched();
   if (e != cudaSuccess) return e;
-  bn_bwd_finalize_kernel<<<(a.C + 7) / 8, 256, 0, s>>>(a, grid);
+  bn_bwd_finalize_kernel<<<(a.C + 7) / 8, 256, 0, s>>>(a, grid * bn_bwd_rows_per_block(a.C));
   return launched();
 }
 
 template <bool POOL>
-__global__ void __launch_bounds__(kBnBwdThreads, POOL ? 2 : 3) bn_bwd_apply_kernel(BnBwdArgs a) {
+__global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(POOL ? 128 : 104) bn_bwd_apply_kernel(BnBwdArgs a) {
   constexpr int ND = POOL ? 4 : 1;
   const int cg = a.C >> 3;
   const int g = threadIdx.x % cg, ri = threadIdx.x / cg, rpb = kBnBwdThreads / cg;
@@ -578,17 +674,22 @@ __global__ void __launch_bounds__(kBnBwdThreads, POOL ? 2 : 3) bn_bwd_apply_kern
       for (int d = 0; d < 4; ++d) st8(a.dy + pix[d] * a.C + g * 8, out[d]);
     }
   } else {
-#pragma unroll 2
-    for (long long u = (long long)blockIdx.x * rpb + ri; u < units; u += (long long)gridDim.x * rpb) {
-      float gm[ND][8], xh[ND][8];
-      long long pix[ND];
-      masked_grad<POOL>(a, k, g, u, gm, xh, pix);
+    constexpr int U = 3;
+    const long long stride = (long long)gridDim.x * rpb;
+    for (long long u0 = (long long)blockIdx.x * rpb + ri; u0 < units; u0 += U * stride) {
+      PlainUnit pu[U];
 #pragma unroll
-      for (int d = 0; d < ND; ++d) {
-        float o[8];
+      for (int i = 0; i < U; ++i)
+        if (u0 + i * stride < units) plain_load(a, k, g, u0 + i * stride, pu[i]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = k.sc[j] * (gm[d][j] - c1[j] - xh[d][j] * c2[j]);
-        st8(a.dy + pix[d] * a.C + g * 8, pack8(o));
+      for (int i = 0; i < U; ++i) {
+        const long long u = u0 + i * stride;
+        if (u >= units) break;
+        float gm[8], xh[8], o[8];
+        plain_compute(k, pu[i], gm, xh);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = k.sc[j] * (gm[j] - c1[j] - xh[j] * c2[j]);
+        st8(a.dy + u * a.C + g * 8, pack8(o));
       }
     }
   }
@@ -648,7 +749,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const bf16* __restrict__ 
       unpack8(ld8(act + p * C + g * 8), f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) { acc[j] = fmaf(d, f[j], acc[j]); o[j] = d * wv[j]; }
-      st8(g_act + p * C + g * 8, pack8(o));
+      if (g_act) st8(g_act + p * C + g * 8, pack8(o));
       if (g == 0) accb += d;
     }
 #pragma unroll
@@ -659,6 +760,26 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const bf16* __restrict__ 
   for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&grad_w[i], sacc[i]);
   if (threadIdx.x == 0 && grad_b) atomicAdd(grad_b, sacc[C]);
 }
+// g_act only (test hook: materialises the activation gradient the fused BN backward forms on the fly)
+__global__ void head_grad_act_kernel(const float* __restrict__ dlogits, long long P, int C, const float* __restrict__ w,
+                                     bf16* __restrict__ g_act) {
+  const int cg = C >> 3;
+  const long long total = P * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    const long long p = i / cg;
+    const float d = __ldg(dlogits + p);
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = d * __ldg(w + g * 8 + j);
+    st8(g_act + p * C + g * 8, pack8(o));
+  }
+}
+cudaError_t launch_head_grad_act(const float* dlogits, long long P, int C, const float* w, bf16* g_act, cudaStream_t s) {
+  head_grad_act_kernel<<<grid_for(P * (C / 8), 256), 256, 0, s>>>(dlogits, P, C, w, g_act);
+  return launched();
+}
+
 cudaError_t launch_head_bwd(const bf16* act, const float* dlogits, long long P, int C, const float* w, bf16* g_act,
                             float* grad_w, float* grad_b, cudaStream_t s) {
   const int rpb = 256 / (C / 8);

@@ -42,14 +42,19 @@ cudaError_t launch_bn_fold_eval(const float* gamma, const float* beta, const flo
 // Training forward: (scale, shift) are derived from the batch statistics inside the kernel (fused bn_finalize_train:
 // block 0 publishes scale/shift/mean/invstd and updates the running statistics), then
 // out[p][out_c0 + c] = relu(y[p][c]*scale[c] + shift[c]); optional 2x2 max-pooled copy (pitch C)
+// head.logits != NULL (last layer, C == 64, no pooling): the 1x1 head is evaluated in the same pass,
+// logits[p] = sum_c out[p][c] * w[c] + b  on the bf16 values as stored.
+struct HeadFwd { const float* w; const float* b; float* logits; };
 cudaError_t launch_bn_relu(const bf16* y, int B, int H, int W, int C, const BnFinalizeArgs& fin, bf16* out,
-                           int out_pitch, int out_c0, bf16* pooled, cudaStream_t s);
+                           int out_pitch, int out_c0, bf16* pooled, const HeadFwd& head, cudaStream_t s);
 // relu/bn already applied (eval path): plain 2x2 max-pool of in[p][c0 + c] (pitch in_pitch) -> pooled (pitch C)
 cudaError_t launch_maxpool(const bf16* in, int in_pitch, int in_c0, int B, int H, int W, int C, bf16* pooled,
                            cudaStream_t s);
 
 struct BnBwdArgs {
   const bf16* g; int g_pitch, g_c0;        // gradient w.r.t. the post-ReLU activation
+  const float* head_dlogits;               // optional (no pooling): g[p][c] = bf16(head_dlogits[p] * head_w[c]) instead of `g`
+  const float* head_w;
   const bf16* g_pool;                      // optional: gradient w.r.t. the 2x2-pooled activation (pitch C)
   const bf16* y;                           // raw conv output (pitch C)
   const float* scale; const float* shift; const float* mean; const float* invstd;
@@ -68,7 +73,8 @@ cudaError_t launch_head_fwd(const bf16* act, long long P, int C, const float* w,
                             cudaStream_t s);
 // g_act[p][c] = dlogits[p]*w[c];  grad_w[c] += sum_p dlogits[p]*act[p][c];  grad_b += sum_p dlogits[p]
 cudaError_t launch_head_bwd(const bf16* act, const float* dlogits, long long P, int C, const float* w, bf16* g_act,
-                            float* grad_w, float* grad_b, cudaStream_t s);
+                            float* grad_w, float* grad_b, cudaStream_t s);   // g_act may be NULL (not materialised)
+cudaError_t launch_head_grad_act(const float* dlogits, long long P, int C, const float* w, bf16* g_act, cudaStream_t s);
 
 // ---- conv-transpose bias gradient -------------------------------------------------------------
 // grad_b[c] = sum_p g[p][c0 + c]

@@ -306,6 +306,8 @@ struct cs_unet_plan {
   bf16* col;                         // im2col of the input image [P1][64]
   float* dwp;                        // packed weight-gradient accumulator, shared by all layers
   float* bn_partial;                 // per-block partial sums of the BN backward reduction
+  float* dlogits_keep;               // copy of the last dlogits (the head's activation gradient is formed on the fly)
+  const float* head_w_keep;          // final_conv.weight of the last backward (device pointer owned by the caller)
   uint8_t* stats_begin;
   size_t stats_bytes;
   // optional per-launch timing of the tensor-core kernels (cs_unet_profile): CUDA events around each GEMM launch
@@ -317,6 +319,11 @@ struct cs_unet_plan {
   std::vector<int> prof_class;
   std::vector<double> prof_flops;
   size_t prof_used;
+  // developer timeline of the backward pass (cs_unet_trace): an event pair around every launch, on either stream
+  bool tracing;
+  std::vector<cudaEvent_t> trace_events;
+  std::vector<int> trace_label;
+  size_t trace_used;
 };
 
 namespace {
@@ -348,6 +355,28 @@ cudaError_t timed(cs_unet_plan* pl, int cls, double flops, cudaStream_t s, F&& l
   e = launch();
   if (e != cudaSuccess) return e;
   return cudaEventRecord(pl->prof_events[2 * i + 1], s);
+}
+// Runs `launch` between two timing events on `s` when tracing is on (label = kind * 100 + layer index).
+template <typename F>
+cudaError_t traced(cs_unet_plan* pl, int label, cudaStream_t s, F&& launch) {
+  if (!pl->tracing) return launch();
+  if (pl->trace_events.size() < 2 * (pl->trace_used + 1)) {
+    cudaEvent_t a, b;
+    cudaError_t e = cudaEventCreate(&a);
+    if (e != cudaSuccess) return e;
+    e = cudaEventCreate(&b);
+    if (e != cudaSuccess) return e;
+    pl->trace_events.push_back(a);
+    pl->trace_events.push_back(b);
+    pl->trace_label.push_back(0);
+  }
+  const size_t i = pl->trace_used++;
+  pl->trace_label[i] = label;
+  cudaError_t e = cudaEventRecord(pl->trace_events[2 * i], s);
+  if (e != cudaSuccess) return e;
+  e = launch();
+  if (e != cudaSuccess) return e;
+  return cudaEventRecord(pl->trace_events[2 * i + 1], s);
 }
 }  // namespace
 
@@ -470,6 +499,7 @@ void layout(cs_unet_plan* pl, uint8_t* base) {
   }
   pl->dwp = train ? a.take<float>(dwp_elems) : nullptr;
   pl->bn_partial = train ? reinterpret_cast<float*>(a.take<uint8_t>(bn_bwd_scratch_bytes(1024))) : nullptr;
+  pl->dlogits_keep = train ? a.take<float>((size_t)pl->B * pl->H * pl->W) : nullptr;
   // statistics (zeroed once per forward): forward sums and backward sums of every BN
   a.off = (a.off + 1023) & ~(size_t)1023;
   pl->stats_begin = base + a.off;
@@ -597,6 +627,15 @@ int cs_unet_pack_weights(cs_unet_plan* pl, const cs_unet_tensors* t, cs_stream_t
   return 0;
 }
 
+// CARTSEG_FUSE_HEAD=0 restores the stand-alone 1x1 head kernels (A/B measurements).
+static bool fuse_head() {
+  static const bool v = [] {
+    const char* e = getenv("CARTSEG_FUSE_HEAD");
+    return !(e && e[0] == '0');
+  }();
+  return v;
+}
+
 int cs_unet_forward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* x, int training, float* logits,
                     cs_stream_t stream) {
   if (!pl || !pl->bound) return fail("plan is not bound to a workspace");
@@ -618,7 +657,9 @@ int cs_unet_forward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* x, 
       f.num_batches_tracked = t->num_batches_tracked[i];
       f.momentum = 0.1f; f.eps = 1e-5f;
       f.scale = c.scale; f.shift = c.shift; f.mean = c.mean; f.invstd = c.invstd; f.C = c.cout;
-      CS_CUDA(launch_bn_relu(c.y, B, c.H, c.W, c.cout, f, c.out.p, c.out.pitch, c.out.c0, c.pooled, s));
+      // the last layer's pass also evaluates the 1x1 head (final_conv) on the activations it has just produced
+      const HeadFwd head = (i == 17 && fuse_head()) ? HeadFwd{t->param[80], t->param[81], logits} : HeadFwd{nullptr, nullptr, nullptr};
+      CS_CUDA(launch_bn_relu(c.y, B, c.H, c.W, c.cout, f, c.out.p, c.out.pitch, c.out.c0, c.pooled, head, s));
     } else {
       if (!t->running_mean[i] || !t->running_var[i]) return fail("running statistics of BN %d are null", i);
       CS_CUDA(launch_bn_fold_eval(t->param[c.pgamma], t->param[c.pbeta], t->param[c.pb], t->running_mean[i],
@@ -637,7 +678,7 @@ int cs_unet_forward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* x, 
     CS_TRY(run_conv(11 + 2 * k));
   }
   const ConvL& last = pl->conv[17];
-  CS_CUDA(launch_head_fwd(last.out.p, last.P, 64, t->param[80], t->param[81], logits, s));
+  if (!training || !fuse_head()) CS_CUDA(launch_head_fwd(last.out.p, last.P, 64, t->param[80], t->param[81], logits, s));
   pl->forward_done = training != 0;
   return 0;
 }
@@ -724,19 +765,37 @@ int cs_unet_backward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* dl
       if (!dlogits) return fail("dlogits is null");
       const ConvL& last = pl->conv[17];
       if (!t->grad[80] || !t->grad[81]) return fail("gradient buffers of final_conv are null");
-      CS_CUDA(launch_head_bwd(last.out.p, dlogits, last.P, 64, t->param[80], last.g_out.p, t->grad[80], t->grad[81], s));
+      // The head's input gradient dlogits * w is not materialised: the BN backward of the last layer forms it on the
+      // fly (BnBwdArgs::head_dlogits).  What is left of the head backward only produces parameter gradients, so it
+      // goes to the weight-gradient stream, off the critical path.
+      if (!t->param[80]) return fail("final_conv.weight is null");
+      if (!fuse_head()) {
+        CS_CUDA(launch_head_bwd(last.out.p, dlogits, last.P, 64, t->param[80], last.g_out.p, t->grad[80], t->grad[81], s));
+        continue;
+      }
+      if (overlap) {
+        CS_CUDA(cudaEventRecord(pl->ev_stage[stage], s));
+        CS_CUDA(cudaStreamWaitEvent(sw, pl->ev_stage[stage], 0));
+      }
+      CS_CUDA(traced(pl, 600, sw, [&] { return launch_head_bwd(last.out.p, dlogits, last.P, 64, t->param[80], nullptr, t->grad[80], t->grad[81], sw); }));
+      CS_CUDA(cudaMemcpyAsync(pl->dlogits_keep, dlogits, (size_t)last.P * sizeof(float), cudaMemcpyDeviceToDevice, sw));
+      pl->head_w_keep = t->param[80];
     } else if (kind == 1) {
       ConvL& c = pl->conv[idx];
       if (idx < frozen_encoder_convs) continue;          // nothing below a frozen prefix needs gradients
       BnBwdArgs a{};
       a.g = c.g_out.p; a.g_pitch = c.g_out.pitch; a.g_c0 = c.g_out.c0;
       a.g_pool = c.g_pool; a.y = c.y;
+      if (idx == 17 && fuse_head()) {
+        if (!dlogits) return fail("dlogits is null");
+        a.head_dlogits = dlogits; a.head_w = t->param[80];
+      }
       a.scale = c.scale; a.shift = c.shift; a.mean = c.mean; a.invstd = c.invstd;
       a.partial = pl->bn_partial; a.c1 = c.bc1; a.c2 = c.bc2; a.dy = c.dy;
       a.grad_gamma = t->grad[c.pgamma]; a.grad_beta = t->grad[c.pbeta]; a.grad_conv_bias = t->grad[c.pb];
       a.B = B; a.H = c.H; a.W = c.W; a.C = c.cout;
-      CS_CUDA(launch_bn_bwd_reduce(a, s));
-      CS_CUDA(launch_bn_bwd_apply(a, s));
+      CS_CUDA(traced(pl, 100 + idx, s, [&] { return launch_bn_bwd_reduce(a, s); }));
+      CS_CUDA(traced(pl, 200 + idx, s, [&] { return launch_bn_bwd_apply(a, s); }));
       if (t->grad[c.pw]) {
         if (overlap) {                                    // dy is final: the wgrad may start on the side stream
           CS_CUDA(cudaEventRecord(pl->ev_stage[stage], s));
@@ -744,25 +803,25 @@ int cs_unet_backward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* dl
         }
         const size_t e = (size_t)(idx == 0 ? 1 : 9) * c.cout * c.cin;
         CS_CUDA(cudaMemsetAsync(pl->dwp, 0, e * sizeof(float), sw));
-        CS_CUDA(timed(pl, wgrad_class(c.bn_w), c.flops, sw, [&] { return launch_wgrad_gemm(c.wg, c.bn_w, sw); }));
+        CS_CUDA(traced(pl, 400 + idx, sw, [&] { return timed(pl, wgrad_class(c.bn_w), c.flops, sw, [&] { return launch_wgrad_gemm(c.wg, c.bn_w, sw); }); }));
         if (idx == 0) CS_CUDA(launch_unpack_first(pl->dwp, c.cout, pl->Cin, t->grad[c.pw], sw));
         else CS_CUDA(launch_unpack_pairs(pl->dwp, c.cout, c.cin, 9, kTapWgrad, t->grad[c.pw], sw));
       }
       if (idx > 0 && idx > frozen_encoder_convs)
-        CS_CUDA(timed(pl, pix_class(c.bn_d), c.flops, s, [&] { return launch_pix_gemm(c.dg, c.bn_d, pl->num_sms, s); }));
+        CS_CUDA(traced(pl, 300 + idx, s, [&] { return timed(pl, pix_class(c.bn_d), c.flops, s, [&] { return launch_pix_gemm(c.dg, c.bn_d, pl->num_sms, s); }); }));
     } else {
       UpL& u = pl->up[idx];
       if (overlap && (t->grad[u.pb] || t->grad[u.pw])) {  // g_out of the conv-transpose is final on the main stream
         CS_CUDA(cudaEventRecord(pl->ev_stage[stage], s));
         CS_CUDA(cudaStreamWaitEvent(sw, pl->ev_stage[stage], 0));
       }
-      if (t->grad[u.pb]) CS_CUDA(launch_channel_sum(u.g_out.p, u.g_out.pitch, u.g_out.c0, 4 * u.P, u.cout, t->grad[u.pb], sw));
+      if (t->grad[u.pb]) CS_CUDA(traced(pl, 900 + idx, sw, [&] { return launch_channel_sum(u.g_out.p, u.g_out.pitch, u.g_out.c0, 4 * u.P, u.cout, t->grad[u.pb], sw); }));
       if (t->grad[u.pw]) {
         CS_CUDA(cudaMemsetAsync(pl->dwp, 0, (size_t)4 * u.cin * u.cout * sizeof(float), sw));
-        CS_CUDA(timed(pl, wgrad_class(u.bn_w), u.flops, sw, [&] { return launch_wgrad_gemm(u.wg, u.bn_w, sw); }));
+        CS_CUDA(traced(pl, 800 + idx, sw, [&] { return timed(pl, wgrad_class(u.bn_w), u.flops, sw, [&] { return launch_wgrad_gemm(u.wg, u.bn_w, sw); }); }));
         CS_CUDA(launch_unpack_pairs(pl->dwp, u.cin, u.cout, 4, kTapIdent, t->grad[u.pw], sw));
       }
-      CS_CUDA(timed(pl, pix_class(u.bn_d), u.flops, s, [&] { return launch_pix_gemm(u.dg, u.bn_d, pl->num_sms, s); }));
+      CS_CUDA(traced(pl, 700 + idx, s, [&] { return timed(pl, pix_class(u.bn_d), u.flops, s, [&] { return launch_pix_gemm(u.dg, u.bn_d, pl->num_sms, s); }); }));
     }
   }
   if (overlap) {                                          // join: the caller's stream continues after both
@@ -810,6 +869,29 @@ int cs_unet_set_overlap(cs_unet_plan* pl, int enable) {
   if (!pl) return fail("plan is null");
   pl->no_overlap = enable == 0;
   return 0;
+}
+
+int cs_unet_trace(cs_unet_plan* pl, int enable) {
+  if (!pl) return fail("plan is null");
+  pl->tracing = enable != 0;
+  pl->trace_used = 0;
+  return 0;
+}
+
+int cs_unet_trace_read(cs_unet_plan* pl, int capacity, int* labels, double* begin_ms, double* end_ms) {
+  if (!pl || !labels || !begin_ms || !end_ms) return fail("cs_unet_trace_read: null pointer");
+  const size_t n = pl->trace_used < (size_t)capacity ? pl->trace_used : (size_t)capacity;
+  for (size_t i = 0; i < n; ++i) {
+    CS_CUDA(cudaEventSynchronize(pl->trace_events[2 * i + 1]));
+    float t0 = 0.f, t1 = 0.f;
+    CS_CUDA(cudaEventElapsedTime(&t0, pl->trace_events[0], pl->trace_events[2 * i]));
+    CS_CUDA(cudaEventElapsedTime(&t1, pl->trace_events[0], pl->trace_events[2 * i + 1]));
+    labels[i] = pl->trace_label[i];
+    begin_ms[i] = t0;
+    end_ms[i] = t1;
+  }
+  pl->trace_used = 0;
+  return (int)n;
 }
 
 int cs_unet_profile_read(cs_unet_plan* pl, int n_classes, double* ms, double* flops, long long* launches) {
@@ -860,6 +942,11 @@ int cs_unet_debug_read(cs_unet_plan* pl, int kind, int index, int dims_out[4], f
   if (dims_out) { dims_out[0] = pl->B; dims_out[1] = C; dims_out[2] = H; dims_out[3] = W; }
   if (!dst) return 0;
   if (!v.p) return fail("tensor (kind %d, index %d) does not exist in this plan", kind, index);
+  if (kind == 3 && index == 17 && fuse_head()) {
+    // never written by the training path: materialise dlogits * w from the copies kept by the last backward
+    if (!pl->head_w_keep) return fail("no backward pass has run on this plan yet");
+    CS_CUDA(launch_head_grad_act(pl->dlogits_keep, pl->conv[17].P, 64, pl->head_w_keep, v.p, static_cast<cudaStream_t>(stream)));
+  }
   CS_CUDA(launch_nhwc_to_nchw_f32(v.p, v.pitch, v.c0, pl->B, H, W, C, dst, static_cast<cudaStream_t>(stream)));
   return 0;
 }

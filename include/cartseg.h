@@ -102,6 +102,12 @@ int cs_unet_backward_wait(cs_unet_plan* plan, cs_stream_t stream);
 #define CS_UNET_NUM_PROFILE_CLASSES 5
 int cs_unet_profile(cs_unet_plan* plan, int enable);
 int cs_unet_profile_read(cs_unet_plan* plan, int n_classes, double* ms, double* flops, long long* launches);
+/* Developer timeline of cs_unet_backward: while enabled, every launch of the backward pass (both internal streams) is
+ * bracketed by timing events.  cs_unet_trace_read waits for them and returns, per launch, a label (kind * 100 + layer:
+ * 1 BN-backward reduce, 2 BN-backward apply, 3 conv dgrad, 4 conv wgrad, 6 head, 7 conv-transpose dgrad, 8 its wgrad,
+ * 9 its bias gradient) and begin / end times in ms relative to the first launch.  Returns the number of entries. */
+int cs_unet_trace(cs_unet_plan* plan, int enable);
+int cs_unet_trace_read(cs_unet_plan* plan, int capacity, int* labels, double* begin_ms, double* end_ms);
 /* Test hook: copies one internal NHWC bf16 tensor of the plan into `dst` as dense fp32 NCHW (dst == NULL: only
  * report dims_out = {B, C, H, W}).  kind 0..5 index a conv (0..17): raw output, activation, grad wrt raw output,
  * grad wrt activation, pooled activation, grad wrt pooled; kind 6/7 index a conv-transpose (0..3): output, its grad. */

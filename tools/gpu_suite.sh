@@ -28,10 +28,18 @@ for part in "$@"; do
     unet)   run test_gpu_unet 1200 python -m pytest tests/test_gpu_unet.py -m gpu -q --tb=short -s --timeout 600 ;;
     smoke)  run smoke 600 python -c "import __graft_entry__ as g; g.smoke()" ;;
     bench)  run bench 900 python bench.py --steps 5 --warmup 3 ;;
+    bench_nohead) CARTSEG_FUSE_HEAD=0 run bench_nohead 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline ;;
+    bench10) run bench10 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline ;;
+    bench_nooverlap) CARTSEG_OVERLAP=0 run bench_nooverlap 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline ;;
+    trace)  run trace_backward 600 python tools/trace_backward.py ;;
+    bench_committed) CARTSEG_LIB_PATH=$PWD/cart-segmentation-unet_b200/cartseg/libcartseg_committed.so run bench_committed 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline ;;
     bench3) run bench_k3 900 python bench.py --steps 3 --warmup 3 --workload k3 --no-cpu-baseline ;;
     bench4) run bench_k4 900 python bench.py --steps 5 --warmup 3 --workload k4 --no-cpu-baseline ;;
     bench8gpu) run bench_8gpu 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --steps 10 --warmup 3 ;;
     bench4gpu) run bench_4gpu 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29522 bench.py --gpus 4 --steps 10 --warmup 3 ;;
+    dp2) run dp_parity_2gpu 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/dp_parity.py ;;
+    bench2gpu_nooverlap) CARTSEG_DP_BUCKET_MB=100000 run bench_2gpu_nooverlap 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 5 --warmup 3 ;;
+    bench2gpu_maxctas) NCCL_MAX_CTAS=4 run bench_2gpu_maxctas 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 2 --steps 5 --warmup 3 ;;
     bench2gpu) run bench_2gpu 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 ;;
     aux)    run bench_aux 900 python tools/bench_aux.py ;;
     aux512) run bench_aux512 900 python tools/bench_aux.py --batch 32 --size 512 --no-cpu ;;
@@ -42,6 +50,7 @@ for part in "$@"; do
     launches) run profile_plain 300 python tools/profile_step.py && \
             run ncu_launches 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none \
                 --csv --log-file gpurun_out/launches.csv python tools/profile_step.py ;;
+    launches3) run ncu_launches_k3 1200 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_k3.csv python tools/profile_step.py --batch 32 --size 512 ;;
     traffic) run ncu_traffic 900 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/step_traffic.csv python tools/profile_step.py ;;
     ncufull) run profile_plain 300 python tools/profile_step.py && \
             run ncu_pix 1500 ncu --profile-from-start off --set full --clock-control none --import-source on \
