@@ -200,18 +200,27 @@ static void wgrad_common(WgradParams& p, int* block_n, int M, int N, int B, int 
   const int tiles = p.tiles_w * p.tiles_h * B;
   const int base = p.m_blocks * p.n_blocks * G;
   // Split-K factor.  One CTA per SM is resident (shared memory), so the grid runs in waves of 148; a CTA costs its
-  // share of the pixel tiles plus a fixed prologue / accumulator drain worth ~6 tiles.  Pick the split count with the
-  // smallest waves x (tiles per CTA + overhead): 13 splits of a 48-item layer are 624 CTAs = five waves with the last
-  // one 22 % full, 12 splits are four full waves of slightly longer CTAs.
+  // share of the pixel tiles plus a fixed prologue / accumulator drain worth ~6 tiles.  The kernel's own time is
+  // waves x (tiles per CTA + overhead): 13 splits of a 48-item layer are 624 CTAs = five waves with the last one 22 %
+  // full; the minimum is one full wave of long-lived CTAs for every layer of this network.
+  // CARTSEG_WGRAD_INVERSION_WEIGHT=w adds w CTA lifetimes to the cost, i.e. prefers several full waves so that a
+  // high-priority dgrad that becomes ready while a wgrad wave is resident waits less (CTAs are not preemptible).
+  // Measured (tools/trace_backward.py, k2): w = 1 cuts the up-conv dgrads' waiting from 0.3-0.5 ms to nothing, but the
+  // weight gradients, now pre-empted at every wave boundary, pile up behind the main stream and the step gets
+  // slower (19.5 vs 18.8 ms; w = 2: 20.6 ms).  Default 0.
   const int kSMs = 148, kOverheadTiles = 6;
+  static const int kInversionWeight = [] {
+    const char* e = getenv("CARTSEG_WGRAD_INVERSION_WEIGHT");
+    return e ? atoi(e) : 0;
+  }();
   int max_splits = tiles / 16;
   if (max_splits < 1) max_splits = 1;
-  if (max_splits > 4 * kSMs) max_splits = 4 * kSMs;
+  if (max_splits > 16 * kSMs) max_splits = 16 * kSMs;
   int splits = 1;
   long long best_cost = -1;
   for (int sp = 1; sp <= max_splits; ++sp) {
     const long long waves = ((long long)base * sp + kSMs - 1) / kSMs;
-    const long long cost = waves * ((tiles + sp - 1) / sp + kOverheadTiles);
+    const long long cost = (waves + kInversionWeight) * ((tiles + sp - 1) / sp + kOverheadTiles);
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; splits = sp; }
   }
   p.splits = splits;

@@ -33,6 +33,8 @@ for part in "$@"; do
     bench_nooverlap) CARTSEG_OVERLAP=0 run bench_nooverlap 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline ;;
     trace)  run trace_backward 600 python tools/trace_backward.py ;;
     bench_committed) CARTSEG_LIB_PATH=$PWD/cart-segmentation-unet_b200/cartseg/libcartseg_committed.so run bench_committed 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline ;;
+    bench_w0) CARTSEG_WGRAD_INVERSION_WEIGHT=0 run bench_w0 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline ;;
+    bench_w2) CARTSEG_WGRAD_INVERSION_WEIGHT=2 run bench_w2 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline ;;
     bench3) run bench_k3 900 python bench.py --steps 3 --warmup 3 --workload k3 --no-cpu-baseline ;;
     bench4) run bench_k4 900 python bench.py --steps 5 --warmup 3 --workload k4 --no-cpu-baseline ;;
     bench8gpu) run bench_8gpu 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --steps 10 --warmup 3 ;;
