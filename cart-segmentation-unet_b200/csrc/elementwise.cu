@@ -604,31 +604,41 @@ __global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(POOL ? 128 : 104) b
     writer = true;
   }
   if (writer) {
-    float* row = a.partial + ((size_t)blockIdx.x * rows_per_block + my_row) * 2 * a.C;
-    *reinterpret_cast<float4*>(row + g * 8) = make_float4(s1[0], s1[1], s1[2], s1[3]);
-    *reinterpret_cast<float4*>(row + g * 8 + 4) = make_float4(s1[4], s1[5], s1[6], s1[7]);
-    *reinterpret_cast<float4*>(row + a.C + g * 8) = make_float4(s2[0], s2[1], s2[2], s2[3]);
-    *reinterpret_cast<float4*>(row + a.C + g * 8 + 4) = make_float4(s2[4], s2[5], s2[6], s2[7]);
+    // channel-major layout partial[2C][rows]: the finalize kernel reads one channel's partials as a contiguous run
+    const size_t rows_total = (size_t)gridDim.x * rows_per_block;
+    const size_t r = (size_t)blockIdx.x * rows_per_block + my_row;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a.partial[(size_t)(g * 8 + j) * rows_total + r] = s1[j];
+      a.partial[(size_t)(a.C + g * 8 + j) * rows_total + r] = s2[j];
+    }
   }
 }
 
-// s1/s2 totals -> per-channel means c1, c2 and the BN parameter gradients.  One warp per channel: lane l sums the
-// partials of blocks l, l+32, ... in fp64, then a fixed-order shuffle tree combines the lanes (deterministic).
-__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(BnBwdArgs a, int blocks) {
-  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (c >= a.C) return;
+// s1/s2 totals -> per-channel means c1, c2 and the BN parameter gradients.  One block per channel: thread t sums the
+// partials of rows t, t+256, ... (contiguous in the channel-major layout) in fp64; warps and then the 8 warp sums are
+// combined in a fixed order (deterministic).
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(BnBwdArgs a, int rows) {
+  __shared__ double st[2][8];
+  const int c = blockIdx.x;
+  const float* p1 = a.partial + (size_t)c * rows;
+  const float* p2 = a.partial + (size_t)(a.C + c) * rows;
   double t1 = 0.0, t2 = 0.0;
-  for (int b = lane; b < blocks; b += 32) {
-    t1 += (double)a.partial[(size_t)b * 2 * a.C + c];
-    t2 += (double)a.partial[(size_t)b * 2 * a.C + a.C + c];
+  for (int r = threadIdx.x; r < rows; r += 256) {
+    t1 += (double)__ldg(p1 + r);
+    t2 += (double)__ldg(p2 + r);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     t1 += __shfl_xor_sync(0xffffffffu, t1, o);
     t2 += __shfl_xor_sync(0xffffffffu, t2, o);
   }
-  if (lane != 0) return;
+  if ((threadIdx.x & 31) == 0) { st[0][threadIdx.x >> 5] = t1; st[1][threadIdx.x >> 5] = t2; }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  t1 = t2 = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { t1 += st[0][k]; t2 += st[1][k]; }
   const double inv_n = 1.0 / ((double)a.B * a.H * a.W);
   a.c1[c] = (float)(t1 * inv_n);
   a.c2[c] = (float)(t2 * inv_n);
@@ -645,7 +655,7 @@ cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t s) {
   else bn_bwd_reduce_kernel<false><<<grid, kBnBwdThreads, 0, s>>>(a);
   cudaError_t e = launched();
   if (e != cudaSuccess) return e;
-  bn_bwd_finalize_kernel<<<(a.C + 7) / 8, 256, 0, s>>>(a, grid * bn_bwd_rows_per_block(a.C));
+  bn_bwd_finalize_kernel<<<a.C, 256, 0, s>>>(a, grid * bn_bwd_rows_per_block(a.C));
   return launched();
 }
 
