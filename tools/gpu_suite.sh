@@ -42,6 +42,7 @@ for part in "$@"; do
     dp2) run dp_parity_2gpu 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/dp_parity.py ;;
     bench2gpu_nooverlap) CARTSEG_DP_BUCKET_MB=100000 run bench_2gpu_nooverlap 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 5 --warmup 3 ;;
     bench2gpu_maxctas) NCCL_MAX_CTAS=4 run bench_2gpu_maxctas 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 2 --steps 5 --warmup 3 ;;
+    dptest) run test_gpu_dp 900 python -m pytest tests/test_gpu_dp.py -m gpu -q --tb=short -s --timeout 600 ;;
     bench2gpu) run bench_2gpu 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 ;;
     aux)    run bench_aux 900 python tools/bench_aux.py ;;
     aux512) run bench_aux512 900 python tools/bench_aux.py --batch 32 --size 512 --no-cpu ;;
