@@ -104,6 +104,8 @@ def init_data_parallel(model, group: Optional[dist.ProcessGroup] = None, bucket_
     from . import ops
     if bucket_mb is None:
         bucket_mb = float(os.environ.get("CARTSEG_DP_BUCKET_MB", DEFAULT_BUCKET_MB))
+    if not reserve_sms:
+        reserve_sms = int(os.environ.get("CARTSEG_DP_RESERVE_SMS", "0"))
     sync = GradSync(group, bucket_mb)
     with torch.no_grad():
         for t in list(model.parameters()) + list(model.buffers()):

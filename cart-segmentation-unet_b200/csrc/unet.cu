@@ -186,19 +186,7 @@ static int build_convT_dgrad(PixGemmParams& p, int* block_n, View dy, int Cout, 
   return 0;
 }
 
-static void wgrad_common(WgradParams& p, int* block_n, int M, int N, int B, int H, int W, int G, float* dw) {
-  memset(&p, 0, sizeof(p));
-  *block_n = N % 128 == 0 ? 128 : 64;
-  p.G = G;
-  p.Mtot = M;
-  p.Ntot = N;
-  p.m_blocks = (M + 127) / 128;
-  p.n_blocks = N / *block_n;
-  p.tiles_w = (W + 7) / 8;
-  p.tiles_h = (H + 15) / 16;
-  p.batch = B;
-  const int tiles = p.tiles_w * p.tiles_h * B;
-  const int base = p.m_blocks * p.n_blocks * G;
+static int choose_wgrad_splits(int base, int tiles, int sms) {
   // Split-K factor.  One CTA per SM is resident (shared memory), so the grid runs in waves of 148; a CTA costs its
   // share of the pixel tiles plus a fixed prologue / accumulator drain worth ~6 tiles.  The kernel's own time is
   // waves x (tiles per CTA + overhead): 13 splits of a 48-item layer are 624 CTAs = five waves with the last one 22 %
@@ -208,7 +196,7 @@ static void wgrad_common(WgradParams& p, int* block_n, int M, int N, int B, int 
   // Measured (tools/trace_backward.py, k2): w = 1 cuts the up-conv dgrads' waiting from 0.3-0.5 ms to nothing, but the
   // weight gradients, now pre-empted at every wave boundary, pile up behind the main stream and the step gets
   // slower (19.5 vs 18.8 ms; w = 2: 20.6 ms).  Default 0.
-  const int kSMs = 148, kOverheadTiles = 6;
+  const int kSMs = sms, kOverheadTiles = 6;
   static const int kInversionWeight = [] {
     const char* e = getenv("CARTSEG_WGRAD_INVERSION_WEIGHT");
     return e ? atoi(e) : 0;
@@ -223,7 +211,23 @@ static void wgrad_common(WgradParams& p, int* block_n, int M, int N, int B, int 
     const long long cost = (waves + kInversionWeight) * ((tiles + sp - 1) / sp + kOverheadTiles);
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; splits = sp; }
   }
-  p.splits = splits;
+  return splits;
+}
+
+static void wgrad_common(WgradParams& p, int* block_n, int M, int N, int B, int H, int W, int G, float* dw) {
+  memset(&p, 0, sizeof(p));
+  *block_n = N % 128 == 0 ? 128 : 64;
+  p.G = G;
+  p.Mtot = M;
+  p.Ntot = N;
+  p.m_blocks = (M + 127) / 128;
+  p.n_blocks = N / *block_n;
+  p.tiles_w = (W + 7) / 8;
+  p.tiles_h = (H + 15) / 16;
+  p.batch = B;
+  const int tiles = p.tiles_w * p.tiles_h * B;
+  const int base = p.m_blocks * p.n_blocks * G;
+  p.splits = choose_wgrad_splits(base, tiles, 148);
   p.dw = dw;
 }
 // dW[kw*3+kh][co][ci] = sum_pixels dy[pixel, co] * x[pixel + (kh-1, kw-1), ci]
@@ -849,6 +853,13 @@ int cs_unet_plan_set_sm_limit(cs_unet_plan* pl, int sms) {
   if (sms <= 0 || sms > all) sms = all;
   pl->num_sms = sms & ~1;                                 // CTA pairs
   if (pl->num_sms < 2) pl->num_sms = 2;
+  if (!pl->infer) {                                       // the single-wave weight-gradient grids follow the limit too
+    auto refit = [&](WgradParams& w) {
+      w.splits = choose_wgrad_splits(w.m_blocks * w.n_blocks * w.G, w.tiles_w * w.tiles_h * w.batch, pl->num_sms);
+    };
+    for (int i = 0; i < 18; ++i) refit(pl->conv[i].wg);
+    for (int k = 0; k < 4; ++k) refit(pl->up[k].wg);
+  }
   return 0;
 }
 

@@ -38,6 +38,8 @@ for part in "$@"; do
     bench3) run bench_k3 900 python bench.py --steps 3 --warmup 3 --workload k3 --no-cpu-baseline ;;
     bench4) run bench_k4 900 python bench.py --steps 5 --warmup 3 --workload k4 --no-cpu-baseline ;;
     bench8gpu) run bench_8gpu 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --steps 10 --warmup 3 ;;
+    bench8gpu_r4) NCCL_MAX_CTAS=4 CARTSEG_DP_RESERVE_SMS=4 run bench_8gpu_r4 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus 8 --steps 10 --warmup 3 ;;
+    bench8gpu_r8) NCCL_MAX_CTAS=8 CARTSEG_DP_RESERVE_SMS=8 run bench_8gpu_r8 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29535 bench.py --gpus 8 --steps 10 --warmup 3 ;;
     bench4gpu) run bench_4gpu 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29522 bench.py --gpus 4 --steps 10 --warmup 3 ;;
     dp2) run dp_parity_2gpu 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/dp_parity.py ;;
     bench2gpu_nooverlap) CARTSEG_DP_BUCKET_MB=100000 run bench_2gpu_nooverlap 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 5 --warmup 3 ;;
@@ -62,7 +64,7 @@ for part in "$@"; do
                 -k regex:wgrad -c 3 -f -o gpurun_out/prof_wgrad python tools/profile_step.py ;;
     ncuone) run profile_plain 300 python tools/profile_step.py && \
             run ncu_one 900 ncu --profile-from-start off --set full --clock-control none --import-source on \
-                -k regex:${NCU_KERNEL:-pix_gemm} -s ${NCU_SKIP:-1} -c ${NCU_COUNT:-1} -f -o gpurun_out/prof_one python tools/profile_step.py ;;
+                -k regex:${NCU_KERNEL:-pix_gemm} -s ${NCU_SKIP:-1} -c ${NCU_COUNT:-1} -f -o gpurun_out/${NCU_OUT:-prof_one} python tools/profile_step.py ;;
     all)    run tests_all 1800 python -m pytest tests -m gpu -q -x --tb=short --timeout 600 ;;
   esac
 done
