@@ -1,6 +1,7 @@
 // Bandwidth-bound kernels around the convolutions: weight (un)packing, input im2col, batch-norm
 // finalize / apply / backward, ReLU, 2x2 max-pool (+ its backward routing), the 1x1 head.
 // All of them are single coalesced passes with 16-byte vectors (8 bf16 channels per thread).
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -540,14 +541,17 @@ size_t bn_bwd_scratch_bytes(int maxC) { return (size_t)kBnBwdMaxBlocks * 4 * max
 // shared memory): the HBM-bound BN backward of layer L-1 then really runs under the tensor-bound wgrad of layer L
 // (cs_unet_backward issues them on two streams).  With three blocks per SM the register file is full and the wgrad
 // CTAs cannot be placed until the BN kernel has drained, which serialises the two.
+// Measured alternatives (ncu totals of the 14 non-pooled launches of a k2 step, same box): three blocks per SM with 80
+// registers and 2 units in flight (spills): apply 1.71 / reduce 1.27 ms vs 1.31 / 1.12 ms for this shape; 4 units in
+// flight in the apply kernel (spills at 104 registers): 1.42 ms.
 static int bn_bwd_grid(const BnBwdArgs& a) {
   const int rpb = kBnBwdThreads / (a.C / 8);
   const long long units = a.g_pool ? (long long)a.B * (a.H / 2) * (a.W / 2) : (long long)a.B * a.H * a.W;
   return grid_for(units, rpb * 2, 148 * 2);
 }
 
-template <bool POOL>
-__global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(POOL ? 128 : 104) bn_bwd_reduce_kernel(BnBwdArgs a) {
+template <bool POOL, int U_, int REGS>
+__global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(REGS) bn_bwd_reduce_kernel(BnBwdArgs a) {
   constexpr int ND = POOL ? 4 : 1;
   const int cg = a.C >> 3;
   const int g = threadIdx.x % cg, ri = threadIdx.x / cg, rpb = kBnBwdThreads / cg;
@@ -563,7 +567,7 @@ __global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(POOL ? 128 : 104) b
       pooled_unit(a, k, g, u, pix, [&](int, int j, float gmv, float xhv) { s1[j] += gmv; s2[j] = fmaf(gmv, xhv, s2[j]); });
     }
   } else {
-    constexpr int U = 4;
+    constexpr int U = U_;
     const long long stride = (long long)gridDim.x * rpb;
     for (long long u0 = (long long)blockIdx.x * rpb + ri; u0 < units; u0 += U * stride) {
       PlainUnit pu[U];
@@ -651,16 +655,16 @@ cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t s) {
   const int cg = a.C / 8;
   if (cg > kBnBwdThreads || kBnBwdThreads % cg) return cudaErrorInvalidValue;
   const int grid = bn_bwd_grid(a);
-  if (a.g_pool) bn_bwd_reduce_kernel<true><<<grid, kBnBwdThreads, 0, s>>>(a);
-  else bn_bwd_reduce_kernel<false><<<grid, kBnBwdThreads, 0, s>>>(a);
+  if (a.g_pool) bn_bwd_reduce_kernel<true, 1, 128><<<grid, kBnBwdThreads, 0, s>>>(a);
+  else bn_bwd_reduce_kernel<false, 4, 104><<<grid, kBnBwdThreads, 0, s>>>(a);
   cudaError_t e = launched();
   if (e != cudaSuccess) return e;
   bn_bwd_finalize_kernel<<<a.C, 256, 0, s>>>(a, grid * bn_bwd_rows_per_block(a.C));
   return launched();
 }
 
-template <bool POOL>
-__global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(POOL ? 128 : 104) bn_bwd_apply_kernel(BnBwdArgs a) {
+template <bool POOL, int U_, int REGS>
+__global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(REGS) bn_bwd_apply_kernel(BnBwdArgs a) {
   constexpr int ND = POOL ? 4 : 1;
   const int cg = a.C >> 3;
   const int g = threadIdx.x % cg, ri = threadIdx.x / cg, rpb = kBnBwdThreads / cg;
@@ -684,7 +688,7 @@ __global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(POOL ? 128 : 104) b
       for (int d = 0; d < 4; ++d) st8(a.dy + pix[d] * a.C + g * 8, out[d]);
     }
   } else {
-    constexpr int U = 3;
+    constexpr int U = U_;
     const long long stride = (long long)gridDim.x * rpb;
     for (long long u0 = (long long)blockIdx.x * rpb + ri; u0 < units; u0 += U * stride) {
       PlainUnit pu[U];
@@ -706,8 +710,8 @@ __global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(POOL ? 128 : 104) b
 }
 cudaError_t launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t s) {
   const int grid = bn_bwd_grid(a);
-  if (a.g_pool) bn_bwd_apply_kernel<true><<<grid, kBnBwdThreads, 0, s>>>(a);
-  else bn_bwd_apply_kernel<false><<<grid, kBnBwdThreads, 0, s>>>(a);
+  if (a.g_pool) bn_bwd_apply_kernel<true, 1, 128><<<grid, kBnBwdThreads, 0, s>>>(a);
+  else bn_bwd_apply_kernel<false, 3, 104><<<grid, kBnBwdThreads, 0, s>>>(a);
   return launched();
 }
 
