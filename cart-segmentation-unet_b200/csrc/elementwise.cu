@@ -29,6 +29,12 @@ CS_DEVINL Vec8 pack8(const float* f) {
 }
 CS_DEVINL Vec8 ld8(const bf16* p) { return *reinterpret_cast<const Vec8*>(p); }
 CS_DEVINL void st8(bf16* p, const Vec8& v) { *reinterpret_cast<Vec8*>(p) = v; }
+CS_DEVINL Vec8 ld8_nc(const bf16* p) {
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+  Vec8 r;
+  r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
+  return r;
+}
 
 // ============================================================================ weight packing
 // Tile of 32 (a) x 32 (b) pairs, T <= 9 taps each.  Thread (b, a) reads the T contiguous taps of its pair (a warp
@@ -242,7 +248,7 @@ cudaError_t launch_bn_fold_eval(const float* gamma, const float* beta, const flo
 
 // ============================================================================ BN apply + ReLU (+ 2x2 max-pool)
 template <bool POOL>
-__global__ void bn_relu_kernel(const bf16* __restrict__ y, int B, int H, int W, int C, const BnFinalizeArgs fin,
+__global__ void __launch_bounds__(256, 3) bn_relu_kernel(const bf16* __restrict__ y, int B, int H, int W, int C, const BnFinalizeArgs fin,
                                bf16* __restrict__ out, int out_pitch, int out_c0, bf16* __restrict__ pooled,
                                const HeadFwd head) {
   // Fused statistics -> affine step (was a kernel of its own between the convolution and this pass): every block
@@ -256,32 +262,50 @@ __global__ void bn_relu_kernel(const bf16* __restrict__ y, int B, int H, int W, 
   __syncthreads();
   const int cg = C >> 3;
   if (!POOL) {
+    // The stride of the grid-stride loop is a multiple of the channel-group count (256 % cg == 0): a thread keeps its
+    // channel group, so its coefficients live in registers; four 16-byte loads are in flight before the first use.
     const long long total = (long long)B * H * W * cg;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-      const int g = (int)(i % cg);
-      const long long p = i / cg;
-      float f[8], sc[8], sh[8];
-      unpack8(ld8(y + p * C + g * 8), f);
-      *reinterpret_cast<float4*>(sc) = *reinterpret_cast<const float4*>(scale + g * 8);
-      *reinterpret_cast<float4*>(sc + 4) = *reinterpret_cast<const float4*>(scale + g * 8 + 4);
-      *reinterpret_cast<float4*>(sh) = *reinterpret_cast<const float4*>(shift + g * 8);
-      *reinterpret_cast<float4*>(sh + 4) = *reinterpret_cast<const float4*>(shift + g * 8 + 4);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int g = (int)(i0 % cg);
+    float sc[8], sh[8], hw[8];
+    *reinterpret_cast<float4*>(sc) = *reinterpret_cast<const float4*>(scale + g * 8);
+    *reinterpret_cast<float4*>(sc + 4) = *reinterpret_cast<const float4*>(scale + g * 8 + 4);
+    *reinterpret_cast<float4*>(sh) = *reinterpret_cast<const float4*>(shift + g * 8);
+    *reinterpret_cast<float4*>(sh + 4) = *reinterpret_cast<const float4*>(shift + g * 8 + 4);
+    if (head.logits) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
-      const Vec8 stored = pack8(f);
-      st8(out + p * out_pitch + out_c0 + g * 8, stored);
-      if (head.logits) {
-        // fused 1x1 head (C == 64: the 8 lanes holding one pixel are adjacent): logits = <stored activation, w> + b.
-        // total is a multiple of 32 (H, W multiples of 16), so whole warps are in range together.
-        float r[8], acc = 0.f;
-        unpack8(stored, r);
+      for (int j = 0; j < 8; ++j) hw[j] = __ldg(head.w + g * 8 + j);
+    }
+    const float hb = (head.logits && head.b) ? __ldg(head.b) : 0.f;
+    constexpr int U = 4;
+    for (long long i = i0; i < total; i += U * stride) {
+      Vec8 v[U];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc = fmaf(r[j], __ldg(head.w + g * 8 + j), acc);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-        if (g == 0) head.logits[p] = acc + (head.b ? __ldg(head.b) : 0.f);
+      for (int k = 0; k < U; ++k)
+        if (i + k * stride < total) v[k] = ld8_nc(y + ((i + k * stride) / cg) * C + g * 8);
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        if (i + k * stride >= total) break;
+        const long long p = (i + k * stride) / cg;
+        float f[8];
+        unpack8(v[k], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+        const Vec8 stored = pack8(f);
+        st8(out + p * out_pitch + out_c0 + g * 8, stored);
+        if (head.logits) {
+          // fused 1x1 head (C == 64: the 8 lanes holding one pixel are adjacent): logits = <stored activation, w> + b.
+          // total and the stride are multiples of 32 (H, W multiples of 16), so whole warps are in range together.
+          float r[8], acc = 0.f;
+          unpack8(stored, r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc = fmaf(r[j], hw[j], acc);
+          acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+          acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+          acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+          if (g == 0) head.logits[p] = acc + hb;
+        }
       }
     }
   } else {
@@ -327,7 +351,8 @@ cudaError_t launch_bn_relu(const bf16* y, int B, int H, int W, int C, const BnFi
     bn_relu_kernel<true><<<grid_for((long long)B * (H / 2) * (W / 2) * (C / 8), 256), 256, smem, s>>>(
         y, B, H, W, C, fin, out, out_pitch, out_c0, pooled, head);
   } else {
-    bn_relu_kernel<false><<<grid_for((long long)B * H * W * (C / 8), 256), 256, smem, s>>>(y, B, H, W, C, fin, out,
+    // three resident blocks per SM (launch bounds), two full waves
+    bn_relu_kernel<false><<<grid_for((long long)B * H * W * (C / 8), 256 * 4, 148 * 6), 256, smem, s>>>(y, B, H, W, C, fin, out,
                                                                                             out_pitch, out_c0, pooled, head);
   }
   return launched();
@@ -450,12 +475,6 @@ CS_DEVINL void masked_grad(const BnBwdArgs& a, const BnCoef& k, int g, long long
 // Non-pooled layers, split into a load phase and a compute phase so that a thread can have several units' loads in
 // flight before the first use (the kernels run at two blocks per SM: memory parallelism has to come from the thread).
 struct PlainUnit { Vec8 y, g; };
-CS_DEVINL Vec8 ld8_nc(const bf16* p) {
-  const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
-  Vec8 r;
-  r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
-  return r;
-}
 CS_DEVINL void plain_load(const BnBwdArgs& a, const BnCoef& k, int g, long long pix, PlainUnit& u) {
   u.y = ld8_nc(a.y + pix * a.C + g * 8);
   if (a.head_dlogits) {
