@@ -42,6 +42,23 @@ WORKLOADS = {
 }
 
 
+def synth_batch(B: int, H: int, W: int, seed: int = 0, in_channels: int = 3):
+    """Synthetic inputs of SURVEY.md §8d: image ~ N(0,1) fp32 [B,3,H,W]; mask = one filled disc per sample (centre in the
+    central half, radius in [min(H,W)/11, min(H,W)/3]) as {0,1} fp32 [B,1,H,W].  numpy PCG64, stable across versions."""
+    import numpy as np
+    import torch
+    rng = np.random.Generator(np.random.PCG64(seed))
+    x = rng.standard_normal((B, in_channels, H, W), dtype=np.float32)
+    yy, xx = np.mgrid[0:H, 0:W]
+    m = np.zeros((B, 1, H, W), dtype=np.float32)
+    for b in range(B):
+        cy = rng.uniform(H * 0.25, H * 0.75)
+        cx = rng.uniform(W * 0.25, W * 0.75)
+        r = rng.uniform(min(H, W) / 11.0, min(H, W) / 3.0)
+        m[b, 0] = ((yy - cy) ** 2 + (xx - cx) ** 2 <= r * r).astype(np.float32)
+    return torch.from_numpy(x), torch.from_numpy(m)
+
+
 def step_traffic(kernel_label: str):
     """DRAM bytes per launch of a kernel class from the committed ncu pass over one k2 step (profiles/, written by
     tools/step_traffic.py); None when no capture is committed."""
@@ -179,7 +196,6 @@ def run_ours(args, wl):
     import torch
     import torch.distributed as dist
     import cartseg
-    from oracle import unet_oracle as O       # synthetic-input generator + the cpu_baseline leg only
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -210,7 +226,7 @@ def run_ours(args, wl):
     else:
         opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True)
 
-    x_h, t_h = O.synth_batch(B, S, S, seed=rank)
+    x_h, t_h = synth_batch(B, S, S, seed=rank)
     x_h, t_h = x_h.pin_memory(), t_h.pin_memory()
     x_d, t_d = x_h.to(dev), t_h.to(dev)
 

@@ -22,7 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "cart-segmentation-unet_b200"))
 import cartseg as cs                              # noqa: E402
-from oracle import unet_oracle as O               # noqa: E402  (synthetic inputs + CPU baselines only)
+from bench import synth_batch                    # noqa: E402  (oracle/ is imported below for the CPU baselines only)
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=64)
@@ -71,7 +71,7 @@ def report(name, ms, bytes_per_call, ref_file, cpu_ms=None, cpu_what=None, **ext
     print(json.dumps(line), flush=True)
 
 
-x, t = O.synth_batch(min(B, 16), S, S, seed=0)
+x, t = synth_batch(min(B, 16), S, S, seed=0)
 rep = (B + t.shape[0] - 1) // t.shape[0]
 t = t.repeat(rep, 1, 1, 1)[:B].contiguous()
 g = torch.Generator().manual_seed(1)

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "cart-segmentation-unet_b200"))
 import cartseg                                   # noqa: E402
-from oracle import unet_oracle as O              # noqa: E402  (synthetic inputs only)
+from bench import synth_batch                   # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--size", type=int, default=224)
@@ -27,7 +27,7 @@ model = cartseg.UNet().cuda().eval()
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"] \
     if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1400.0
 for B in [int(b) for b in args.batches.split(",")]:
-    x, _ = O.synth_batch(min(B, 8), args.size, args.size, seed=0)
+    x, _ = synth_batch(min(B, 8), args.size, args.size, seed=0)
     x = x.repeat((B + x.shape[0] - 1) // x.shape[0], 1, 1, 1)[:B].contiguous().cuda()
     x_h = x.cpu().pin_memory()
 

@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "cart-segmentation-unet_b200"))
 import cartseg                                   # noqa: E402
-from oracle import unet_oracle as O              # noqa: E402  (synthetic inputs only)
+from bench import synth_batch                   # noqa: E402
 
 
 def main():
@@ -27,7 +27,7 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     B, S = int(os.environ.get("DP_PARITY_BATCH", "8")), int(os.environ.get("DP_PARITY_SIZE", "96"))
-    x, t = O.synth_batch(B * world, S, S, seed=3)                     # the global batch, identical on every rank
+    x, t = synth_batch(B * world, S, S, seed=3)                     # the global batch, identical on every rank
     torch.manual_seed(1)
     model = cartseg.UNet().to(dev).train()
     sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}

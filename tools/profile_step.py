@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "cart-segmentation-unet_b200"))
 import cartseg                                   # noqa: E402
-from oracle import unet_oracle as O              # noqa: E402  (synthetic inputs only)
+from bench import synth_batch                   # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=64)
@@ -25,7 +25,7 @@ torch.manual_seed(0)
 model = cartseg.UNet().cuda()
 crit = cartseg.FocalDiceLoss(0.5, 2.0, 1.0, 0.7) if args.loss == "focal_dice" else cartseg.CompositeSegLoss(0.5, 0.3)
 opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True)
-x, t = O.synth_batch(args.batch, args.size, args.size, seed=0)
+x, t = synth_batch(args.batch, args.size, args.size, seed=0)
 x, t = x.cuda(), t.cuda()
 
 

@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "cart-segmentation-unet_b200"))
 import cartseg                                   # noqa: E402
 from cartseg import ops                          # noqa: E402
-from oracle import unet_oracle as O              # noqa: E402  (synthetic inputs only)
+from bench import synth_batch                   # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=64)
@@ -23,7 +23,7 @@ torch.manual_seed(0)
 model = cartseg.UNet().cuda().train()
 crit = cartseg.FocalDiceLoss(0.5, 2.0, 1.0, 0.7)
 opt = torch.optim.AdamW(model.parameters(), lr=1e-3, fused=True)
-x, t = O.synth_batch(args.batch, args.size, args.size, seed=0)
+x, t = synth_batch(args.batch, args.size, args.size, seed=0)
 x, t = x.cuda(), t.cuda()
 
 
