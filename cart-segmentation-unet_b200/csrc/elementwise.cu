@@ -231,18 +231,22 @@ cudaError_t launch_bn_finalize_train(const BnFinalizeArgs& a, cudaStream_t s) {
   return launched();
 }
 
-__global__ void bn_fold_eval_kernel(const float* gamma, const float* beta, const float* conv_bias, const float* rm,
-                                    const float* rv, float eps, float* scale, float* shift, int C) {
+// Eval mode: all layers of the network in ONE launch (blockIdx.y = layer) — 18 separate launches of this tiny kernel
+// were a tenth of a batch-1 forward.
+__global__ void bn_fold_eval_kernel(BnFoldBatch a) {
+  const int l = blockIdx.y;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const float invstd = 1.0f / sqrtf(rv[c] + eps);
-  const float sc = gamma[c] * invstd;
-  scale[c] = sc;
-  shift[c] = beta[c] + ((conv_bias ? conv_bias[c] : 0.f) - rm[c]) * sc;
+  if (c >= a.C[l]) return;
+  const float invstd = 1.0f / sqrtf(a.rv[l][c] + a.eps);
+  const float sc = a.gamma[l][c] * invstd;
+  a.scale[l][c] = sc;
+  a.shift[l][c] = a.beta[l][c] + ((a.conv_bias[l] ? a.conv_bias[l][c] : 0.f) - a.rm[l][c]) * sc;
 }
-cudaError_t launch_bn_fold_eval(const float* gamma, const float* beta, const float* conv_bias, const float* rm,
-                                const float* rv, float eps, float* scale, float* shift, int C, cudaStream_t s) {
-  bn_fold_eval_kernel<<<(C + 127) / 128, 128, 0, s>>>(gamma, beta, conv_bias, rm, rv, eps, scale, shift, C);
+cudaError_t launch_bn_fold_eval(const BnFoldBatch& a, cudaStream_t s) {
+  if (a.layers < 1 || a.layers > BnFoldBatch::kMax) return cudaErrorInvalidValue;
+  int maxC = 0;
+  for (int l = 0; l < a.layers; ++l) maxC = a.C[l] > maxC ? a.C[l] : maxC;
+  bn_fold_eval_kernel<<<dim3((maxC + 127) / 128, a.layers), 128, 0, s>>>(a);
   return launched();
 }
 

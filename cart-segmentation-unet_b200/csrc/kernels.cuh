@@ -37,8 +37,17 @@ struct BnFinalizeArgs {
   int C;
 };
 cudaError_t launch_bn_finalize_train(const BnFinalizeArgs& a, cudaStream_t s);
-cudaError_t launch_bn_fold_eval(const float* gamma, const float* beta, const float* conv_bias, const float* rm,
-                                const float* rv, float eps, float* scale, float* shift, int C, cudaStream_t s);
+// Eval mode: running statistics folded into (scale, shift) for up to 18 layers in one launch.
+struct BnFoldBatch {
+  static constexpr int kMax = 18;
+  const float* gamma[kMax]; const float* beta[kMax]; const float* conv_bias[kMax];
+  const float* rm[kMax]; const float* rv[kMax];
+  float* scale[kMax]; float* shift[kMax];
+  int C[kMax];
+  int layers;
+  float eps;
+};
+cudaError_t launch_bn_fold_eval(const BnFoldBatch& a, cudaStream_t s);
 // Training forward: (scale, shift) are derived from the batch statistics inside the kernel (fused bn_finalize_train:
 // block 0 publishes scale/shift/mean/invstd and updates the running statistics), then
 // out[p][out_c0 + c] = relu(y[p][c]*scale[c] + shift[c]); optional 2x2 max-pooled copy (pitch C)

@@ -657,6 +657,19 @@ int cs_unet_forward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* x, 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int B = pl->B;
   if (training) CS_CUDA(cudaMemsetAsync(pl->stats_begin, 0, pl->stats_bytes, s));
+  if (!training) {                                           // fold the running statistics of all 18 BN layers
+    BnFoldBatch f{};
+    f.layers = 18;
+    f.eps = 1e-5f;
+    for (int i = 0; i < 18; ++i) {
+      const ConvL& c = pl->conv[i];
+      if (!t->running_mean[i] || !t->running_var[i]) return fail("running statistics of BN %d are null", i);
+      f.gamma[i] = t->param[c.pgamma]; f.beta[i] = t->param[c.pbeta]; f.conv_bias[i] = t->param[c.pb];
+      f.rm[i] = t->running_mean[i]; f.rv[i] = t->running_var[i];
+      f.scale[i] = c.scale; f.shift[i] = c.shift; f.C[i] = c.cout;
+    }
+    CS_CUDA(launch_bn_fold_eval(f, s));
+  }
   CS_CUDA(launch_im2col_first(x, B, pl->Cin, pl->H, pl->W, pl->col, s));
 
   auto run_conv = [&](int i) -> int {
@@ -674,9 +687,6 @@ int cs_unet_forward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* x, 
       const HeadFwd head = (i == 17 && fuse_head()) ? HeadFwd{t->param[80], t->param[81], logits} : HeadFwd{nullptr, nullptr, nullptr};
       CS_CUDA(launch_bn_relu(c.y, B, c.H, c.W, c.cout, f, c.out.p, c.out.pitch, c.out.c0, c.pooled, head, s));
     } else {
-      if (!t->running_mean[i] || !t->running_var[i]) return fail("running statistics of BN %d are null", i);
-      CS_CUDA(launch_bn_fold_eval(t->param[c.pgamma], t->param[c.pbeta], t->param[c.pb], t->running_mean[i],
-                                  t->running_var[i], 1e-5f, c.scale, c.shift, c.cout, s));
       CS_CUDA(timed(pl, pix_class(c.bn_f), c.flops, s, [&] { return launch_pix_gemm(c.fp_eval, c.bn_f, pl->num_sms, s); }));
       if (c.pooled) CS_CUDA(launch_maxpool(c.out.p, c.out.pitch, c.out.c0, B, c.H, c.W, c.cout, c.pooled, s));
     }
