@@ -219,18 +219,6 @@ CS_DEVINL void bn_channel_coef(const BnFinalizeArgs& a, int c, bool publish, flo
     a.running_var[c] = (float)((1.0 - m) * (double)a.running_var[c] + m * unbiased);
   }
 }
-__global__ void bn_finalize_train_kernel(BnFinalizeArgs a) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && a.num_batches_tracked) *a.num_batches_tracked += 1;
-  if (c >= a.C) return;
-  float sc, sh;
-  bn_channel_coef(a, c, true, &sc, &sh);
-}
-cudaError_t launch_bn_finalize_train(const BnFinalizeArgs& a, cudaStream_t s) {
-  bn_finalize_train_kernel<<<(a.C + 127) / 128, 128, 0, s>>>(a);
-  return launched();
-}
-
 // Eval mode: all layers of the network in ONE launch (blockIdx.y = layer) — 18 separate launches of this tiny kernel
 // were a tenth of a batch-1 forward.
 __global__ void bn_fold_eval_kernel(BnFoldBatch a) {
@@ -411,71 +399,6 @@ CS_DEVINL void load_coef(const BnBwdArgs& a, int g, BnCoef& k) {
   load8(a.invstd + g * 8, k.is);
   if (a.head_dlogits) load8(a.head_w + g * 8, k.hw);
 }
-// Computes, for one pixel (no pool) or one 2x2 window (pool), the masked gradient gm[d][8] and xhat[d][8].
-template <bool POOL>
-CS_DEVINL void masked_grad(const BnBwdArgs& a, const BnCoef& k, int g, long long unit, float gm[][8], float xh[][8],
-                           long long pix[]) {
-  constexpr int ND = POOL ? 4 : 1;
-  float act[ND][8];
-  if (POOL) {
-    const int H2 = a.H >> 1, W2 = a.W >> 1;
-    const int w2 = (int)(unit % W2);
-    const int h2 = (int)((unit / W2) % H2);
-    const int b = (int)(unit / ((long long)W2 * H2));
-#pragma unroll
-    for (int d = 0; d < ND; ++d) pix[d] = ((long long)b * a.H + 2 * h2 + (d >> 1)) * a.W + 2 * w2 + (d & 1);
-  } else {
-    pix[0] = unit;
-  }
-  Vec8 yv8[ND], gv8[ND];
-#pragma unroll
-  for (int d = 0; d < ND; ++d) {                         // issue every load before the first use
-    yv8[d] = ld8(a.y + pix[d] * a.C + g * 8);
-    if (!POOL && a.head_dlogits) {
-      // the layer feeds the 1x1 head: its activation gradient dlogits[p] * w[c] (rounded to bf16, as the stand-alone
-      // head backward used to store it) is formed here instead of being written to and read back from HBM twice
-      const float dl = __ldg(a.head_dlogits + pix[d]);
-      float o[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = dl * k.hw[j];
-      gv8[d] = pack8(o);
-    } else {
-      gv8[d] = ld8(a.g + pix[d] * a.g_pitch + a.g_c0 + g * 8);
-    }
-  }
-#pragma unroll
-  for (int d = 0; d < ND; ++d) {
-    float yv[8], t[8];
-    unpack8(yv8[d], yv);
-    unpack8(gv8[d], gm[d]);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) t[j] = fmaxf(fmaf(yv[j], k.sc[j], k.sh[j]), 0.f);
-    unpack8(pack8(t), act[d]);                          // bf16-rounded, as stored by the forward
-#pragma unroll
-    for (int j = 0; j < 8; ++j) xh[d][j] = (yv[j] - k.mu[j]) * k.is[j];
-  }
-  if (POOL) {
-    float gp[8];
-    unpack8(ld8(a.g_pool + unit * a.C + g * 8), gp);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      int best = 0;
-      float bv = act[0][j];
-#pragma unroll
-      for (int d = 1; d < ND; ++d)
-        if (act[d][j] > bv) { bv = act[d][j]; best = d; }
-#pragma unroll
-      for (int d = 0; d < ND; ++d)
-        if (d == best) gm[d][j] += gp[j];
-    }
-  }
-#pragma unroll
-  for (int d = 0; d < ND; ++d)
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (!(act[d][j] > 0.f)) gm[d][j] = 0.f;
-}
-
 // Non-pooled layers, split into a load phase and a compute phase so that a thread can have several units' loads in
 // flight before the first use (the kernels run at two blocks per SM: memory parallelism has to come from the thread).
 struct PlainUnit { Vec8 y, g; };
@@ -575,7 +498,6 @@ static int bn_bwd_grid(const BnBwdArgs& a) {
 
 template <bool POOL, int U_, int REGS>
 __global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(REGS) bn_bwd_reduce_kernel(BnBwdArgs a) {
-  constexpr int ND = POOL ? 4 : 1;
   const int cg = a.C >> 3;
   const int g = threadIdx.x % cg, ri = threadIdx.x / cg, rpb = kBnBwdThreads / cg;
   const long long units = POOL ? (long long)a.B * (a.H >> 1) * (a.W >> 1) : (long long)a.B * a.H * a.W;
@@ -688,7 +610,6 @@ cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t s) {
 
 template <bool POOL, int U_, int REGS>
 __global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(REGS) bn_bwd_apply_kernel(BnBwdArgs a) {
-  constexpr int ND = POOL ? 4 : 1;
   const int cg = a.C >> 3;
   const int g = threadIdx.x % cg, ri = threadIdx.x / cg, rpb = kBnBwdThreads / cg;
   const long long units = POOL ? (long long)a.B * (a.H >> 1) * (a.W >> 1) : (long long)a.B * a.H * a.W;

@@ -36,7 +36,6 @@ struct BnFinalizeArgs {
   float* scale; float* shift; float* mean; float* invstd;
   int C;
 };
-cudaError_t launch_bn_finalize_train(const BnFinalizeArgs& a, cudaStream_t s);
 // Eval mode: running statistics folded into (scale, shift) for up to 18 layers in one launch.
 struct BnFoldBatch {
   static constexpr int kMax = 18;
