@@ -269,6 +269,22 @@ def run_ours(args, wl):
     ms = e0.elapsed_time(e1)
     launches = cartseg.lib().cs_kernel_launch_count() - n0
     clocks = sampler.stop(w0, w1) if rank == 0 else None
+    # ---- forward + backward only (SURVEY.md §8d asks for it beside the full step): same K steps without optimizer.step
+    def step_fb(x, t):
+        opt.zero_grad(set_to_none=True)
+        loss = crit(model(x), t)
+        loss.backward()
+        return loss
+
+    step_fb(x_d, t_d)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        step_fb(x_d, t_d)
+    f1.record()
+    barrier()
+    fb_ms = f0.elapsed_time(f1)
     # ---- per-kernel roofline pass: the same steps again, weight-gradient overlap off so that every tensor-core
     # launch runs alone between its two CUDA events (in the timed region above the wgrad GEMMs share the GPU with
     # the BN-backward passes and dgrads, which is what makes the step faster but their own durations meaningless)
@@ -325,9 +341,9 @@ def run_ours(args, wl):
     assert bool(torch.isfinite(losses_h).all())
 
     if world > 1:
-        tt = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+        tt = torch.tensor([ms, e2e_ms, fb_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = tt.tolist()
+        ms, e2e_ms, fb_ms = tt.tolist()
     value = world * B * args.steps / (ms / 1e3)
     e2e = world * B * args.steps / (e2e_ms / 1e3)
 
@@ -348,6 +364,8 @@ def run_ours(args, wl):
                        "last_loss": last_loss},
             "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": int(x_h.numel() * 4 + t_h.numel() * 4),
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
+            "fwd_bwd_only": {"value": world * B * args.steps / (fb_ms / 1e3), "unit": "img/s",
+                             "ms_per_step": fb_ms / args.steps, "note": "same steps without optimizer.step()"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": dom["tflops"], "peak": pk["tf_sust"], "unit": "TFLOP/s",
