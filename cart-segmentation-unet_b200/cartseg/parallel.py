@@ -19,6 +19,8 @@ import torch
 import torch.distributed as dist
 
 
+# Bucket size of the gradient all-reduce.  Measured on 2 x B200 in one box (k2, ms per step): 16 MB 19.01 / 19.04,
+# 4 MB 19.18 / 19.20, 2 MB 19.50, one bucket after the whole backward (no overlap) 19.52; single GPU 18.8.
 DEFAULT_BUCKET_MB = 16.0
 
 
