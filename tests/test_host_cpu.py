@@ -228,3 +228,23 @@ def test_bf16_storage_alone_moves_relu_network_gradients_by_tens_of_percent():
     (l32, g32), (l16, g16) = res
     assert abs(l32 - l16) / l32 < 1e-3
     assert float((g16 - g32).norm() / g32.norm()) > 0.1
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) prints one JSON line with the contract's
+    keys; without a GPU the product arm refuses to run instead of falling back."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-1000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["metric"] == "train_images_per_sec" and line["unit"] == "img/s"
+    assert line["higher_is_better"] is True and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    if not torch.cuda.is_available():
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True,
+                           text=True, timeout=600)
+        assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
