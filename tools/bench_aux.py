@@ -114,7 +114,7 @@ ths = np.linspace(0.2, 0.8, 13)
 ms = timed(lambda: cs.sweep_thresholds(zd, td, ths))
 report("threshold_stats (13 thresholds, one pass)", ms, 8 * PX, "train_bce_dice.py:214-232")
 
-# ---- pseudo-label QC: probs read 7x from L2/HBM (1 stats + 6 select passes), mask 1 B written; algorithmic 5 B/px
+# ---- pseudo-label QC: probs read 3x (L2-resident after the first pass), mask 1 B written; algorithmic 5 B/px
 probs = torch.sigmoid(zd)[:, 0].contiguous()
 ms = timed(lambda: cs.pseudo_label_qc(probs, 0.5))
 cpu = None
