@@ -141,50 +141,96 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_step_rate(loss_name: str, size: int, steps: int, warmup: int, batch: int = 4):
-    """The reference's CPU path (the oracle port of its UNet + loss classes, torch CPU fp32, all host threads)
-    on a bounded sample of the workload: `batch` images per step."""
+def cpu_model_string() -> str:
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.lower().startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def cpu_reference_step_rate(loss_name: str, size: int, steps: int, warmup: int, batch: int = 4, optimizer: bool = False):
+    """The reference's CPU path on a bounded sample of the workload (`batch` images per step, torch CPU fp32, all host
+    threads; BASELINE.md §4: >= 3 warm-ups, >= 10 timed steps, best and median reported).  When /root/reference is
+    present the reference's OWN classes are lifted by `ast` and run unmodified (kind "reference"); elsewhere — the GPU
+    box — the restatement in oracle/unet_oracle.py runs (kind "port")."""
     import torch
+    from oracle import ref_lift
     from oracle import unet_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    steps, warmup = max(steps, 10), max(warmup, 3)
     x, tgt = O.synth_batch(batch, size, size, seed=0)
-    sd = O.synth_state_dict(seed=0)
-    keys = O.param_keys(sd)
-    for k in keys:
-        sd[k].requires_grad_(True)
-    fn = {"focal_dice": lambda z, t: O.focal_dice_loss(z, t, 0.5, 2.0, 1.0, 0.7),
-          "composite": lambda z, t: O.composite_seg_loss(z, t, 0.5, 0.3),
-          "bce_dice": lambda z, t: O.bce_dice_loss(z, t)}[loss_name]
     times = []
-    for i in range(warmup + steps):
+    if ref_lift.available():
+        kind = "reference"
+        torch.manual_seed(0)
+        net, logits_of, crit = ref_lift.reference_model_and_loss(loss_name)    # default init under seed 0
+        net.train()
+        opt = torch.optim.AdamW(net.parameters(), lr=1e-3, weight_decay=1e-4) if optimizer else None
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            net.zero_grad(set_to_none=True)
+            loss = crit(logits_of(x), tgt)
+            loss.backward()
+            if opt is not None:
+                opt.step()
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    else:
+        kind = "port"
+        sd = O.synth_state_dict(seed=0)
+        keys = O.param_keys(sd)
         for k in keys:
-            sd[k].grad = None
-        t0 = time.perf_counter()
-        loss = fn(O.unet_logits(x, sd, training=True), tgt)
-        loss.backward()
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
+            sd[k].requires_grad_(True)
+        fn = {"focal_dice": lambda z, t: O.focal_dice_loss(z, t, 0.5, 2.0, 1.0, 0.7),
+              "composite": lambda z, t: O.composite_seg_loss(z, t, 0.5, 0.3),
+              "bce_dice": lambda z, t: O.bce_dice_loss(z, t)}[loss_name]
+        opt = torch.optim.AdamW([sd[k] for k in keys], lr=1e-3, weight_decay=1e-4) if optimizer else None
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            for k in keys:
+                sd[k].grad = None
+            loss = fn(O.unet_logits(x, sd, training=True), tgt)
+            loss.backward()
+            if opt is not None:
+                opt.step()
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
     total = sum(times)
+    best, med = min(times), statistics.median(times)
     return dict(value=batch * len(times) / total, ms_per_step=1e3 * total / len(times), cores=torch.get_num_threads(),
-                sample=f"{len(times)} fwd+bwd steps of {batch}x3x{size}x{size} fp32, {loss_name}, torch CPU "
-                       f"({warmup} warm-up)")
+                kind=kind, best_ms=1e3 * best, median_ms=1e3 * med, best_img_per_s=batch / best,
+                median_img_per_s=batch / med, cpu_model=cpu_model_string(),
+                sample=f"{len(times)} fwd+bwd{'+AdamW' if optimizer else ''} steps of {batch}x3x{size}x{size} fp32, {loss_name}, "
+                       f"torch CPU on {torch.get_num_threads()} threads of '{cpu_model_string()}' ({warmup} warm-ups; "
+                       f"best {1e3 * best:.0f} ms, median {1e3 * med:.0f} ms per step)")
+
+
+def cpu_baseline_block(r):
+    return {"value": r["value"], "unit": "img/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+            "best_img_per_s": r["best_img_per_s"], "median_img_per_s": r["median_img_per_s"], "cpu_model": r["cpu_model"]}
 
 
 def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 6))
-    r = cpu_reference_step_rate(wl["loss"], wl["size"], steps, max(1, min(args.warmup, 2)))
+    steps = max(10, min(args.steps, 20))
+    warmup = max(3, min(args.warmup, 5))
+    r = cpu_reference_step_rate(wl["loss"], wl["size"], steps, warmup)
     line = {
         "impl": "reference", "metric": "train_images_per_sec", "value": r["value"], "unit": "img/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": r["ms_per_step"],
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "note": "reference CPU path (oracle port of the reference classes) on a "
-                   "bounded sample: 4 images per step on the host cores"},
-        "cpu_baseline": {"value": r["value"], "unit": "img/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "config": {"workload": wl["desc"], "note": "reference CPU path (" + ("the reference's own classes lifted from "
+                   "/root/reference" if r["kind"] == "reference" else "oracle port of the reference classes") +
+                   ") on a bounded sample: 4 images per step on the host cores"},
+        "cpu_baseline": cpu_baseline_block(r),
         "e2e": {"value": r["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -192,6 +238,75 @@ def run_reference(args, wl):
 
 
 # ------------------------------------------------------------------------------------------------
+def make_criterion_and_optimizer(name, model):
+    import torch
+    import cartseg
+    wl = WORKLOADS[name]
+    if wl["loss"] == "focal_dice":
+        crit = cartseg.FocalDiceLoss(alpha=0.5, gamma=2.0, smooth=1.0, w_focal=0.7)
+    elif wl["loss"] == "composite":
+        crit = cartseg.CompositeSegLoss(bce_weight=0.5, boundary_weight=0.3)
+    else:
+        crit = cartseg.BCEDiceLoss()
+    if name == "k3":                             # src/train_with_focalDice_unfrozen.py:388-392
+        opt = torch.optim.AdamW([{"params": list(model.encoder.parameters()), "lr": 1e-4},
+                                 {"params": list(model.decoder.parameters()), "lr": 1e-3},
+                                 {"params": list(model.segmentation_head.parameters()), "lr": 3e-3}],
+                                weight_decay=1e-4, fused=True)
+    else:
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True)
+    return crit, opt
+
+
+def quick_workload(name, model, world, rank, dev, steps, barrier):
+    """Device-resident throughput of another workload: 3 warm-up steps, `steps` timed steps between CUDA events,
+    barrier + synchronize on both sides, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    import cartseg
+    from cartseg import ops as cs_ops
+    wl = WORKLOADS[name]
+    B, S = wl["batch"], wl["size"]
+    crit, opt = make_criterion_and_optimizer(name, model)
+    x, t = synth_batch(B, S, S, seed=100 + rank)
+    x, t = x.to(dev), t.to(dev)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = crit(model(x), t)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(3):
+        step()
+    barrier()
+    n0 = cartseg.lib().cs_kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = cartseg.lib().cs_kernel_launch_count() - n0
+    if world > 1:
+        tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt[0])
+    last = float(loss.item())
+    del x, t
+    cs_ops.release_plans()
+    torch.cuda.empty_cache()
+    value = world * B * steps / (ms / 1e3)
+    tf = (value / world) * GFLOP_TRAIN[S] / 1e3
+    pk = peaks()
+    return {"workload": wl["desc"], "value": value, "unit": "img/s", "ms_per_step": ms / steps, "steps": steps, "warmup": 3,
+            "per_gpu_batch": B, "n_gpus": world, "gpu_launches": int(launches), "last_loss": last,
+            "whole_step": {"tflops": tf, "frac": tf / pk["tf_sust"], "frac_of_burst_peak": tf / pk["tf_burst"],
+                           "gflop_per_image": GFLOP_TRAIN[S]}}
+
+
 def run_ours(args, wl):
     import torch
     import torch.distributed as dist
@@ -212,19 +327,7 @@ def run_ours(args, wl):
     model = cartseg.UNet().to(dev).train()
     if world > 1:
         cartseg.parallel.init_data_parallel(model)
-    if wl["loss"] == "focal_dice":
-        crit = cartseg.FocalDiceLoss(alpha=0.5, gamma=2.0, smooth=1.0, w_focal=0.7)
-    elif wl["loss"] == "composite":
-        crit = cartseg.CompositeSegLoss(bce_weight=0.5, boundary_weight=0.3)
-    else:
-        crit = cartseg.BCEDiceLoss()
-    if args.workload == "k3":                    # src/train_with_focalDice_unfrozen.py:388-392
-        opt = torch.optim.AdamW([{"params": list(model.encoder.parameters()), "lr": 1e-4},
-                                 {"params": list(model.decoder.parameters()), "lr": 1e-3},
-                                 {"params": list(model.segmentation_head.parameters()), "lr": 3e-3}],
-                                weight_decay=1e-4, fused=True)
-    else:
-        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True)
+    crit, opt = make_criterion_and_optimizer(args.workload, model)
 
     x_h, t_h = synth_batch(B, S, S, seed=rank)
     x_h, t_h = x_h.pin_memory(), t_h.pin_memory()
@@ -340,6 +443,17 @@ def run_ours(args, wl):
     e2e_ms = 1e3 * (time.perf_counter() - t0)
     assert bool(torch.isfinite(losses_h).all())
 
+    # ---- the other workloads north_star names, measured the same way (device-resident, CUDA events, max over ranks)
+    # with fewer steps, so that one driver run (and its 1/2/4/8 scaling run) also carries the 512^2 and boundary-loss
+    # numbers.  They reuse the model; each builds its own criterion / optimizer / plan.
+    others = {}
+    if not args.no_extra_workloads:
+        del x_d, t_d
+        cs_ops.release_plans()
+        torch.cuda.empty_cache()
+        for name in [w for w in ("k2", "k3", "k4") if w != args.workload]:
+            others[name] = quick_workload(name, model, world, rank, dev, min(args.steps, 10), barrier)
+
     if world > 1:
         tt = torch.tensor([ms, e2e_ms, fb_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -385,11 +499,11 @@ def run_ours(args, wl):
                          "whole_step": {"tflops": per_gpu_tflops, "frac": per_gpu_tflops / pk["tf_sust"],
                                         "gflop_per_image": GFLOP_TRAIN[S]},
                          "kernels": kernels},
+            "other_workloads": others,
         }
         if world == 1 and not args.no_cpu_baseline:
-            r = cpu_reference_step_rate(wl["loss"], S, steps=3, warmup=1)
-            line["cpu_baseline"] = {"value": r["value"], "unit": "img/s", "cores": r["cores"], "kind": "port",
-                                    "sample": r["sample"]}
+            r = cpu_reference_step_rate(wl["loss"], S, steps=10, warmup=3)
+            line["cpu_baseline"] = cpu_baseline_block(r)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -403,6 +517,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="k2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-workloads", action="store_true",
+                    help="skip the short k3 / k4 (or k2) measurements reported under other_workloads")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

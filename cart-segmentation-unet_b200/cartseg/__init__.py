@@ -10,6 +10,8 @@ from .modules import (ABL, BCEDiceABL, BCEDiceLoss, BCEDiceLossPerSample, Compos
 from .metrics import (dice_iou_at_t, dice_metric, find_best_threshold, hard_dice_metric, hard_iou_metric, iou_metric,
                       precision_recall_f1, pseudo_label_mask, sweep_thresholds, threshold_sums)
 from . import parallel
+from . import graphs
+from .graphs import GraphedInference, GraphedTrainStep
 from . import postproc
 from . import preproc
 from .preproc import letterbox_resize_normalize, resize_masks
@@ -18,7 +20,7 @@ from .postproc import (clean_mask, clean_mask_largest_component, ensemble_forwar
 lib()   # fail loudly at import time if the extension has not been built
 
 __all__ = [
-    "CartsegError", "LIB_PATH", "lib", "ops", "parallel",
+    "CartsegError", "LIB_PATH", "lib", "ops", "parallel", "graphs", "GraphedInference", "GraphedTrainStep",
     "UNet", "DoubleConv", "BCEDiceLoss", "BCEDiceLossPerSample", "FocalLoss", "FocalDiceLoss",
     "SymmetricBoundaryLoss", "CompositeSegLoss", "batch_sdf_from_masks", "ABL", "BCEDiceABL",
     "dice_metric", "iou_metric", "precision_recall_f1", "dice_iou_at_t", "hard_dice_metric", "hard_iou_metric",

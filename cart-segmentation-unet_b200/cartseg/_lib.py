@@ -91,6 +91,8 @@ _SIGNATURES = {
     "cs_loss_scratch_bytes": (C.c_size_t, [C.c_int]),
     "cs_loss_forward": (C.c_int, [C.POINTER(LossDesc), _P, _P, _P, _P, _P, _P, _P]),
     "cs_loss_backward": (C.c_int, [C.POINTER(LossDesc), _P, _P, _P, _P, _P, _P, _P, _P]),
+    "cs_focal_map_forward": (C.c_int, [_P, _P, C.c_longlong, C.c_float, C.c_float, _P, _P]),
+    "cs_focal_map_backward": (C.c_int, [_P, _P, _P, C.c_longlong, C.c_float, C.c_float, _P, _P]),
     "cs_threshold_stats": (C.c_int, [_P, _P, C.c_int, C.c_longlong, _P, C.c_int, _P, _P, _P]),
     "cs_threshold_mask": (C.c_int, [_P, C.c_longlong, C.c_float, _P, _P]),
     "cs_abl_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),

@@ -73,12 +73,17 @@ class _ParamGroup:
         return self
 
     def train(self, mode: bool = True):
+        """Per-group train / eval flags are accepted (scripts call ``model.encoder.eval()`` to freeze BN statistics),
+        but the fused op has ONE BatchNorm mode: ``UNet.forward`` raises if the groups disagree with the model."""
         for m in self._modules_list:
             m.train(mode)
         return self
 
     def eval(self):
         return self.train(False)
+
+
+_next_uid = 1
 
 
 class UNet(nn.Module):
@@ -113,8 +118,37 @@ class UNet(nn.Module):
         self.dconv1 = DoubleConv(128, 64)
         self.final_conv = nn.Conv2d(64, out_channels, 1)
         self._dp_handle = 0
-        self._weights_epoch = 0          # advanced by every training-mode forward (see ops._ensure_packed)
+        # bf16 weight packs follow (instance id, epoch): see ops._ensure_packed
+        global _next_uid
+        self._uid = _next_uid
+        _next_uid += 1
+        self._weights_epoch = 0          # advanced by every forward (eval too, unless freeze_packed) and load_state_dict
+        self._packed_frozen = False
         self._reserve_sms = 0            # SMs left to the NCCL kernels in data-parallel runs (parallel.init_data_parallel)
+        self.register_load_state_dict_post_hook(UNet._after_load_state_dict)
+
+    @staticmethod
+    def _after_load_state_dict(module, incompatible_keys) -> None:
+        module._weights_epoch += 1
+
+    def freeze_packed(self, flag: bool = True) -> "UNet":
+        """Latency-critical inference (batch 1): promise that the parameters do not change between eval-mode forwards,
+        so the bf16 weight packs are reused instead of being rebuilt on every call.  Training-mode forwards and
+        ``load_state_dict`` still invalidate them; in-place edits through ``p.data`` do NOT — call this again (or
+        ``freeze_packed(False)``) after such an edit."""
+        self._packed_frozen = bool(flag)
+        self._weights_epoch += 1
+        return self
+
+    def _check_single_bn_mode(self) -> None:
+        mods = self._modules
+        for name in ("conv1", "conv2", "conv3", "conv4", "conv5", "dconv4", "dconv3", "dconv2", "dconv1"):
+            seq = mods[name]._modules["conv"]._modules
+            if seq["1"].training != self.training or seq["4"].training != self.training:
+                raise CartsegError(
+                    f"{name}: BatchNorm is in {'train' if seq['1'].training else 'eval'} mode but the model is in "
+                    f"{'train' if self.training else 'eval'} mode.  cartseg.UNet runs as one fused op with a single "
+                    "BatchNorm mode: per-group model.encoder.eval() (frozen BN statistics) is not supported")
 
     # ---- groups the training scripts address (smp.Unet naming) --------------------------------
     @property
@@ -195,27 +229,34 @@ class UNet(nn.Module):
         x = x.detach()
         if x.dtype != torch.float32 or not x.is_contiguous():
             x = x.to(torch.float32).contiguous()
+        self._check_single_bn_mode()
         params = self._flat_params()
         buffers = self._flat_buffers()
         grad_mode = torch.is_grad_enabled()
-        need_grad = self.training and grad_mode and any(p.requires_grad for p in params)
+        wants_grad = grad_mode and any(p.requires_grad for p in params)
+        need_grad = self.training and wants_grad
         plan = ops.get_plan(B, C, H, W, x.device, inference_only=not self.training)
-        if self.training:
+        if self.training or not self._packed_frozen:
             self._weights_epoch += 1
+        token = (self._uid << 40) | (self._weights_epoch & ((1 << 40) - 1))
         if self._reserve_sms != plan.reserved_sms:
             ops.set_plan_sm_reserve(plan, self._reserve_sms)
         if need_grad:
             frozen = self._frozen_encoder_convs(params)
-            logits = ops.UNetFunction.apply(x, plan.id, True, frozen, self._dp_handle, self._weights_epoch,
+            logits = ops.UNetFunction.apply(x, plan.id, True, frozen, self._dp_handle, token,
                                             len(params), *params, *buffers)
+        elif wants_grad and not torch.compiler.is_compiling():
+            # eval mode with autograd on and trainable parameters: go through the autograd function so that a later
+            # backward() gets the explicit error of UNetFunction.backward instead of a generic "does not require grad"
+            logits = ops.UNetFunction.apply(x, plan.id, False, 0, 0, token, len(params), *params, *buffers)
         else:
             # without grad mode (torch.no_grad / inference_mode: every inference caller of the reference) the parameters
             # go to the op as they are; 82 detach() calls are 0.1 ms of host time
             if grad_mode or self.training or torch.compiler.is_compiling():
                 plist = [p.detach() for p in params] if grad_mode else params
-                logits = torch.ops.cartseg.unet_forward(x, plist, buffers, self.training, plan.id, self._weights_epoch)
+                logits = torch.ops.cartseg.unet_forward(x, plist, buffers, self.training, plan.id, token)
             else:                                        # eager inference: same body, without the dispatcher
-                logits = ops.unet_forward_impl(x, params, buffers, False, plan.id, self._weights_epoch)
+                logits = ops.unet_forward_impl(x, params, buffers, False, plan.id, token)
         return torch.sigmoid(logits) if self.final_sigmoid else logits
 
 
@@ -282,13 +323,14 @@ class FocalLoss(nn.Module):
 
     def __init__(self, alpha: float = 0.25, gamma: float = 2.0, reduction: str = "mean"):
         super().__init__()
-        if reduction not in ("mean", "sum"):
-            raise CartsegError("cartseg.FocalLoss provides the fused reductions 'mean' and 'sum' "
-                               "(the reference only ever uses 'mean', src/train_with_focalDice.py:226)")
+        # 'mean' / 'sum': the fused reduction kernels; anything else returns the unreduced map, as the reference's
+        # if / elif / else does (src/train_with_focalDice.py:214-219)
         self.alpha, self.gamma, self.reduction = alpha, gamma, reduction
 
     def forward(self, logits: Tensor, targets: Tensor) -> Tensor:
         lg, tg = _prep(logits, targets)
+        if self.reduction not in ("mean", "sum"):
+            return torch.ops.cartseg.focal_map(lg, tg, float(self.alpha), float(self.gamma))
         return _seg_loss(lg, tg, None, None, lg.shape[0], w_elem=1.0, alpha=self.alpha, gamma=self.gamma,
                          elem_sum=self.reduction == "sum")
 

@@ -24,7 +24,8 @@ from ._lib import CartsegError, LossDesc, UnetTensors, check, ptr
 # =============================================================================================
 # U-Net plans: one per (batch, channels, H, W, device, inference_only); each owns its workspace.
 # =============================================================================================
-_MAX_PLANS = {False: 2, True: 4}          # training / inference plans kept alive per process
+_MAX_PLANS = {False: 4, True: 6}          # training / inference plans kept alive per process (a ragged last batch, a
+                                          # validation shape and the main shape must not evict each other every epoch)
 
 
 class Plan:
@@ -116,9 +117,6 @@ _WEIGHT_SLOTS = tuple([b + o for b in list(range(0, 40, 8)) + list(range(48, 80,
                       + [40, 42, 44, 46])
 
 
-_checked_layouts: Dict[tuple, bool] = {}
-
-
 def _fill_tensors(params: List[Tensor], grads: Optional[List[Optional[Tensor]]],
                   buffers: Optional[List[Tensor]]) -> UnetTensors:
     t = UnetTensors()
@@ -126,24 +124,21 @@ def _fill_tensors(params: List[Tensor], grads: Optional[List[Optional[Tensor]]],
         raise CartsegError(f"expected {_lib.NUM_PARAMS} parameters in state-dict order, got {len(params)}")
     if buffers is not None and len(buffers) != 3 * _lib.NUM_BN:
         raise CartsegError(f"expected {3 * _lib.NUM_BN} BN buffers (mean, var, count per layer), got {len(buffers)}")
-    # dtype / layout / device checks once per set of tensor objects (this runs on every forward and backward)
-    ident = (tuple(map(id, params)), tuple(map(id, buffers)) if buffers is not None else None)
-    if ident not in _checked_layouts:
-        for i, p in enumerate(params):
-            if not p.is_cuda:
+    # dtype / layout / device are checked on EVERY call (raw pointers go to the kernels): a cache keyed on object ids can
+    # be hit by recycled ids after model.half() / .cpu() / a channels_last conversion.  ~20 us of host time.
+    f32 = torch.float32
+    for i, p in enumerate(params):
+        if not p.is_cuda:
+            raise CartsegError("cartseg ops take CUDA tensors only (no CPU fallback)")
+        if p.dtype is not f32 or not p.is_contiguous():
+            raise CartsegError(f"parameter {i} must be a contiguous float32 tensor")
+    if buffers is not None:
+        for i in range(_lib.NUM_BN):
+            rm, rv, nbt = buffers[3 * i], buffers[3 * i + 1], buffers[3 * i + 2]
+            if not (rm.is_cuda and rv.is_cuda and nbt.is_cuda):
                 raise CartsegError("cartseg ops take CUDA tensors only (no CPU fallback)")
-            if p.dtype != torch.float32 or not p.is_contiguous():
-                raise CartsegError(f"parameter {i} must be a contiguous float32 tensor")
-        if buffers is not None:
-            for i in range(_lib.NUM_BN):
-                rm, rv, nbt = buffers[3 * i], buffers[3 * i + 1], buffers[3 * i + 2]
-                if not (rm.is_cuda and rv.is_cuda and nbt.is_cuda):
-                    raise CartsegError("cartseg ops take CUDA tensors only (no CPU fallback)")
-                if rm.dtype != torch.float32 or rv.dtype != torch.float32 or nbt.dtype != torch.int64:
-                    raise CartsegError("BN buffers must be float32 running_mean / running_var and int64 num_batches_tracked")
-        if len(_checked_layouts) > 64:
-            _checked_layouts.clear()
-        _checked_layouts[ident] = True
+            if rm.dtype is not f32 or rv.dtype is not f32 or nbt.dtype is not torch.int64:
+                raise CartsegError("BN buffers must be float32 running_mean / running_var and int64 num_batches_tracked")
     tp = t.param
     for i, p in enumerate(params):
         tp[i] = p.data_ptr()
@@ -162,9 +157,10 @@ def _fill_tensors(params: List[Tensor], grads: Optional[List[Optional[Tensor]]],
 
 def _ensure_packed(plan: Plan, params: List[Tensor], t: UnetTensors, pack_token: int) -> None:
     """Re-pack the bf16 weight copies when the fp32 parameters may have changed.  Tensor version counters are not
-    enough (fused optimizers update parameters without bumping them), so the module also passes a token that
-    it advances on every training-mode forward: training steps always re-pack, and an eval-mode plan re-packs
-    after any training step that happened since its last use."""
+    enough (fused optimizers and ``p.data`` updates change parameters without bumping them; a freshly built model can
+    reuse a freed model's addresses), so the module passes a token = (its unique instance id, a counter): the counter
+    advances on every training-mode forward, every ``load_state_dict`` and — unless ``model.freeze_packed()`` was
+    called — every eval-mode forward too.  The pack is one launch of ~30 us."""
     key = (pack_token,) + tuple((params[i].data_ptr(), params[i]._version) for i in _WEIGHT_SLOTS)
     if key != plan.pack_key:
         check(_lib.lib().cs_unet_pack_weights(plan.handle, C.byref(t), _lib.current_stream()), "cs_unet_pack_weights")
@@ -240,8 +236,10 @@ def grad_layout(params: List[Tensor]) -> Tuple[List[int], List[int], List[int]]:
 
 @torch.library.custom_op("cartseg::unet_backward", mutates_args=(), device_types="cuda")
 def unet_backward(dlogits: Tensor, params: List[Tensor], plan_id: int, generation: int, frozen_encoder_convs: int,
-                  dp_handle: int) -> Tensor:
-    """Returns ONE flat float32 buffer holding every parameter gradient (layout: grad_layout)."""
+                  dp_handle: int, no_grad_params: List[int]) -> Tensor:
+    """Returns ONE flat float32 buffer holding every parameter gradient (layout: grad_layout).  Parameters listed in
+    ``no_grad_params`` (requires_grad == False) get no gradient kernel at all — their weight-gradient GEMM is skipped —
+    and their slice of the buffer is zero."""
     plan = _plan(plan_id)
     if generation != plan.generation:
         raise CartsegError("the activations of this forward pass were overwritten by a later training-mode forward "
@@ -251,15 +249,16 @@ def unet_backward(dlogits: Tensor, params: List[Tensor], plan_id: int, generatio
         raise CartsegError(f"dlogits must have shape {(B, 1, H, W)}")
     dlogits = dlogits.to(torch.float32).contiguous()
     order, offs, stage_off = grad_layout(params)
-    flat = torch.empty(stage_off[-1], dtype=torch.float32, device=dlogits.device)
+    skip = set(int(i) for i in no_grad_params)
+    for j in range(frozen_encoder_convs):              # a frozen encoder prefix is skipped by the kernels altogether
+        base = (j // 2) * 8 + (j % 2) * 4
+        skip.update(range(base, base + 4))
+    # slices nobody writes must not be garbage (a data-parallel bucket all-reduces them)
+    flat = (torch.zeros if skip else torch.empty)(stage_off[-1], dtype=torch.float32, device=dlogits.device)
     grads: List[Optional[Tensor]] = [None] * len(params)
     for i, o in zip(order, offs):
-        grads[i] = flat[o:o + params[i].numel()]
-    for j in range(frozen_encoder_convs):
-        # frozen encoder convs are skipped by the kernels: their slices must not be garbage
-        base = (j // 2) * 8 + (j % 2) * 4
-        for i in range(base, base + 4):
-            grads[i].zero_()
+        if i not in skip:
+            grads[i] = flat[o:o + params[i].numel()]
     t = _fill_tensors(params, grads, None)
     L = _lib.lib()
     sync = _DP_STATES.get(dp_handle) if dp_handle else None
@@ -289,7 +288,7 @@ def unet_backward(dlogits: Tensor, params: List[Tensor], plan_id: int, generatio
 
 
 @unet_backward.register_fake
-def _(dlogits, params, plan_id, generation, frozen_encoder_convs, dp_handle):
+def _(dlogits, params, plan_id, generation, frozen_encoder_convs, dp_handle, no_grad_params):
     return dlogits.new_empty(sum(p.numel() for p in params), dtype=torch.float32)
 
 
@@ -318,10 +317,11 @@ class UNetFunction(torch.autograd.Function):
             raise CartsegError("backward through an eval-mode forward is not available: call model.train() "
                                "(batch-statistics BN) for training steps")
         params = [p.detach() for p in ctx.saved_tensors]
-        flat = torch.ops.cartseg.unet_backward(dlogits, params, ctx.plan_id, ctx.generation, ctx.frozen, ctx.dp_handle)
+        need = ctx.needs_input_grad[7:7 + ctx.n_params]
+        flat = torch.ops.cartseg.unet_backward(dlogits, params, ctx.plan_id, ctx.generation, ctx.frozen, ctx.dp_handle,
+                                               [i for i in range(ctx.n_params) if not need[i]])
         order, offs, _ = grad_layout(params)
         out: List[Optional[Tensor]] = [None] * ctx.n_params
-        need = ctx.needs_input_grad[7:7 + ctx.n_params]
         for i, o in zip(order, offs):
             if need[i]:
                 out[i] = flat[o:o + params[i].numel()].view(params[i].shape)
@@ -424,6 +424,57 @@ def _seg_loss_bwd(ctx, grad_loss, grad_scratch):
 seg_loss.register_autograd(_seg_loss_bwd, setup_context=_seg_loss_setup)
 # under torch.autocast the loss takes float32 like the reference's native op (label_smooth.py:63 custom_fwd(cast_inputs=float32))
 seg_loss.register_autocast("cuda", torch.float32)
+
+
+# ---- FocalLoss(reduction="none"): the unreduced map (src/train_with_focalDice.py:214-219) --------------------------------
+@torch.library.custom_op("cartseg::focal_map", mutates_args=(), device_types="cuda")
+def focal_map(logits: Tensor, targets: Tensor, alpha: float, gamma: float) -> Tensor:
+    for name, v in (("logits", logits), ("targets", targets)):
+        if not v.is_cuda:
+            raise CartsegError(f"cartseg::focal_map: {name} must be a CUDA tensor (no CPU fallback)")
+        if v.dtype != torch.float32 or not v.is_contiguous() or v.numel() != logits.numel():
+            raise CartsegError(f"cartseg::focal_map: {name} must be contiguous float32 with {logits.numel()} elements")
+    out = torch.empty_like(logits)
+    if logits.numel():
+        with torch.cuda.device(logits.device):
+            check(_lib.lib().cs_focal_map_forward(ptr(logits), ptr(targets), logits.numel(), alpha, gamma, ptr(out),
+                                                  _lib.current_stream()), "cs_focal_map_forward")
+    return out
+
+
+@focal_map.register_fake
+def _(logits, targets, alpha, gamma):
+    return torch.empty_like(logits)
+
+
+@torch.library.custom_op("cartseg::focal_map_backward", mutates_args=(), device_types="cuda")
+def focal_map_backward(grad_out: Tensor, logits: Tensor, targets: Tensor, alpha: float, gamma: float) -> Tensor:
+    go = grad_out.to(torch.float32).contiguous()
+    dlogits = torch.empty_like(logits)
+    if logits.numel():
+        with torch.cuda.device(logits.device):
+            check(_lib.lib().cs_focal_map_backward(ptr(logits), ptr(targets), ptr(go), logits.numel(), alpha, gamma,
+                                                   ptr(dlogits), _lib.current_stream()), "cs_focal_map_backward")
+    return dlogits
+
+
+@focal_map_backward.register_fake
+def _(grad_out, logits, targets, alpha, gamma):
+    return torch.empty_like(logits)
+
+
+def _focal_map_setup(ctx, inputs, output):
+    ctx.scalars = inputs[2:]
+    ctx.save_for_backward(inputs[0], inputs[1])
+
+
+def _focal_map_bwd(ctx, grad):
+    logits, targets = ctx.saved_tensors
+    return torch.ops.cartseg.focal_map_backward(grad, logits, targets, *ctx.scalars), None, None, None
+
+
+focal_map.register_autograd(_focal_map_bwd, setup_context=_focal_map_setup)
+focal_map.register_autocast("cuda", torch.float32)
 
 
 # =============================================================================================

@@ -182,6 +182,29 @@ CS_DEVINL void umma_bf16_steps_warp(uint32_t tmem_d, uint32_t a_lo, uint32_t b_l
 #undef CS_MMA_STEP
 }
 
+// Four K-steps with separate descriptor high words for A (a register: SBO / base offset vary) and B (SBO = 1024).
+template <bool PAIR>
+CS_DEVINL void umma_bf16_steps4_warp_hi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t idesc,
+                                        uint32_t accumulate_first) {
+#define CS_MMA_STEP2(i, PRED)                                                                    \
+  "add.u32 al, %1, " #i "*2;\n\t"                                                                \
+  "add.u32 bl, %2, " #i "*2;\n\t"                                                                \
+  "mov.b64 da, {al, %7};\n\t"                                                                    \
+  "mov.b64 db, {bl, %3};\n\t"                                                                    \
+  "@q tcgen05.mma.cta_group::%8.kind::f16 [%0], da, db, %5, " PRED ";\n\t"
+  asm volatile(
+      "{\n\t.reg .pred p, q, t;\n\t.reg .b64 da, db;\n\t.reg .b32 al, bl;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.eq.b32 t, 0, 0;\n\t"
+      CS_MMA_STEP2(0, "p") CS_MMA_STEP2(1, "t") CS_MMA_STEP2(2, "t") CS_MMA_STEP2(3, "t")
+      "}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "n"(kDescHiSw128), "n"(0), "r"(idesc), "r"(accumulate_first), "r"(a_hi),
+      "n"(PAIR ? 2 : 1)
+      : "memory");
+#undef CS_MMA_STEP2
+}
+
 template <bool PAIR>
 CS_DEVINL void umma_commit_warp(uint64_t* bar) {
   if (PAIR) {

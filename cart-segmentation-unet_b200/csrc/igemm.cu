@@ -333,6 +333,132 @@ __global__ void __launch_bounds__(kThreads, 1) pix_gemm_kernel(const __grid_cons
   }
 }
 
+// Epilogue of the CTA-pair pixel GEMMs (EG groups of 128 threads, warps 2..): TMEM -> registers -> (affine / ReLU) -> bf16 ->
+// 128B-swizzled staging tile -> TMA store; train-mode BN statistics (sum, sum of squares) from the staged bf16 tile.
+// Shared by pix_gemm2_kernel and conv3_gemm_kernel.
+template <int BLOCK_N, int EG, int BPG, class Decode>
+CS_DEVINL void pix_pair_epilogue(const PixGemmParams& p, uint8_t* stage_base, float* vec, float* red_base, uint64_t* tmem_full,
+                                 uint64_t* tmem_empty, uint32_t tmem_base, int warp, int lane, int first_unit, int unit_stride,
+                                 int num_units, bool want_stats, Decode&& decode) {
+  const int eg = (warp - 2) >> 2;            // epilogue group: owns accumulator buffer `eg` when EG == 2
+  const int et = threadIdx.x - 64 - eg * 128;
+  const int sub = warp & 3;                  // TMEM sub-partition this warp may read
+  const int ewarp = (warp - 2) & 3;
+  const int bar0 = 3 * eg;                   // named barriers 1..3 (group 0), 4..6 (group 1)
+  float* gvec = vec + eg * 2048;             // this group's statistics accumulators
+  const int row = sub * 32 + lane;           // pixel row of the tile held by this thread
+  float* red = red_base + eg * 512;
+  int acc = 0, acc_phase = 0, unit_no = 0;
+  uint32_t buf_ctr = 0;
+  const bool affine = !want_stats && (p.scale != nullptr || p.shift != nullptr || p.relu);
+  for (int u = first_unit; u < num_units; u += unit_stride, ++unit_no) {
+    if (EG == 2) {                           // alternate units between the groups; acc buffer == group
+      if ((unit_no & 1) != eg) continue;
+      acc = eg;
+      acc_phase = (unit_no >> 1) & 1;
+    }
+    int nb, b, w0, h0;
+    const bool valid = decode(u, nb, b, w0, h0);
+
+    mbar_wait(&tmem_full[acc], acc_phase);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+    for (int cb = 0; cb < BLOCK_N / 64; ++cb) {
+      // an n-block may span several output maps (conv-transpose: one map per (i,j) of the 2x2 kernel)
+      const int col0 = nb * BLOCK_N + cb * 64;
+      const int omap = col0 / p.cols_per_map;
+      const int nin = col0 - omap * p.cols_per_map;     // first channel of this 64-wide chunk inside its map
+      uint8_t* sbuf = stage_base + (eg * BPG + (int)(buf_ctr % BPG)) * kStageBytes;
+      ++buf_ctr;
+      if (et == 0) tma_store_wait_read<BPG - 1>();     // the store that last used this buffer has drained
+      bar_sync(1 + bar0, 128);
+      uint32_t v[64];
+      tmem_ld32(taddr + cb * 64, v);
+      tmem_ld32(taddr + cb * 64 + 32, v + 32);
+      tmem_ld_wait();
+      if (cb == BLOCK_N / 64 - 1) {                    // accumulator fully read: hand it back to the MMA issuer
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive_cluster(mapa_cluster(smem_u32(&tmem_empty[acc]), 0));
+        }
+      }
+      uint32_t packed[32];
+      if (affine) {
+        const float* sc = vec + nin;
+        const float* sh = vec + 1024 + nin;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float a = __uint_as_float(v[2 * i]) * sc[2 * i] + sh[2 * i];
+          float c = __uint_as_float(v[2 * i + 1]) * sc[2 * i + 1] + sh[2 * i + 1];
+          if (p.relu) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
+          packed[i] = pack_bf16x2(a, c);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) packed[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+      }
+      {
+        uint8_t* rowp = sbuf + row * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 q = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+          *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = q;
+        }
+      }
+      fence_proxy_async();
+      bar_sync(2 + bar0, 128);
+      if (et == 0 && valid) {
+        tma_store_4d(&p.tmapO[omap], sbuf, p.o_chan0 + nin, w0, h0, b);
+        tma_store_commit();
+      }
+      if (want_stats) {
+        // Column sums over the staged bf16 tile: this warp covers rows [32*sub, 32*sub+32), lane
+        // covers the channel pair (2*lane, 2*lane+1).  Tile rows that lie outside the image hold
+        // values the store clips away; they are masked out here.
+        const uint32_t* s32 = reinterpret_cast<const uint32_t*>(sbuf);
+        const int chunk = lane >> 2, word = lane & 3;
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        if (valid) {
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {
+            const int r2 = sub * 32 + rr;
+            if (w0 + (r2 & 7) >= p.W || h0 + (r2 >> 3) >= p.H) continue;
+            const uint32_t w = s32[r2 * 32 + (((chunk ^ (r2 & 7)) << 2) | word)];
+            const float f0 = bf16_lo(w), f1 = bf16_hi(w);
+            s0 += f0; q0 += f0 * f0; s1 += f1; q1 += f1 * f1;
+          }
+        }
+        float* rw = red + (ewarp * 64 + 2 * lane) * 2;
+        rw[0] = s0; rw[1] = q0; rw[2] = s1; rw[3] = q1;
+        bar_sync(3 + bar0, 128);
+        const int c = et & 63, which = et >> 6;
+        float tot = 0.f;
+#pragma unroll
+        for (int w4 = 0; w4 < 4; ++w4) tot += red[(w4 * 64 + c) * 2 + which];
+        gvec[which * 1024 + nin + c] += tot;
+      }
+    }
+    if (EG == 1) {
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  if (et == 0) tma_store_wait_all<0>();
+  if (want_stats) {
+    bar_sync(1 + bar0, 128);
+    const int nvec = p.cols_per_map;
+    for (int i = et; i < nvec; i += 128) {
+      const float s = gvec[i], q = gvec[1024 + i];
+      if (q != 0.f) {
+        atomicAdd(&p.stat_sum[i], (double)s);
+        atomicAdd(&p.stat_sq[i], (double)q);
+      }
+    }
+  }
+}
+
 // Pair-only kernel with unified pipeline stages (A patch + its R weight tiles per stage, one mbarrier wait and one
 // commit per 4*R MMAs): ncu showed the single MMA-issuing warp to be the bottleneck of the finer-grained ring.
 // EG = number of 4-warp epilogue groups: with EG = 2 the groups take alternate work units (group e owns TMEM
@@ -509,124 +635,8 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) pix_gemm2_kernel(const __gri
     }
   } else {
     // ------------------------------------------------------------------ epilogue (EG groups of 128 threads)
-    const int eg = (warp - 2) >> 2;            // epilogue group: owns accumulator buffer `eg` when EG == 2
-    const int et = threadIdx.x - 64 - eg * 128;
-    const int sub = warp & 3;                  // TMEM sub-partition this warp may read
-    const int ewarp = (warp - 2) & 3;
-    const int bar0 = 3 * eg;                   // named barriers 1..3 (group 0), 4..6 (group 1)
-    float* gvec = vec + eg * 2048;             // this group's statistics accumulators
-    const int row = sub * 32 + lane;           // pixel row of the tile held by this thread
-    float* red = reinterpret_cast<float*>(smem + L::kRed) + eg * 512;
-    int acc = 0, acc_phase = 0, unit_no = 0;
-    uint32_t buf_ctr = 0;
-    const bool affine = !want_stats && (p.scale != nullptr || p.shift != nullptr || p.relu);
-    for (int u = first_unit; u < num_units; u += unit_stride, ++unit_no) {
-      if (EG == 2) {                           // alternate units between the groups; acc buffer == group
-        if ((unit_no & 1) != eg) continue;
-        acc = eg;
-        acc_phase = (unit_no >> 1) & 1;
-      }
-      int nb, b, w0, h0;
-      const bool valid = decode(u, nb, b, w0, h0);
-
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + acc * BLOCK_N;
-#pragma unroll 1
-      for (int cb = 0; cb < BLOCK_N / 64; ++cb) {
-        // an n-block may span several output maps (conv-transpose: one map per (i,j) of the 2x2 kernel)
-        const int col0 = nb * BLOCK_N + cb * 64;
-        const int omap = col0 / p.cols_per_map;
-        const int nin = col0 - omap * p.cols_per_map;     // first channel of this 64-wide chunk inside its map
-        uint8_t* sbuf = smem + L::kStage + (eg * BPG + (int)(buf_ctr % BPG)) * kStageBytes;
-        ++buf_ctr;
-        if (et == 0) tma_store_wait_read<BPG - 1>();     // the store that last used this buffer has drained
-        bar_sync(1 + bar0, 128);
-        uint32_t v[64];
-        tmem_ld32(taddr + cb * 64, v);
-        tmem_ld32(taddr + cb * 64 + 32, v + 32);
-        tmem_ld_wait();
-        if (cb == BLOCK_N / 64 - 1) {                    // accumulator fully read: hand it back to the MMA issuer
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (PAIR) mbar_arrive_cluster(mapa_cluster(smem_u32(&tmem_empty[acc]), 0));
-            else mbar_arrive(&tmem_empty[acc]);
-          }
-        }
-        uint32_t packed[32];
-        if (affine) {
-          const float* sc = vec + nin;
-          const float* sh = vec + 1024 + nin;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float a = __uint_as_float(v[2 * i]) * sc[2 * i] + sh[2 * i];
-            float c = __uint_as_float(v[2 * i + 1]) * sc[2 * i + 1] + sh[2 * i + 1];
-            if (p.relu) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
-            packed[i] = pack_bf16x2(a, c);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) packed[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-        }
-        {
-          uint8_t* rowp = sbuf + row * 128;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            uint4 q = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-            *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = q;
-          }
-        }
-        fence_proxy_async();
-        bar_sync(2 + bar0, 128);
-        if (et == 0 && valid) {
-          tma_store_4d(&p.tmapO[omap], sbuf, p.o_chan0 + nin, w0, h0, b);
-          tma_store_commit();
-        }
-        if (want_stats) {
-          // Column sums over the staged bf16 tile: this warp covers rows [32*sub, 32*sub+32), lane
-          // covers the channel pair (2*lane, 2*lane+1).  Tile rows that lie outside the image hold
-          // values the store clips away; they are masked out here.
-          const uint32_t* s32 = reinterpret_cast<const uint32_t*>(sbuf);
-          const int chunk = lane >> 2, word = lane & 3;
-          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-          if (valid) {
-#pragma unroll 8
-            for (int rr = 0; rr < 32; ++rr) {
-              const int r2 = sub * 32 + rr;
-              if (w0 + (r2 & 7) >= p.W || h0 + (r2 >> 3) >= p.H) continue;
-              const uint32_t w = s32[r2 * 32 + (((chunk ^ (r2 & 7)) << 2) | word)];
-              const float f0 = bf16_lo(w), f1 = bf16_hi(w);
-              s0 += f0; q0 += f0 * f0; s1 += f1; q1 += f1 * f1;
-            }
-          }
-          float* rw = red + (ewarp * 64 + 2 * lane) * 2;
-          rw[0] = s0; rw[1] = q0; rw[2] = s1; rw[3] = q1;
-          bar_sync(3 + bar0, 128);
-          const int c = et & 63, which = et >> 6;
-          float tot = 0.f;
-#pragma unroll
-          for (int w4 = 0; w4 < 4; ++w4) tot += red[(w4 * 64 + c) * 2 + which];
-          gvec[which * 1024 + nin + c] += tot;
-        }
-      }
-      if (EG == 1) {
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
-      }
-    }
-    if (et == 0) tma_store_wait_all<0>();
-    if (want_stats) {
-      bar_sync(1 + bar0, 128);
-      const int nvec = p.cols_per_map;
-      for (int i = et; i < nvec; i += 128) {
-        const float s = gvec[i], q = gvec[1024 + i];
-        if (q != 0.f) {
-          atomicAdd(&p.stat_sum[i], (double)s);
-          atomicAdd(&p.stat_sq[i], (double)q);
-        }
-      }
-    }
+    pix_pair_epilogue<BLOCK_N, EG, BPG>(p, smem + L::kStage, vec, reinterpret_cast<float*>(smem + L::kRed), tmem_full, tmem_empty,
+                                        tmem_base, warp, lane, first_unit, unit_stride, num_units, want_stats, decode);
   }
   tc_fence_before();
   if (PAIR) cluster_sync();                                  // the peer's smem / TMEM / barriers stay alive until here
@@ -636,6 +646,296 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) pix_gemm2_kernel(const __gri
     if (PAIR) tmem_dealloc_pair<L::kTmemCols>(tmem_base);
     else tmem_dealloc<L::kTmemCols>(tmem_base);
   }
+}
+
+// =============================================================================================
+//                       3x3 convolution with ONE activation patch per K-chunk
+// =============================================================================================
+// pix_gemm2_kernel loads an 8 x 18 pixel patch per (64-channel chunk, horizontal tap): every activation byte crosses
+// L2 -> shared memory three times, and the kernel is paced by that traffic, not by the MMAs (ncu, round 1: 9.4 TB/s of
+// l1tex<-xbar reads at N = 256; at N = 64 the loads per MMA-cycle are 3.6x higher still: 0.45 of the tensor peak).
+// Here ONE (8+2) x (16+2) patch per 64-channel chunk serves all nine taps: tap (kh, kw) of the tile is the same patch
+// read from row offset (kh * PW + kw) with a row-group stride (SBO) of PW * 128 B — the 128B swizzle is a function of
+// the shared-memory address, so the view stays consistent with what TMA wrote.  Weights: a ring of 3-tap groups
+// (RESIDENT = false), or, for the Cout = 64 layers (n_blocks == 1, K <= 128), ALL taps resident in shared memory for the
+// whole kernel (73 KB): per work unit only the 23 KB patch moves.
+template <int BLOCK_N, int PW, int SA, int SB, int NSTG, int EG, bool RESIDENT>
+struct Conv3Layout {
+  static constexpr int kAPatch = 18 * PW * 128;
+  static constexpr int kASlot = (kAPatch + 1023) & ~1023;
+  static constexpr int kBRows = BLOCK_N / 2;
+  static constexpr int kBTile = kBRows * 128;
+  static constexpr int kBGroup = 3 * kBTile;
+  static constexpr int kMaxResidentChunks = 2;
+  static constexpr int kBBytes = RESIDENT ? kMaxResidentChunks * 9 * kBTile : SB * kBGroup;
+  static constexpr int kNumB = RESIDENT ? 1 : SB;
+  static constexpr int kA = 0;
+  static constexpr int kB = kA + SA * kASlot;
+  static constexpr int kStage = kB + kBBytes;
+  static constexpr int kVec = kStage + NSTG * kStageBytes;   // EG x (2 x 1024 floats)
+  static constexpr int kRed = kVec + EG * 2 * 1024 * 4;      // EG x (4 x 64 x 2 floats)
+  static constexpr int kBar = kRed + EG * 4 * 64 * 2 * 4;
+  static constexpr int kThreadsTotal = 64 + 128 * EG;
+  static constexpr int kNumBar = 2 * SA + 2 * kNumB + 4;
+  static constexpr int kTmemPtr = kBar + kNumBar * 8;
+  static constexpr int kTotal = kTmemPtr + 16;
+  static constexpr int kDyn = kTotal + 1024;                 // slack for manual 1024-B alignment
+  static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  static_assert(RESIDENT || (3 * SA) % SB == 0, "the weight-ring slot of (A slot, tap group) must be a compile-time constant");
+};
+
+template <int BLOCK_N, int PW, int SA, int SB, int NSTG, int EG, bool RESIDENT>
+__global__ void __launch_bounds__(64 + 128 * EG, 1) conv3_gemm_kernel(const __grid_constant__ PixGemmParams p) {
+  using L = Conv3Layout<BLOCK_N, PW, SA, SB, NSTG, EG, RESIDENT>;
+  static_assert(NSTG % EG == 0, "every epilogue group owns NSTG / EG staging buffers");
+  constexpr int BPG = NSTG / EG;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBar);
+  uint64_t* fullA = bars;
+  uint64_t* emptyA = fullA + SA;
+  uint64_t* fullB = emptyA + SA;
+  uint64_t* emptyB = fullB + L::kNumB;
+  uint64_t* tmem_full = emptyB + L::kNumB;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtr);
+  float* vec = reinterpret_cast<float*>(smem + L::kVec);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int m_tiles = p.tiles_w * p.tiles_h * p.batch;
+  const int m_units = (m_tiles + 1) / 2;                     // two consecutive m-tiles (one per CTA of the pair)
+  const int num_units = m_units * p.n_blocks;
+  const int first_unit = (int)(blockIdx.x >> 1);
+  const int unit_stride = (int)(gridDim.x >> 1);
+  const bool want_stats = p.stat_sum != nullptr;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < SA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
+    for (int i = 0; i < L::kNumB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
+    fence_barrier_init();
+    tma_prefetch_desc(&p.tmapA3);
+    tma_prefetch_desc(&p.tmapB);
+    tma_prefetch_desc(&p.tmapO[0]);
+  }
+  if (warp == 2) tmem_alloc_pair<L::kTmemCols>(tmem_ptr);
+  {
+    const int nvec = p.cols_per_map;                         // <= 1024
+    for (int i = threadIdx.x; i < 1024; i += L::kThreadsTotal) {
+      float a = 0.f, b = 0.f;
+      if (!want_stats && i < nvec) {
+        a = p.scale ? p.scale[i] : 1.f;
+        b = p.shift ? p.shift[i] : 0.f;
+      }
+      vec[i] = a;                                            // group 0's copy doubles as the scale / shift table
+      vec[1024 + i] = b;
+      if (EG == 2) { vec[2048 + i] = 0.f; vec[3072 + i] = 0.f; }
+    }
+  }
+  tc_fence_before();
+  cluster_sync();                                            // both CTAs: barriers initialised, TMEM allocated
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int per_img = p.tiles_w * p.tiles_h;
+  auto decode = [&](int u, int& nb, int& b, int& w0, int& h0) -> bool {
+    const int m_unit = u / p.n_blocks;
+    nb = u - m_unit * p.n_blocks;
+    const int m_tile = 2 * m_unit + (int)rank;
+    const bool valid = m_tile < m_tiles;
+    b = valid ? m_tile / per_img : p.batch;                  // batch coordinate == batch: loads zero-filled, stores clipped
+    const int rem = valid ? m_tile - b * per_img : 0;
+    const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
+    w0 = tw * 8;
+    h0 = th * 16;
+    return valid;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    // The activation patch of K-chunk q+1 is requested right after the first weight group of chunk q, so that the
+    // weight ring never holds the patches back by more than one group.
+    int a_u = first_unit, a_kc = 0, sa = 0, pa = 0;
+    bool a_more = a_u < num_units;
+    auto issue_A = [&]() {
+      int nb, b, w0, h0;
+      decode(a_u, nb, b, w0, h0);
+      mbar_wait(&emptyA[sa], pa ^ 1);
+      if (lane == 0) {
+        if (leader) mbar_arrive_expect_tx(&fullA[sa], 2 * L::kAPatch);
+        tma_load_4d_pair(smem + L::kA + sa * L::kASlot, &p.tmapA3, mapa_cluster(smem_u32(&fullA[sa]), 0),
+                         p.a_chan0 + a_kc * 64, w0 - 1, h0 - 1, b);
+      }
+      __syncwarp();
+      if (++sa == SA) { sa = 0; pa ^= 1; }
+      if (++a_kc == p.kchunks) { a_kc = 0; a_u += unit_stride; a_more = a_u < num_units; }
+    };
+    if (RESIDENT) {
+      if (lane == 0 && first_unit < num_units) {
+        const uint32_t bar = mapa_cluster(smem_u32(&fullB[0]), 0);
+        if (leader) mbar_arrive_expect_tx(&fullB[0], 2 * p.kchunks * 9 * L::kBTile);
+        for (int kc = 0; kc < p.kchunks; ++kc)
+          for (int t = 0; t < 9; ++t)
+            tma_load_2d_pair(smem + L::kB + (kc * 9 + t) * L::kBTile, &p.tmapB, bar, kc * 64, t * p.Ntot + (int)rank * L::kBRows);
+      }
+      __syncwarp();
+      while (a_more) issue_A();
+    } else {
+      int sb = 0, pb = 0;
+      if (a_more) issue_A();
+      for (int u = first_unit; u < num_units; u += unit_stride) {
+        const int nb = u % p.n_blocks;
+        const int n0 = nb * BLOCK_N + (int)rank * L::kBRows;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          for (int g = 0; g < 3; ++g) {
+            mbar_wait(&emptyB[sb], pb ^ 1);
+            if (lane == 0) {
+              const uint32_t bar = mapa_cluster(smem_u32(&fullB[sb]), 0);
+              if (leader) mbar_arrive_expect_tx(&fullB[sb], 2 * L::kBGroup);
+              for (int r = 0; r < 3; ++r)
+                tma_load_2d_pair(smem + L::kB + sb * L::kBGroup + r * L::kBTile, &p.tmapB, bar, kc * 64,
+                                 (g * 3 + r) * p.Ntot + n0);
+            }
+            __syncwarp();
+            if (++sb == SB) { sb = 0; pb ^= 1; }
+            if (g == 0 && a_more) issue_A();
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc(256, BLOCK_N, 0, 0);
+      const uint32_t lbo_lo = (16u >> 4) << 16;                             // LBO field lives in the low word
+      const uint32_t s_base = (smem_u32(smem) >> 4) | lbo_lo;
+      // A descriptor high word: SBO = one image row of the patch (PW pixels x 128 B), version 1, 128B swizzle
+      constexpr uint32_t a_hi0 = ((uint32_t)(PW * 128) >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t base_off_on = p.conv3_desc_mode == 1 ? 1u : 0u;
+      int kc = 0, acc = 0, acc_phase = 0, phA = 0, u = first_unit;
+      uint32_t gq = 0;                                                      // weight groups consumed so far
+      uint32_t accumulate = 0;
+      bool more = u < num_units;
+      if (RESIDENT && more) { mbar_wait(&fullB[0], 0); tc_fence_after(); }
+      while (more) {
+#pragma unroll
+        for (int st = 0; st < SA; ++st) {
+          if (more) {
+            if (kc == 0) {
+              mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+              accumulate = 0;
+            }
+            mbar_wait(&fullA[st], phA);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+            const uint32_t a_slot = s_base + (uint32_t)((L::kA + st * L::kASlot) >> 4);
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+              uint32_t b_lo;
+              constexpr int kSlotMod = RESIDENT ? 1 : SB;
+              const int slot = RESIDENT ? 0 : (3 * st + g) % kSlotMod;
+              if (RESIDENT) {
+                b_lo = s_base + (uint32_t)(L::kB >> 4) + (uint32_t)((kc * 9 + g * 3) * (L::kBTile >> 4));
+              } else {
+                mbar_wait(&fullB[slot], (gq / (uint32_t)kSlotMod) & 1u);
+                tc_fence_after();
+                b_lo = s_base + (uint32_t)((L::kB + slot * L::kBGroup) >> 4);
+              }
+#pragma unroll
+              for (int r = 0; r < 3; ++r) {
+                const uint32_t row0 = (uint32_t)(r * PW + g);               // first patch row of this tap's view
+                const uint32_t a_hi = a_hi0 | (base_off_on * ((row0 & 7u) << 17));
+                // four K-steps of 16 channels: +32 bytes = +2 in the descriptor start field per step
+                umma_bf16_steps4_warp_hi<true>(d_tmem, a_slot + row0 * 8u, a_hi, b_lo + (uint32_t)(r * (L::kBTile >> 4)), idesc,
+                                               accumulate);
+                accumulate = 1;
+              }
+              if (!RESIDENT) umma_commit_warp<true>(&emptyB[slot]);
+              ++gq;
+            }
+            umma_commit_warp<true>(&emptyA[st]);
+            if (++kc == p.kchunks) {
+              umma_commit_warp<true>(&tmem_full[acc]);
+              kc = 0;
+              acc ^= 1;
+              if (acc == 0) acc_phase ^= 1;
+              u += unit_stride;
+              more = u < num_units;
+            }
+          }
+        }
+        phA ^= 1;
+      }
+    }
+  } else {
+    pix_pair_epilogue<BLOCK_N, EG, BPG>(p, smem + L::kStage, vec, reinterpret_cast<float*>(smem + L::kRed), tmem_full, tmem_empty,
+                                        tmem_base, warp, lane, first_unit, unit_stride, num_units, want_stats, decode);
+  }
+  tc_fence_before();
+  cluster_sync();                                            // the peer's smem / TMEM / barriers stay alive until here
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair<L::kTmemCols>(tmem_base);
+  }
+}
+
+template <int BLOCK_N, int PW, int SA, int SB, int NSTG, int EG, bool RESIDENT>
+static cudaError_t launch_conv3(const PixGemmParams& p, int num_sms, cudaStream_t stream) {
+  using L = Conv3Layout<BLOCK_N, PW, SA, SB, NSTG, EG, RESIDENT>;
+  static_assert(L::kDyn <= 232448, "shared memory budget exceeded");
+  auto kern = conv3_gemm_kernel<BLOCK_N, PW, SA, SB, NSTG, EG, RESIDENT>;
+  static std::atomic<unsigned long long> attr_done{0};
+  {
+    cudaError_t ae = ensure_dynamic_smem(kern, L::kDyn, attr_done);
+    if (ae != cudaSuccess) return ae;
+  }
+  const int m_tiles = p.tiles_w * p.tiles_h * p.batch;
+  const int units = ((m_tiles + 1) / 2) * p.n_blocks;
+  if (units <= 0) return cudaSuccess;
+  const int clusters = units < num_sms / 2 ? units : num_sms / 2;
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  cfg.gridDim = dim3(2 * clusters);
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cfg.blockDim = dim3(L::kThreadsTotal);
+  cfg.dynamicSmemBytes = L::kDyn;
+  cfg.stream = stream;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+  if (e != cudaSuccess) return e;
+  return launched();
+}
+
+static cudaError_t launch_conv3_gemm(const PixGemmParams& p, int block_n, int num_sms, cudaStream_t stream) {
+  if (p.G != 3 || p.R != 3 || !p.pair) return cudaErrorInvalidValue;
+  const bool resident = block_n == 64 && p.n_blocks == 1 && p.kchunks <= 2;
+  if (p.conv3_pw == 10) {
+    switch (block_n) {
+      case 64: return resident ? launch_conv3<64, 10, 4, 3, 2, 2, true>(p, num_sms, stream)
+                               : launch_conv3<64, 10, 4, 3, 2, 2, false>(p, num_sms, stream);
+      case 128: return launch_conv3<128, 10, 4, 3, 2, 2, false>(p, num_sms, stream);
+      case 256: return launch_conv3<256, 10, 2, 3, 1, 1, false>(p, num_sms, stream);
+      default: return cudaErrorInvalidValue;
+    }
+  }
+  if (p.conv3_pw == 16) {
+    switch (block_n) {
+      case 64: return resident ? launch_conv3<64, 16, 2, 3, 2, 2, true>(p, num_sms, stream)
+                               : launch_conv3<64, 16, 2, 3, 2, 2, false>(p, num_sms, stream);
+      case 128: return launch_conv3<128, 16, 2, 3, 2, 2, false>(p, num_sms, stream);
+      case 256: return launch_conv3<256, 16, 2, 2, 1, 1, false>(p, num_sms, stream);
+      default: return cudaErrorInvalidValue;
+    }
+  }
+  return cudaErrorInvalidValue;
 }
 
 template <int BLOCK_N, int S, int NSTG, int EG>
@@ -705,6 +1005,7 @@ static cudaError_t launch_pix(const PixGemmParams& p, int num_sms, cudaStream_t 
 }
 
 cudaError_t launch_pix_gemm(const PixGemmParams& p, int block_n, int num_sms, cudaStream_t stream) {
+  if (p.conv3) return launch_conv3_gemm(p, block_n, num_sms, stream);
   if (p.pair) {
     switch (block_n) {
       case 64: return launch_pix2<64, 5, 2, 2>(p, num_sms, stream);

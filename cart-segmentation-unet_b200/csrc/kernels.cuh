@@ -17,6 +17,20 @@ typedef __nv_bfloat16 bf16;
 struct TapMap { int v[9]; };
 cudaError_t launch_pack_pairs(const float* in, int Na, int Nb, int T, bf16* out_ab, TapMap map_ab, bf16* out_ba,
                               TapMap map_ba, cudaStream_t s);
+// The same for every weight tensor of the network in one launch (+ the stem pack below).
+struct PackJob {
+  const float* in; bf16* out_ab; bf16* out_ba;
+  int Na, Nb, T, map_ab, map_ba;      // map_*: index into PackBatch::maps
+  int tile0, tiles_x;                 // filled by the launcher
+};
+struct PackBatch {
+  static constexpr int kMaxJobs = 24;
+  PackJob job[kMaxJobs];
+  TapMap maps[4];
+  int n, total_tiles;
+  const float* first_in; bf16* first_out; int first_cout, first_cin;   // stem (first_in == NULL: none)
+};
+cudaError_t launch_pack_batch(PackBatch& pb, cudaStream_t s);
 // conv1.0: W[64][Cin<=7][3][3] -> [64][64] with k = (r*3+s)*Cin + c, zero padded
 cudaError_t launch_pack_first(const float* in, int Cout, int Cin, bf16* out, cudaStream_t s);
 // dWp[t][a][b] (fp32) -> grad[(a*Nb+b)*T + map[t]]
@@ -118,6 +132,12 @@ struct LossArgs {
 size_t loss_scratch_bytes(int rows);
 cudaError_t launch_loss_forward(const LossArgs& a, cudaStream_t s);
 cudaError_t launch_loss_backward(const LossArgs& a, cudaStream_t s);
+
+// FocalLoss(reduction="none"): out[i] = alpha (1-p_t)^gamma BCE_i ; dx[i] = go[i] * d out[i] / d x[i]
+cudaError_t launch_focal_map_forward(const float* x, const float* t, long long n, float alpha, float gamma, float* out,
+                                     cudaStream_t s);
+cudaError_t launch_focal_map_backward(const float* x, const float* t, const float* go, long long n, float alpha,
+                                      float gamma, float* dx, cudaStream_t s);
 
 // ---- threshold / metrics ---------------------------------------------------------------------
 // For each row and threshold k (given as logit-space bounds xs[k], pred = x >= xs[k]):

@@ -188,6 +188,54 @@ cudaError_t launch_loss_backward(const LossArgs& a, cudaStream_t s) {
   return launched();
 }
 
+// ============================================================================ focal loss, reduction = "none"
+// FocalLoss(reduction="none") of src/train_with_focalDice.py:214-219: the unreduced map alpha * (1 - p_t)^gamma * BCE and
+// its gradient against an element-wise grad_out.  Same per-element arithmetic as the fused kernels above.
+__global__ void __launch_bounds__(256) focal_map_forward_kernel(const float* __restrict__ x, const float* __restrict__ t,
+                                                               long long n, float alpha, float gamma,
+                                                               float* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float xv = __ldg(x + i), tv = __ldg(t + i);
+    const float p = sigmoidf_(xv);
+    const float q = (tv == 1.0f) ? 1.0f - p : p;
+    out[i] = alpha * pow_gamma(q, gamma) * bce_logits(xv, tv);
+  }
+}
+__global__ void __launch_bounds__(256) focal_map_backward_kernel(const float* __restrict__ x, const float* __restrict__ t,
+                                                                const float* __restrict__ go, long long n, float alpha,
+                                                                float gamma, float* __restrict__ dx) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float xv = __ldg(x + i), tv = __ldg(t + i);
+    const float p = sigmoidf_(xv);
+    float ge;
+    if (gamma == 0.f) {
+      ge = alpha * (p - tv);
+    } else {
+      const float dp = p * (1.0f - p);
+      const bool pos = tv == 1.0f;
+      const float q = pos ? 1.0f - p : p;
+      const float dq = pos ? -dp : dp;
+      const float qg1 = pow_gamma(q, gamma - 1.0f);
+      ge = alpha * (gamma * qg1 * dq * bce_logits(xv, tv) + qg1 * q * (p - tv));
+    }
+    dx[i] = ge * __ldg(go + i);
+  }
+}
+static int focal_grid(long long n) {
+  long long g = (n + 256 * 4 - 1) / (256 * 4);
+  return (int)(g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g));
+}
+cudaError_t launch_focal_map_forward(const float* x, const float* t, long long n, float alpha, float gamma, float* out,
+                                     cudaStream_t s) {
+  focal_map_forward_kernel<<<focal_grid(n), 256, 0, s>>>(x, t, n, alpha, gamma, out);
+  return launched();
+}
+cudaError_t launch_focal_map_backward(const float* x, const float* t, const float* go, long long n, float alpha,
+                                      float gamma, float* dx, cudaStream_t s) {
+  focal_map_backward_kernel<<<focal_grid(n), 256, 0, s>>>(x, t, go, n, alpha, gamma, dx);
+  return launched();
+}
+
 // ============================================================================ thresholded metrics
 // pred_k = (x >= xs[k]).  The host turns "sigmoid(x) > t" / ">= t" into the exact fp32 bound xs[k]
 // (smallest float whose ATen sigmoid passes the test), so masks are bit-identical to the

@@ -84,6 +84,14 @@ static int nhwc_map_strided(CUtensorMap* m, const bf16* base, int pitch, int B, 
   if (r != 0) return fail("cuTensorMapEncodeTiled (strided NHWC) failed: %d", r);
   return 0;
 }
+static int nhwc_patch_map(CUtensorMap* m, const bf16* base, int pitch, int B, int H, int W, int pw) {
+  const uint64_t dims[4] = {(uint64_t)pitch, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  const uint64_t st[3] = {(uint64_t)pitch * 2, (uint64_t)W * pitch * 2, (uint64_t)H * W * pitch * 2};
+  const uint32_t box[4] = {64, (uint32_t)pw, 18, 1};
+  int r = make_tmap_4d(m, base, dims, st, box);
+  if (r != 0) return fail("cuTensorMapEncodeTiled (NHWC patch %dx%dx%dx%d, pitch %d) failed: %d", B, H, W, pitch, pitch, r);
+  return 0;
+}
 // CTA-pair (cta_group::2) pixel GEMMs are the default; CARTSEG_PAIR=0 selects the single-CTA kernels (debugging).
 static bool use_pair() {
   static const bool v = [] {
@@ -101,6 +109,19 @@ static int weight_map(CUtensorMap* m, const bf16* base, int K, int rows, int blo
 }
 
 static int pick_block_n(int n) { return n % 256 == 0 ? 256 : (n % 128 == 0 ? 128 : 64); }
+
+// 3x3 convolutions through conv3_gemm_kernel (one activation patch per K-chunk for all nine taps).  Developer knobs for
+// A/B runs: CARTSEG_CONV3=0 selects pix_gemm2_kernel, CARTSEG_CONV3_PW=10|16 the patch width, CARTSEG_CONV3_MODE=0|1 the
+// descriptor base-offset convention.
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+static int conv3_enabled() { static const int v = env_int("CARTSEG_CONV3", 0); return v; }
+static int conv3_pw() { static const int v = env_int("CARTSEG_CONV3_PW", 10); return v; }
+static int conv3_mode() { static const int v = env_int("CARTSEG_CONV3_MODE", 0); return v; }
+// TMA map over an NHWC buffer with a (64, pw, 18, 1) box: the whole halo patch of an 8 x 16 pixel tile.
+static int nhwc_patch_map(CUtensorMap* m, const bf16* base, int pitch, int B, int H, int W, int pw);
 
 static void pix_common(PixGemmParams& p, int B, int H, int W, int K, int Ntot, int block_n) {
   memset(&p, 0, sizeof(p));
@@ -130,6 +151,12 @@ static int build_conv3x3(PixGemmParams& p, int* block_n, View in, int K, View ou
   CS_TRY(nhwc_map(&p.tmapA[0], in.p, in.pitch, B, H, W, 18));
   CS_TRY(weight_map(&p.tmapB, wpack, K, 9 * N, *block_n));
   CS_TRY(nhwc_map(&p.tmapO[0], out.p, out.pitch, B, H, W, 16));
+  if (use_pair() && conv3_enabled()) {
+    p.conv3 = 1;
+    p.conv3_pw = conv3_pw();
+    p.conv3_desc_mode = conv3_mode();
+    CS_TRY(nhwc_patch_map(&p.tmapA3, in.p, in.pitch, B, H, W, p.conv3_pw));
+  }
   return 0;
 }
 // Plain [pixels x K] * [K x N] (the im2col'd first conv).
@@ -609,6 +636,8 @@ void cs_unet_plan_destroy(cs_unet_plan* plan) {
 
 size_t cs_unet_plan_workspace_bytes(const cs_unet_plan* plan) { return plan ? plan->ws_bytes : 0; }
 
+static int ensure_streams(cs_unet_plan* pl);
+
 int cs_unet_plan_bind(cs_unet_plan* pl, void* workspace, size_t bytes) {
   if (!pl) return fail("plan is null");
   if (!workspace || bytes < pl->ws_bytes) return fail("workspace too small: %zu < %zu bytes", bytes, pl->ws_bytes);
@@ -617,6 +646,7 @@ int cs_unet_plan_bind(cs_unet_plan* pl, void* workspace, size_t bytes) {
   pl->ws = static_cast<uint8_t*>(workspace);
   layout(pl, pl->ws);
   CS_TRY(encode_maps(pl));
+  if (!pl->infer) CS_TRY(ensure_streams(pl));   // not lazily inside cs_unet_backward: illegal during stream capture
   pl->bound = true;
   pl->forward_done = false;
   return 0;
@@ -625,18 +655,30 @@ int cs_unet_plan_bind(cs_unet_plan* pl, void* workspace, size_t bytes) {
 int cs_unet_pack_weights(cs_unet_plan* pl, const cs_unet_tensors* t, cs_stream_t stream) {
   if (!pl || !pl->bound) return fail("plan is not bound to a workspace");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // one launch for all 22 weight tensors (was 22 launches per call, twice per training step with the unpacks)
+  PackBatch pb;
+  memset(&pb, 0, sizeof(pb));
+  pb.maps[0] = kTapFprop; pb.maps[1] = kTapDgrad; pb.maps[2] = kTapIdent;
   for (int i = 0; i < 18; ++i) {
     const ConvL& c = pl->conv[i];
     if (!t->param[c.pw]) return fail("parameter %d is null", c.pw);
-    if (i == 0) CS_CUDA(launch_pack_first(t->param[c.pw], c.cout, pl->Cin, c.wf, s));
-    else CS_CUDA(launch_pack_pairs(t->param[c.pw], c.cout, c.cin, 9, c.wf, kTapFprop, c.wd, kTapDgrad, s));
+    if (i == 0) {
+      pb.first_in = t->param[c.pw]; pb.first_out = c.wf; pb.first_cout = c.cout; pb.first_cin = pl->Cin;
+    } else {
+      PackJob& j = pb.job[pb.n++];
+      j.in = t->param[c.pw]; j.Na = c.cout; j.Nb = c.cin; j.T = 9;
+      j.out_ab = c.wf; j.map_ab = 0; j.out_ba = c.wd; j.map_ba = 1;
+    }
   }
   for (int k = 0; k < 4; ++k) {
     const UpL& u = pl->up[k];
     if (!t->param[u.pw]) return fail("parameter %d is null", u.pw);
     // IOHW [ci][co][ij]: dgrad pack [ij][ci][co] (a-major), fprop pack [ij][co][ci] (b-major)
-    CS_CUDA(launch_pack_pairs(t->param[u.pw], u.cin, u.cout, 4, u.wd, kTapIdent, u.wf, kTapIdent, s));
+    PackJob& j = pb.job[pb.n++];
+    j.in = t->param[u.pw]; j.Na = u.cin; j.Nb = u.cout; j.T = 4;
+    j.out_ab = u.wd; j.map_ab = 2; j.out_ba = u.wf; j.map_ba = 2;
   }
+  CS_CUDA(launch_pack_batch(pb, s));
   return 0;
 }
 
@@ -787,7 +829,6 @@ int cs_unet_backward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* dl
     if (kind == 0) {
       if (!dlogits) return fail("dlogits is null");
       const ConvL& last = pl->conv[17];
-      if (!t->grad[80] || !t->grad[81]) return fail("gradient buffers of final_conv are null");
       // The head's input gradient dlogits * w is not materialised: the BN backward of the last layer forms it on the
       // fly (BnBwdArgs::head_dlogits).  What is left of the head backward only produces parameter gradients, so it
       // goes to the weight-gradient stream, off the critical path.
@@ -830,7 +871,9 @@ int cs_unet_backward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* dl
         if (idx == 0) CS_CUDA(launch_unpack_first(pl->dwp, c.cout, pl->Cin, t->grad[c.pw], sw));
         else CS_CUDA(launch_unpack_pairs(pl->dwp, c.cout, c.cin, 9, kTapWgrad, t->grad[c.pw], sw));
       }
-      if (idx > 0 && idx > frozen_encoder_convs)
+      // Decoder convs always run their dgrad: it is the only writer of the concat-gradient buffer that the conv-transpose
+      // weight / bias gradients read.  An encoder conv needs it only if something below it still trains.
+      if (idx >= 10 || (idx > 0 && idx > frozen_encoder_convs))
         CS_CUDA(traced(pl, 300 + idx, s, [&] { return timed(pl, pix_class(c.bn_d), c.flops, s, [&] { return launch_pix_gemm(c.dg, c.bn_d, pl->num_sms, s); }); }));
     } else {
       UpL& u = pl->up[idx];
@@ -844,7 +887,9 @@ int cs_unet_backward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* dl
         CS_CUDA(traced(pl, 800 + idx, sw, [&] { return timed(pl, wgrad_class(u.bn_w), u.flops, sw, [&] { return launch_wgrad_gemm(u.wg, u.bn_w, sw); }); }));
         CS_CUDA(launch_unpack_pairs(pl->dwp, u.cin, u.cout, 4, kTapIdent, t->grad[u.pw], sw));
       }
-      CS_CUDA(traced(pl, 700 + idx, s, [&] { return timed(pl, pix_class(u.bn_d), u.flops, s, [&] { return launch_pix_gemm(u.dg, u.bn_d, pl->num_sms, s); }); }));
+      // upconv4's input gradient only feeds conv5.3: nothing reads it when the whole encoder is frozen
+      if (!(idx == 0 && frozen_encoder_convs >= 10))
+        CS_CUDA(traced(pl, 700 + idx, s, [&] { return timed(pl, pix_class(u.bn_d), u.flops, s, [&] { return launch_pix_gemm(u.dg, u.bn_d, pl->num_sms, s); }); }));
     }
   }
   if (overlap) {                                          // join: the caller's stream continues after both
@@ -1028,6 +1073,22 @@ int cs_loss_backward(const cs_loss_desc* d, const float* logits, const float* ta
   a.logits = logits; a.targets = targets; a.sdf_gt = sdf_gt; a.sdf_pred = sdf_pred;
   a.stats = const_cast<double*>(static_cast<const double*>(scratch)); a.grad_out = grad_out; a.dlogits = dlogits;
   CS_CUDA(launch_loss_backward(a, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int cs_focal_map_forward(const float* logits, const float* targets, long long n, float alpha, float gamma, float* out,
+                         cs_stream_t stream) {
+  if (!logits || !targets || !out) return fail("cs_focal_map_forward: null pointer");
+  if (n < 1) return fail("cs_focal_map_forward: empty input");
+  CS_CUDA(launch_focal_map_forward(logits, targets, n, alpha, gamma, out, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int cs_focal_map_backward(const float* logits, const float* targets, const float* grad_out, long long n, float alpha,
+                          float gamma, float* dlogits, cs_stream_t stream) {
+  if (!logits || !targets || !grad_out || !dlogits) return fail("cs_focal_map_backward: null pointer");
+  if (n < 1) return fail("cs_focal_map_backward: empty input");
+  CS_CUDA(launch_focal_map_backward(logits, targets, grad_out, n, alpha, gamma, dlogits, static_cast<cudaStream_t>(stream)));
   return 0;
 }
 

@@ -11,7 +11,10 @@
  * Conventions
  *   - every pointer is a DEVICE pointer on the current CUDA device unless stated otherwise;
  *   - the caller owns every buffer (including workspaces, sized by the *_bytes queries);
- *   - nothing here allocates device memory, frees it, or synchronises; all work goes to `stream`;
+ *   - nothing here allocates device memory, frees it, or synchronises; all work goes to `stream` — so every call can
+ *     be captured in a CUDA graph (cs_unet_plan_bind creates the two internal backward streams and their events).
+ *     The only exceptions are developer / test hooks that hand results to the HOST and say so:
+ *     cs_unet_profile_read, cs_unet_trace_read (wait for their timing events), cs_abl_debug_read (synchronises);
  *   - return value 0 = success, negative = failure; cs_last_error() gives a thread-local message;
  *   - image tensors are fp32 NCHW exactly as the reference's DataLoader yields them; logits,
  *     targets, SDFs and dlogits are fp32 [B,1,H,W]; H and W must be multiples of 16.
@@ -76,8 +79,10 @@ int cs_unet_forward(cs_unet_plan* plan, const cs_unet_tensors* t, const float* x
 /* Backward of the last training forward.  Stages [stage_begin, stage_end) in reverse execution
  * order; gradients of the parameters owned by those stages are final when the call's work
  * completes, so a data-parallel caller can all-reduce them while later stages run.
- * need_input_grads_from: index of the first encoder conv (0..9) whose parameters need gradients —
- * 0 trains everything, 10 freezes the whole encoder (src/train_with_focalDice.py:384-391). */
+ * frozen_encoder_convs: number of leading encoder convs (conv1.0, conv1.3, conv2.0, ...) whose parameters need no
+ * gradient — 0 trains everything, 10 freezes the whole encoder (src/train_with_focalDice.py:384-391): their backward
+ * stages are skipped altogether.  Any other parameter whose grad[] entry is NULL just loses its own gradient kernel
+ * (weight-gradient GEMM / bias sum); gradients still flow through the layer. */
 int cs_unet_backward(cs_unet_plan* plan, const cs_unet_tensors* t, const float* dlogits, int stage_begin,
                      int stage_end, int frozen_encoder_convs, cs_stream_t stream);
 /* Per-launch timing of the tensor-core kernels (bench.py's roofline): while enabled, every implicit-GEMM launch of
@@ -152,6 +157,13 @@ int cs_loss_forward(const cs_loss_desc* d, const float* logits, const float* tar
 int cs_loss_backward(const cs_loss_desc* d, const float* logits, const float* targets, const float* sdf_gt,
                      const float* sdf_pred, const void* scratch, const float* grad_out, float* dlogits,
                      cs_stream_t stream);
+
+/* FocalLoss(reduction="none") (src/train_with_focalDice.py:214-219): the unreduced map
+ * out[i] = alpha * (1 - p_t)^gamma * BCE(logits[i], targets[i]), and its backward against an element-wise grad_out. */
+int cs_focal_map_forward(const float* logits, const float* targets, long long n, float alpha, float gamma, float* out,
+                         cs_stream_t stream);
+int cs_focal_map_backward(const float* logits, const float* targets, const float* grad_out, long long n, float alpha,
+                          float gamma, float* dlogits, cs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Thresholding / metrics (replaces dice_metric, iou_metric, find_best_threshold

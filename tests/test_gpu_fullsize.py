@@ -96,3 +96,38 @@ def test_train_step_full_k2_properties():
         assert rel_l2(g2[k], g1[k]) < 1e-4, k                             # fp32 atomic ordering only
         assert rel_l2(g3[k] / 65536.0, g1[k]) < 1e-4, k                   # exact linearity in the loss scale
         assert torch.isfinite(g3[k]).all(), k
+
+
+def test_train_step_full_k2_teacher_forced_stages_and_loss():
+    """Train-mode parity AT the benchmarked size (K2: B=64 @224^2, focal-Dice) — where the weight-gradient split-K
+    (K = 3.2 M pixels) and the fp64 BN-statistics atomics operate.  Loss vs the oracle on the GPU's logits; then the
+    full-resolution blocks conv1.* / dconv1.* and the bottleneck conv5.* stage by stage ("teacher-forced": each kernel's
+    output against torch-CPU fp32 applied to the tensors the GPU path actually produced, read back through
+    cs_unet_debug_read): conv fprop, BN statistics + ReLU (+pool), BN backward, BN parameter gradients, wgrad, dgrad;
+    the conv-transposes feeding dconv1 / leaving conv5, and the head.  Bars as in test_gpu_unet_stages.py
+    (4e-3 bf16 tensors, 3e-3 fp32 parameter gradients; the north-star bar is 3e-2).  ~1 min of CPU on 16 cores."""
+    import cartseg
+    from cartseg import ops
+    from oracle import unet_oracle as O
+    import test_gpu_unet_stages as S
+    B, H = 64, 224
+    x, tgt = O.synth_batch(B, H, H, seed=5)
+    torch.manual_seed(0)
+    m = cartseg.UNet()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m = m.cuda().train()
+    crit = cartseg.FocalDiceLoss(0.5, 2.0, 1.0, 0.7)
+    z, loss = S._run(m, crit, x, tgt)
+    ref_loss = O.focal_dice_loss(z.detach().cpu(), tgt, 0.5, 2.0, 1.0, 0.7).item()
+    assert abs(loss.item() - ref_loss) / ref_loss < 1e-5
+    plan = ops.get_plan(B, 3, H, H, torch.device("cuda"), inference_only=False)
+    snap = S._LazySnapshot(plan)
+    grads = {k: p.grad.detach().cpu() for k, p in m.named_parameters()}
+    rows = S.check_stages(snap, sd, x, z.detach().cpu(), z.grad.detach().cpu(), grads,
+                          conv_ids=(0, 1, 8, 9, 16, 17), up_ids=(0, 3), head=True)
+    worst = sorted(rows, key=lambda r: -r[1] / r[2])[:8]
+    print(f"\n[K2 B{B} {H}x{H}] {len(rows)} stage checks; worst (rel-L2 / tolerance):")
+    for n, e, tol in worst:
+        print(f"   {n:40s} {e:.3e} / {tol:g}")
+    bad = [(n, f"{e:.3e}", tol) for n, e, tol in rows if not e < tol]
+    assert not bad, bad

@@ -129,3 +129,77 @@ def test_torch_compile_of_the_model_matches_eager():
         compiled = torch.compile(model)
         got = compiled(x.cuda())
     assert torch.equal(got, ref)
+
+
+def test_cuda_graph_capture_of_a_training_step_replays_identically():
+    """nothing in the path synchronises or allocates behind the caller's back, so forward + loss +
+    backward (incl. the two internal backward streams, forked / joined with events made at plan-bind time) capture into
+    ONE CUDA graph.  The replay must reproduce the eager step: logits / loss / activation-gradient chain bit for bit,
+    weight gradients up to the fp32 atomic ordering of the split-K accumulation; and it must follow new inputs and
+    new weights (the bf16 re-pack is part of the graph)."""
+    import cartseg
+    from oracle import unet_oracle as O
+    torch.manual_seed(4)
+    model = cartseg.UNet().cuda().train()
+    crit = cartseg.CompositeSegLoss(bce_weight=0.5, boundary_weight=0.3)      # exercises the EDT + fused loss too
+    (x0, t0), (x1, t1) = _loader(2, 4, 64, seed=20)
+    x0, t0, x1, t1 = x0.cuda(), t0.cuda(), x1.cuda(), t1.cuda()
+
+    def eager(x, t):
+        model.zero_grad(set_to_none=True)
+        z = model(x)
+        loss = crit(z, t)
+        loss.backward()
+        torch.cuda.synchronize()
+        return z.detach().clone(), loss.detach().clone(), {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+
+    step = cartseg.GraphedTrainStep(model, crit, x0, t0)
+    n0 = cartseg.lib().cs_kernel_launch_count()
+    for (x, t) in ((x0, t0), (x1, t1), (x0, t0)):
+        loss_g = step(x, t).clone()
+        torch.cuda.synchronize()
+        g_graph = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+        z_e, loss_e, g_e = eager(x, t)
+        assert torch.equal(loss_g, loss_e), (float(loss_g), float(loss_e))
+        for k in g_e:
+            d = (g_graph[k] - g_e[k]).norm() / g_e[k].norm().clamp_min(1e-30)
+            assert float(d) < 1e-4, (k, float(d))
+        step.restore_grads()           # eager() replaced the parameters' .grad tensors: point them at the graph's again
+    # weights change between replays: the graph re-packs them
+    with torch.no_grad():
+        for p in model.parameters():
+            p.mul_(0.9)
+    loss_g = step(x1, t1).clone()
+    _, loss_e, _ = eager(x1, t1)
+    assert torch.equal(loss_g, loss_e)
+    assert cartseg.lib().cs_kernel_launch_count() > n0
+
+
+def test_cuda_graph_inference_matches_eager_and_is_one_launch():
+    import cartseg
+    from oracle import unet_oracle as O
+    torch.manual_seed(5)
+    model = cartseg.UNet().cuda().eval()
+    x, _ = O.synth_batch(1, 224, 224, seed=2)
+    xg = x.cuda()
+    with torch.no_grad():
+        ref_mask = cartseg.pseudo_label_mask(model(xg), 0.5)
+        ref_logits = model(xg).clone()
+    g_mask = cartseg.GraphedInference(model, xg, threshold=0.5)
+    g_logits = cartseg.GraphedInference(model, xg)
+    assert torch.equal(g_mask(xg).reshape(ref_mask.shape), ref_mask)
+    assert torch.equal(g_logits(xg), ref_logits)
+    x2, _ = O.synth_batch(1, 224, 224, seed=3)
+    with torch.no_grad():
+        assert torch.equal(g_logits(x2.cuda()), model(x2.cuda()))
+    # parameter edits between replays are seen (the re-pack is inside the graph) ...
+    with torch.no_grad():
+        for p in model.parameters():
+            p.data.mul_(0.5)
+        assert torch.equal(g_logits(xg), model(xg))
+    # ... unless the packs were frozen before capture (lowest latency)
+    model.freeze_packed()
+    g_frozen = cartseg.GraphedInference(model, xg)
+    with torch.no_grad():
+        a = g_frozen(xg).clone()
+        assert torch.equal(a, model(xg))

@@ -151,3 +151,24 @@ def test_losses_reject_cpu_tensors():
     import cartseg as cs
     with pytest.raises(Exception):
         cs.BCEDiceLoss()(torch.zeros(1, 1, 16, 16), torch.zeros(1, 1, 16, 16))
+
+
+def test_focal_loss_reduction_none_vs_oracle():
+    """FocalLoss(reduction="none") (src/train_with_focalDice.py:214-219): unreduced map and its gradient against an
+    arbitrary element-wise upstream gradient, vs the oracle (fp32 both sides: 2e-5 / 1e-4 of scale)."""
+    import cartseg
+    from oracle import unet_oracle as O
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(3, 1, 40, 36, generator=g) * 3).requires_grad_(True)
+    t = (torch.rand(3, 1, 40, 36, generator=g) > 0.6).float()
+    up = torch.randn(3, 1, 40, 36, generator=g)
+    for alpha, gamma in ((0.25, 2.0), (0.6, 1.5), (1.0, 0.0)):
+        ref = O.focal_loss(x, t, alpha, gamma, reduction="none")
+        x.grad = None
+        (ref * up).sum().backward()
+        xg = x.detach().cuda().requires_grad_(True)
+        out = cartseg.FocalLoss(alpha=alpha, gamma=gamma, reduction="none")(xg, t.cuda())
+        assert out.shape == ref.shape
+        (out * up.cuda()).sum().backward()
+        assert (out.detach().cpu() - ref.detach()).abs().max() <= 2e-5 * ref.detach().abs().max() + 1e-7
+        assert (xg.grad.cpu() - x.grad).abs().max() <= 1e-4 * x.grad.abs().max()

@@ -134,8 +134,31 @@ def test_train_step_vs_oracle(B, H, W, loss):
     err_oo, cos_oo = _global_grad_agreement(g_emu, g_ref)
     print(f"whole-gradient rel-L2 / cosine: GPU vs fp32 oracle {err_f:.3f} / {cos_f:.4f}; GPU vs bf16-emulating oracle "
           f"{err_e:.3f} / {cos_e:.4f}; bf16-emulating vs fp32 oracle (CPU only) {err_oo:.3f} / {cos_oo:.4f}")
-    assert cos_f > 0.9 and cos_e > 0.9
-    assert err_f < 1.5 * err_oo + 0.05          # no worse than what bf16 storage alone does to the oracle
+    # The bars DESIGN.md §1 states.  Measured on B200 at these worst-conditioned sizes (B <= 4, noise images, default
+    # init): cosine 0.9715 / 0.9906 / 0.9937 vs fp32 and 0.9902 / 0.9966 / 0.9979 vs the bf16-emulating oracle; the
+    # bars sit half a percent under the worst case because every change of summation order re-rolls the mask flips.
+    assert cos_f >= 0.965 and cos_e >= 0.985, (cos_f, cos_e)
+    assert err_f <= 1.1 * err_oo + 0.01, (err_f, err_oo)   # no worse than what bf16 storage alone does to the oracle
+    # per tensor, so that one wrong tensor cannot hide in the global norm: the head and the last decoder block meet the
+    # north-star 3e-2 against the bf16-emulating oracle; every other tensor stays within what the oracle's own bf16
+    # emulation loses against its fp32 run on that tensor (x2 + 5e-2: two roundings per stored tensor on the GPU path
+    # — y and the activation — where the emulation has the same two; mask flips differ per realisation)
+    worst = []
+    for k in g_ref:
+        if k.endswith(".conv.0.bias") or k.endswith(".conv.3.bias"):
+            assert g_gpu[k].abs().max().item() == 0.0, k          # exactly zero: BN removes the conv bias
+            continue
+        e_emu, e_oo = rel_l2(g_gpu[k], g_emu[k]), rel_l2(g_emu[k], g_ref[k])
+        c = float(torch.dot(g_gpu[k].double().flatten(), g_emu[k].double().flatten())
+                  / (g_gpu[k].double().norm() * g_emu[k].double().norm()).clamp_min(1e-300))
+        worst.append((e_emu, e_oo, c, k))
+        if k.startswith("final_conv."):
+            assert e_emu < GRAD_TOL, (k, e_emu)
+        assert e_emu <= 2.0 * e_oo + 5e-2, (k, e_emu, e_oo)
+        assert c >= 0.9, (k, c)
+    worst.sort(reverse=True)
+    print("per-tensor worst (rel-L2 GPU vs emu, emu vs fp32, cosine):",
+          [(k, f"{a:.3f}", f"{b:.3f}", f"{c:.4f}") for a, b, c, k in worst[:5]])
     # BN running statistics were updated in place (momentum 0.1, unbiased variance)
     bufs = dict(m.named_buffers())
     for k, v in sd_after.items():
@@ -170,8 +193,16 @@ def test_frozen_encoder_and_param_groups():
     x, tgt = O.synth_batch(2, 96, 96, seed=7)
     sd = _torch_init_state_dict(2)
     crit = cartseg.FocalDiceLoss(0.5, 2.0, 1.0, 0.7)
+    from cartseg import ops
     full = _model(sd).train()
     crit(full(x.cuda()), tgt.cuda()).backward()
+    torch.cuda.synchronize()
+    # Fresh plan with a POISONED workspace: a gradient buffer the frozen run forgets to write must not be rescued by
+    # what the unfrozen run left behind (round 1 skipped dconv4.0's dgrad when the whole encoder was frozen — the only
+    # writer of the buffer upconv4's weight gradient reads).
+    ops.release_plans()
+    plan = ops.get_plan(2, 3, 96, 96, torch.device("cuda"), inference_only=False)
+    plan.workspace.view(torch.int16).fill_(0x7FC0)            # bf16 NaN everywhere (fp32: NaN too)
     frozen = _model(sd).train()
     for p in frozen.encoder.parameters():
         p.requires_grad = False
@@ -183,7 +214,19 @@ def test_frozen_encoder_and_param_groups():
             assert p.grad is None
         else:
             assert rel_l2(p.grad, fp[k].grad) < 1e-4, k
+    # the same frozen step against the oracle (frozen from step 0, nothing warm): decoder + head gradients
+    z_ref, loss_ref, g_ref, _ = _oracle_train(O, x, tgt, sd, lambda z, t: O.focal_dice_loss(z, t, 0.5, 2.0, 1.0, 0.7),
+                                              emulate_bf16=True)
+    for k, p in frozen.named_parameters():
+        if id(p) not in enc and not (k.endswith(".conv.0.bias") or k.endswith(".conv.3.bias")):
+            assert torch.isfinite(p.grad).all(), k
+            c = float(torch.dot(p.grad.cpu().double().flatten(), g_ref[k].double().flatten())
+                      / (p.grad.double().norm().cpu() * g_ref[k].double().norm()))
+            assert c > 0.95, (k, c)
     # half-frozen: conv1..conv3 frozen, gradients of everything above unchanged
+    ops.release_plans()
+    plan = ops.get_plan(2, 3, 96, 96, torch.device("cuda"), inference_only=False)
+    plan.workspace.view(torch.int16).fill_(0x7FC0)
     half = _model(sd).train()
     for mod in (half.conv1, half.conv2, half.conv3):
         for p in mod.parameters():
@@ -191,6 +234,49 @@ def test_frozen_encoder_and_param_groups():
     crit(half(x.cuda()), tgt.cuda()).backward()
     for k, p in half.named_parameters():
         if k.startswith(("conv1.", "conv2.", "conv3.")):
+            assert p.grad is None
+        else:
+            assert rel_l2(p.grad, fp[k].grad) < 1e-4, k
+    # non-prefix freezing (decoder frozen, encoder + head trainable): the frozen tensors get no gradient and no
+    # weight-gradient GEMM, everything else is unchanged
+    ops.release_plans()
+    plan = ops.get_plan(2, 3, 96, 96, torch.device("cuda"), inference_only=False)
+    plan.workspace.view(torch.int16).fill_(0x7FC0)
+    dec = _model(sd).train()
+    for p in dec.decoder.parameters():
+        p.requires_grad = False
+    n0 = cartseg.lib().cs_kernel_launch_count()
+    crit(dec(x.cuda()), tgt.cuda()).backward()
+    torch.cuda.synchronize()
+    n_dec = cartseg.lib().cs_kernel_launch_count() - n0
+    frozen_ids = {id(p) for p in dec.decoder.parameters()}
+    for k, p in dec.named_parameters():
+        if id(p) in frozen_ids:
+            assert p.grad is None
+        else:
+            assert rel_l2(p.grad, fp[k].grad) < 1e-4, k
+    n0 = cartseg.lib().cs_kernel_launch_count()
+    full.zero_grad(set_to_none=True)
+    crit(full(x.cuda()), tgt.cuda()).backward()
+    torch.cuda.synchronize()
+    assert n_dec < cartseg.lib().cs_kernel_launch_count() - n0       # 12 wgrad GEMMs (+ unpacks) were not launched
+
+
+def test_frozen_head_only():
+    """segmentation_head frozen (final_conv.weight / bias without gradients): everything else unchanged."""
+    import cartseg
+    from oracle import unet_oracle as O
+    x, tgt = O.synth_batch(2, 64, 64, seed=8)
+    sd = _torch_init_state_dict(4)
+    crit = cartseg.BCEDiceLoss()
+    full = _model(sd).train()
+    crit(full(x.cuda()), tgt.cuda()).backward()
+    fp = dict(full.named_parameters())
+    m = _model(sd).train()
+    m.segmentation_head.requires_grad_(False)
+    crit(m(x.cuda()), tgt.cuda()).backward()
+    for k, p in m.named_parameters():
+        if k.startswith("final_conv."):
             assert p.grad is None
         else:
             assert rel_l2(p.grad, fp[k].grad) < 1e-4, k
@@ -231,7 +317,7 @@ def test_weight_tied_multi_step_drift():
     upd_ref = {k: sd[k].detach() - sd0[k] for k in keys}
     err, cos = _global_grad_agreement(upd_gpu, upd_ref)
     print(f"accumulated update after 4 steps: rel-L2 {err:.3f}, cosine {cos:.4f}")
-    assert cos > 0.9
+    assert cos >= 0.99                                    # measured 0.998
 
 
 def test_fused_optimizer_updates_reach_the_kernels():
@@ -262,6 +348,68 @@ def test_fused_optimizer_updates_reach_the_kernels():
         ref = O.unet_logits(x, sd, training=False)
     assert rel_l2(after.cpu(), ref) < 2e-2                        # eval uses the UPDATED weights
     assert rel_l2(after, before) > 0.05
+
+
+def test_eval_packs_follow_data_updates_and_model_recreation():
+    """(1) in-place updates through ``p.data`` (EMA / SWA / checkpoint averaging) do not bump version
+    counters, and such a model never runs a training forward; (2) a model rebuilt in a loop can land on the freed
+    model's addresses with identical versions.  Eval-mode forwards must see the current weights in both cases."""
+    import cartseg
+    from oracle import unet_oracle as O
+    x, _ = O.synth_batch(1, 32, 32, seed=3)
+    xg = x.cuda()
+    m = _model(O.synth_state_dict(seed=1)).eval()
+    with torch.no_grad():
+        a = m(xg).clone()
+        for p in m.parameters():
+            p.data.mul_(0.5)                              # version counters unchanged
+        b = m(xg).clone()
+        sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+        ref = O.unet_logits(x, sd, training=False)
+    assert rel_l2(b.cpu(), ref) < 2e-2 and rel_l2(b, a) > 0.05
+    # opt-in: packs frozen -> the same .data edit is (by contract) NOT seen until freeze_packed is called again
+    m.freeze_packed()
+    with torch.no_grad():
+        c0 = m(xg).clone()
+        for p in m.parameters():
+            p.data.mul_(2.0)
+        c1 = m(xg).clone()
+        assert torch.equal(c0, c1)
+        m.freeze_packed()
+        c2 = m(xg).clone()
+    assert rel_l2(c2, a) < 1e-3
+    # checkpoint loop: same addresses, same versions, different weights
+    outs = []
+    for seed in (1, 2, 3):
+        mm = _model(O.synth_state_dict(seed=seed)).eval()
+        with torch.no_grad():
+            outs.append(mm(xg).clone())
+        ref = O.unet_logits(x, O.synth_state_dict(seed=seed), training=False)
+        assert rel_l2(outs[-1].cpu(), ref) < 2e-2, seed
+        del mm
+    assert rel_l2(outs[1], outs[0]) > 1e-3 and rel_l2(outs[2], outs[1]) > 1e-3
+
+
+def test_per_group_bn_mode_and_eval_backward_raise_clearly():
+    import cartseg
+    from cartseg import CartsegError
+    from oracle import unet_oracle as O
+    x, _ = O.synth_batch(1, 32, 32, seed=1)
+    m = _model(O.synth_state_dict(seed=1)).train()
+    m.encoder.eval()                                       # the usual way to freeze BN statistics: unsupported, loud
+    with pytest.raises(CartsegError, match="single BatchNorm mode"):
+        m(x.cuda())
+    m.train()
+    m(x.cuda())
+    m.eval()
+    z = m(x.cuda())                                        # grad mode on, eval mode
+    with pytest.raises(CartsegError, match="eval-mode forward"):
+        z.sum().backward()
+    # dtype / device conversions after a forward are re-validated on every call
+    m.half()
+    with pytest.raises(CartsegError, match="float32"):
+        with torch.no_grad():
+            m(x.cuda())
 
 
 def test_backward_after_overwritten_forward_raises():

@@ -6,7 +6,11 @@ any collective — rank 0 recomputes every shard on its own GPU, one after the o
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/dp_parity.py
 
 BatchNorm statistics are per shard on both sides (DDP semantics; the reference has no SyncBN), so the comparison is
-exact up to the fp32 atomics of the split-K weight-gradient accumulation (~1e-6 relative).  Prints one JSON line."""
+exact up to the fp32 atomics of the split-K weight-gradient accumulation (~1e-6 relative).  Prints one JSON line.
+
+DP_PARITY_BACKEND=gloo runs the same check with every rank on GPU (LOCAL_RANK mod device_count): on a single-GPU box two
+ranks share GPU 0 (NCCL refuses two ranks per device; gloo stages CUDA tensors through the host), so the staged backward,
+the stage-ordered flat gradient buffer, the bucket slicing and the side-stream joins are exercised without a second GPU."""
 import json
 import os
 import sys
@@ -23,9 +27,14 @@ from bench import synth_batch                   # noqa: E402
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    backend = os.environ.get("DP_PARITY_BACKEND", "nccl")
+    local = local % torch.cuda.device_count()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    if backend == "nccl":
+        dist.init_process_group("nccl", device_id=dev)
+    else:
+        dist.init_process_group(backend)
     B, S = int(os.environ.get("DP_PARITY_BATCH", "8")), int(os.environ.get("DP_PARITY_SIZE", "96"))
     x, t = synth_batch(B * world, S, S, seed=3)                     # the global batch, identical on every rank
     torch.manual_seed(1)
@@ -40,7 +49,8 @@ def main():
     torch.cuda.synchronize()
     dp_grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
     loss_mean = loss.detach().clone()
-    dist.all_reduce(loss_mean, op=dist.ReduceOp.AVG)
+    dist.all_reduce(loss_mean, op=dist.ReduceOp.SUM)
+    loss_mean /= world
 
     # every rank must hold the same averaged gradients
     worst_spread = 0.0
@@ -72,7 +82,7 @@ def main():
             den += float(ref.double().pow(2).sum())
             if e > worst:
                 worst, worst_key = e, k
-        out = {"check": "dp_parity", "world": world, "per_gpu_batch": B, "size": S,
+        out = {"check": "dp_parity", "world": world, "backend": backend, "gpus": torch.cuda.device_count(), "per_gpu_batch": B, "size": S,
                "loss_dp_mean": float(loss_mean), "loss_shard_mean": sum(losses) / world,
                "grad_rel_l2_whole": (num / max(den, 1e-300)) ** 0.5, "grad_rel_l2_worst_tensor": worst,
                "worst_tensor": worst_key, "max_abs_spread_between_ranks": worst_spread}
