@@ -62,7 +62,7 @@ def synth_batch(B: int, H: int, W: int, seed: int = 0, in_channels: int = 3):
 def step_traffic(kernel_label: str):
     """DRAM bytes per launch of a kernel class from the committed ncu pass over one k2 step (profiles/, written by
     tools/step_traffic.py); None when no capture is committed."""
-    path = os.path.join(ROOT, "profiles", "r1_step_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r2_step_traffic.json")
     if not os.path.exists(path):
         return None, None
     data = json.load(open(path))
@@ -391,7 +391,7 @@ def run_ours(args, wl):
     # ---- per-kernel roofline pass: the same steps again, weight-gradient overlap off so that every tensor-core
     # launch runs alone between its two CUDA events (in the timed region above the wgrad GEMMs share the GPU with
     # the BN-backward passes and dgrads, which is what makes the step faster but their own durations meaningless)
-    NC = 5
+    NC = 8
     k_ms, k_fl, k_n = (C.c_double * NC)(), (C.c_double * NC)(), (C.c_longlong * NC)()
     L.cs_unet_set_overlap(plan.handle, 0)
     step(x_d, t_d)
@@ -406,11 +406,13 @@ def run_ours(args, wl):
     L.cs_unet_profile_read(plan.handle, NC, k_ms, k_fl, k_n)
     L.cs_unet_profile(plan.handle, 0)
     L.cs_unet_set_overlap(plan.handle, 1)
-    k_names = ["pix_gemm2_kernel<256> (conv/convT fprop+dgrad, Cout-side 256)", "pix_gemm2_kernel<128>",
-               "pix_gemm2_kernel<64>", "wgrad_gemm_kernel<128>", "wgrad_gemm_kernel<64>"]
+    k_names = ["pix_gemm2_kernel<256> (conv-transpose fprop+dgrad)", "pix_gemm2_kernel<128>",
+               "pix_gemm2_kernel<64> (stem)", "wgrad_gemm_kernel<128>", "wgrad_gemm_kernel<64>",
+               "conv3_gemm_kernel<256> (3x3 conv fprop+dgrad, N-side 256)", "conv3_gemm_kernel<128>",
+               "conv3_gemm_kernel<64> (weights resident in shared memory)"]
     kernels = [{"kernel": k_names[i], "launches_per_step": k_n[i] / args.steps, "ms_per_step": k_ms[i] / args.steps,
                 "avg_launch_us": 1e3 * k_ms[i] / max(1, k_n[i]), "tflops": k_fl[i] / max(1e-9, k_ms[i]) / 1e9}
-               for i in range(NC)]
+               for i in range(NC) if k_n[i] > 0]
     last_loss = float(loss.item())
 
     # ---- end to end: pinned host inputs -> H2D -> step -> loss read back, every step ----------

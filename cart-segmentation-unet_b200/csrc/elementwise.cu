@@ -289,7 +289,7 @@ cudaError_t launch_bn_fold_eval(const BnFoldBatch& a, cudaStream_t s) {
 
 // ============================================================================ BN apply + ReLU (+ 2x2 max-pool)
 template <bool POOL>
-__global__ void __launch_bounds__(256, 3) bn_relu_kernel(const bf16* __restrict__ y, int B, int H, int W, int C, const BnFinalizeArgs fin,
+__global__ void __launch_bounds__(256, 4) bn_relu_kernel(const bf16* __restrict__ y, int B, int H, int W, int C, const BnFinalizeArgs fin,
                                bf16* __restrict__ out, int out_pitch, int out_c0, bf16* __restrict__ pooled,
                                const HeadFwd head) {
   // Fused statistics -> affine step (was a kernel of its own between the convolution and this pass): every block
@@ -392,8 +392,8 @@ cudaError_t launch_bn_relu(const bf16* y, int B, int H, int W, int C, const BnFi
     bn_relu_kernel<true><<<grid_for((long long)B * (H / 2) * (W / 2) * (C / 8), 256), 256, smem, s>>>(
         y, B, H, W, C, fin, out, out_pitch, out_c0, pooled, head);
   } else {
-    // three resident blocks per SM (launch bounds), two full waves
-    bn_relu_kernel<false><<<grid_for((long long)B * H * W * (C / 8), 256 * 4, 148 * 6), 256, smem, s>>>(y, B, H, W, C, fin, out,
+    // four resident blocks per SM (launch bounds; 64 KB of loads in flight per SM), two full waves
+    bn_relu_kernel<false><<<grid_for((long long)B * H * W * (C / 8), 256 * 4, 148 * 8), 256, smem, s>>>(y, B, H, W, C, fin, out,
                                                                                             out_pitch, out_c0, pooled, head);
   }
   return launched();
@@ -450,26 +450,31 @@ CS_DEVINL void load_coef(const BnBwdArgs& a, int g, BnCoef& k) {
 }
 // Non-pooled layers, split into a load phase and a compute phase so that a thread can have several units' loads in
 // flight before the first use (the kernels run at two blocks per SM: memory parallelism has to come from the thread).
-struct PlainUnit { Vec8 y, g; };
-CS_DEVINL void plain_load(const BnBwdArgs& a, const BnCoef& k, int g, long long pix, PlainUnit& u) {
+// HEAD: the layer feeds the 1x1 head — its activation gradient dlogits[p] * w[c] (rounded to bf16, as a stand-alone head
+// backward would store it) is formed here instead of being written to and read back from HBM twice.  Such a unit holds
+// 20 bytes of loads instead of 32, so the HEAD instantiations keep more units in flight (memory parallelism comes from
+// the thread: ncu showed the U = 3 head variant at 2.8 TB/s where the two-tensor variant reaches 5.7 TB/s).
+template <bool HEAD> struct PlainUnit { Vec8 y, g; };
+template <> struct PlainUnit<true> { Vec8 y; float dl; };
+template <bool HEAD>
+CS_DEVINL void plain_load(const BnBwdArgs& a, int g, long long pix, PlainUnit<HEAD>& u) {
   u.y = ld8_nc(a.y + pix * a.C + g * 8);
-  if (a.head_dlogits) {
-    // the layer feeds the 1x1 head: its activation gradient dlogits[p] * w[c] (rounded to bf16, as the stand-alone
-    // head backward used to store it) is formed here instead of being written to and read back from HBM twice
-    const float dl = __ldg(a.head_dlogits + pix);
-    float o[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = dl * k.hw[j];
-    u.g = pack8(o);
-  } else {
-    u.g = ld8_nc(a.g + pix * a.g_pitch + a.g_c0 + g * 8);
-  }
+  if constexpr (HEAD) u.dl = __ldg(a.head_dlogits + pix);
+  else u.g = ld8_nc(a.g + pix * a.g_pitch + a.g_c0 + g * 8);
 }
 // gm[j] = g[j] where the stored (bf16-rounded) activation is positive, else 0;  xh[j] = (y - mean) * invstd
-CS_DEVINL void plain_compute(const BnCoef& k, const PlainUnit& u, float gm[8], float xh[8]) {
+template <bool HEAD>
+CS_DEVINL void plain_compute(const BnCoef& k, const PlainUnit<HEAD>& u, float gm[8], float xh[8]) {
   float yv[8], t[8], act[8];
   unpack8(u.y, yv);
-  unpack8(u.g, gm);
+  if constexpr (HEAD) {
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = u.dl * k.hw[j];
+    unpack8(pack8(o), gm);
+  } else {
+    unpack8(u.g, gm);
+  }
 #pragma unroll
   for (int j = 0; j < 8; ++j) t[j] = fmaxf(fmaf(yv[j], k.sc[j], k.sh[j]), 0.f);
   unpack8(pack8(t), act);
@@ -545,7 +550,7 @@ static int bn_bwd_grid(const BnBwdArgs& a) {
   return grid_for(units, rpb * 2, 148 * 2);
 }
 
-template <bool POOL, int U_, int REGS>
+template <bool POOL, bool HEAD, int U_, int REGS>
 __global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(REGS) bn_bwd_reduce_kernel(BnBwdArgs a) {
   const int cg = a.C >> 3;
   const int g = threadIdx.x % cg, ri = threadIdx.x / cg, rpb = kBnBwdThreads / cg;
@@ -564,15 +569,15 @@ __global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(REGS) bn_bwd_reduce
     constexpr int U = U_;
     const long long stride = (long long)gridDim.x * rpb;
     for (long long u0 = (long long)blockIdx.x * rpb + ri; u0 < units; u0 += U * stride) {
-      PlainUnit pu[U];
+      PlainUnit<HEAD> pu[U];
 #pragma unroll
       for (int i = 0; i < U; ++i)
-        if (u0 + i * stride < units) plain_load(a, k, g, u0 + i * stride, pu[i]);
+        if (u0 + i * stride < units) plain_load<HEAD>(a, g, u0 + i * stride, pu[i]);
 #pragma unroll
       for (int i = 0; i < U; ++i) {
         if (u0 + i * stride >= units) break;
         float gm[8], xh[8];
-        plain_compute(k, pu[i], gm, xh);
+        plain_compute<HEAD>(k, pu[i], gm, xh);
 #pragma unroll
         for (int j = 0; j < 8; ++j) { s1[j] += gm[j]; s2[j] = fmaf(gm[j], xh[j], s2[j]); }
       }
@@ -649,15 +654,21 @@ cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t s) {
   const int cg = a.C / 8;
   if (cg > kBnBwdThreads || kBnBwdThreads % cg) return cudaErrorInvalidValue;
   const int grid = bn_bwd_grid(a);
-  if (a.g_pool) bn_bwd_reduce_kernel<true, 1, 128><<<grid, kBnBwdThreads, 0, s>>>(a);
-  else bn_bwd_reduce_kernel<false, 4, 104><<<grid, kBnBwdThreads, 0, s>>>(a);
+  if (a.g_pool) {
+    if (a.head_dlogits) return cudaErrorInvalidValue;
+    bn_bwd_reduce_kernel<true, false, 1, 128><<<grid, kBnBwdThreads, 0, s>>>(a);
+  } else if (a.head_dlogits) {
+    bn_bwd_reduce_kernel<false, true, 6, 128><<<grid, kBnBwdThreads, 0, s>>>(a);
+  } else {
+    bn_bwd_reduce_kernel<false, false, 4, 104><<<grid, kBnBwdThreads, 0, s>>>(a);
+  }
   cudaError_t e = launched();
   if (e != cudaSuccess) return e;
   bn_bwd_finalize_kernel<<<a.C, 256, 0, s>>>(a, grid * bn_bwd_rows_per_block(a.C));
   return launched();
 }
 
-template <bool POOL, int U_, int REGS>
+template <bool POOL, bool HEAD, int U_, int REGS>
 __global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(REGS) bn_bwd_apply_kernel(BnBwdArgs a) {
   const int cg = a.C >> 3;
   const int g = threadIdx.x % cg, ri = threadIdx.x / cg, rpb = kBnBwdThreads / cg;
@@ -684,16 +695,16 @@ __global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(REGS) bn_bwd_apply_
     constexpr int U = U_;
     const long long stride = (long long)gridDim.x * rpb;
     for (long long u0 = (long long)blockIdx.x * rpb + ri; u0 < units; u0 += U * stride) {
-      PlainUnit pu[U];
+      PlainUnit<HEAD> pu[U];
 #pragma unroll
       for (int i = 0; i < U; ++i)
-        if (u0 + i * stride < units) plain_load(a, k, g, u0 + i * stride, pu[i]);
+        if (u0 + i * stride < units) plain_load<HEAD>(a, g, u0 + i * stride, pu[i]);
 #pragma unroll
       for (int i = 0; i < U; ++i) {
         const long long u = u0 + i * stride;
         if (u >= units) break;
         float gm[8], xh[8], o[8];
-        plain_compute(k, pu[i], gm, xh);
+        plain_compute<HEAD>(k, pu[i], gm, xh);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = k.sc[j] * (gm[j] - c1[j] - xh[j] * c2[j]);
         st8(a.dy + u * a.C + g * 8, pack8(o));
@@ -703,8 +714,9 @@ __global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(REGS) bn_bwd_apply_
 }
 cudaError_t launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t s) {
   const int grid = bn_bwd_grid(a);
-  if (a.g_pool) bn_bwd_apply_kernel<true, 1, 128><<<grid, kBnBwdThreads, 0, s>>>(a);
-  else bn_bwd_apply_kernel<false, 3, 104><<<grid, kBnBwdThreads, 0, s>>>(a);
+  if (a.g_pool) bn_bwd_apply_kernel<true, false, 1, 128><<<grid, kBnBwdThreads, 0, s>>>(a);
+  else if (a.head_dlogits) bn_bwd_apply_kernel<false, true, 5, 128><<<grid, kBnBwdThreads, 0, s>>>(a);
+  else bn_bwd_apply_kernel<false, false, 3, 104><<<grid, kBnBwdThreads, 0, s>>>(a);
   return launched();
 }
 

@@ -814,8 +814,10 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) conv3_gemm_kernel(const __gr
       const uint32_t lbo_lo = (16u >> 4) << 16;                             // LBO field lives in the low word
       const uint32_t s_base = (smem_u32(smem) >> 4) | lbo_lo;
       // A descriptor high word: SBO = one image row of the patch (PW pixels x 128 B), version 1, 128B swizzle
-      constexpr uint32_t a_hi0 = ((uint32_t)(PW * 128) >> 4) | (1u << 14) | (2u << 29);
-      const uint32_t base_off_on = p.conv3_desc_mode == 1 ? 1u : 0u;
+      // (the descriptor's base-offset field stays 0: measured on B200, the swizzle is applied to the absolute shared-
+      // memory address, so a view that starts k rows into a 1024-byte atom needs no correction — setting the field to
+      // the row phase, as the PTX text for non-aligned matrices suggests, gives wrong results)
+      constexpr uint32_t a_hi = ((uint32_t)(PW * 128) >> 4) | (1u << 14) | (2u << 29);
       int kc = 0, acc = 0, acc_phase = 0, phA = 0, u = first_unit;
       uint32_t gq = 0;                                                      // weight groups consumed so far
       uint32_t accumulate = 0;
@@ -848,7 +850,6 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) conv3_gemm_kernel(const __gr
 #pragma unroll
               for (int r = 0; r < 3; ++r) {
                 const uint32_t row0 = (uint32_t)(r * PW + g);               // first patch row of this tap's view
-                const uint32_t a_hi = a_hi0 | (base_off_on * ((row0 & 7u) << 17));
                 // four K-steps of 16 channels: +32 bytes = +2 in the descriptor start field per step
                 umma_bf16_steps4_warp_hi<true>(d_tmem, a_slot + row0 * 8u, a_hi, b_lo + (uint32_t)(r * (L::kBTile >> 4)), idesc,
                                                accumulate);
@@ -917,25 +918,13 @@ static cudaError_t launch_conv3(const PixGemmParams& p, int num_sms, cudaStream_
 static cudaError_t launch_conv3_gemm(const PixGemmParams& p, int block_n, int num_sms, cudaStream_t stream) {
   if (p.G != 3 || p.R != 3 || !p.pair) return cudaErrorInvalidValue;
   const bool resident = block_n == 64 && p.n_blocks == 1 && p.kchunks <= 2;
-  if (p.conv3_pw == 10) {
-    switch (block_n) {
-      case 64: return resident ? launch_conv3<64, 10, 4, 3, 2, 2, true>(p, num_sms, stream)
-                               : launch_conv3<64, 10, 4, 3, 2, 2, false>(p, num_sms, stream);
-      case 128: return launch_conv3<128, 10, 4, 3, 2, 2, false>(p, num_sms, stream);
-      case 256: return launch_conv3<256, 10, 2, 3, 1, 1, false>(p, num_sms, stream);
-      default: return cudaErrorInvalidValue;
-    }
+  switch (block_n) {
+    case 64: return resident ? launch_conv3<64, 10, 4, 3, 2, 2, true>(p, num_sms, stream)
+                             : launch_conv3<64, 10, 4, 3, 2, 2, false>(p, num_sms, stream);
+    case 128: return launch_conv3<128, 10, 4, 3, 2, 2, false>(p, num_sms, stream);
+    case 256: return launch_conv3<256, 10, 2, 3, 1, 1, false>(p, num_sms, stream);
+    default: return cudaErrorInvalidValue;
   }
-  if (p.conv3_pw == 16) {
-    switch (block_n) {
-      case 64: return resident ? launch_conv3<64, 16, 2, 3, 2, 2, true>(p, num_sms, stream)
-                               : launch_conv3<64, 16, 2, 3, 2, 2, false>(p, num_sms, stream);
-      case 128: return launch_conv3<128, 16, 2, 3, 2, 2, false>(p, num_sms, stream);
-      case 256: return launch_conv3<256, 16, 2, 2, 1, 1, false>(p, num_sms, stream);
-      default: return cudaErrorInvalidValue;
-    }
-  }
-  return cudaErrorInvalidValue;
 }
 
 template <int BLOCK_N, int S, int NSTG, int EG>

@@ -43,9 +43,7 @@ struct PixGemmParams {
   // conv3_gemm_kernel (3x3 convolutions, G = R = 3): ONE (8+2) x (16+2) pixel patch per 64-channel chunk serves all nine
   // taps (the three horizontal taps are 128-byte row offsets into it) instead of three 8 x 18 patches.
   int conv3;            // 1: use conv3_gemm_kernel with tmapA3
-  int conv3_pw;         // patch width in pixels (10, or 16 = two whole swizzle atoms per image row)
-  int conv3_desc_mode;  // 0: descriptor base offset 0 (swizzle on absolute smem address bits); 1: base offset = row phase
-  CUtensorMap tmapA3;   // box (64 ch, conv3_pw, 18, 1)
+  CUtensorMap tmapA3;   // box (64 ch, 10, 18, 1)
 };
 
 cudaError_t launch_pix_gemm(const PixGemmParams& p, int block_n, int num_sms, cudaStream_t stream);

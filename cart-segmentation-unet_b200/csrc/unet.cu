@@ -110,16 +110,13 @@ static int weight_map(CUtensorMap* m, const bf16* base, int K, int rows, int blo
 
 static int pick_block_n(int n) { return n % 256 == 0 ? 256 : (n % 128 == 0 ? 128 : 64); }
 
-// 3x3 convolutions through conv3_gemm_kernel (one activation patch per K-chunk for all nine taps).  Developer knobs for
-// A/B runs: CARTSEG_CONV3=0 selects pix_gemm2_kernel, CARTSEG_CONV3_PW=10|16 the patch width, CARTSEG_CONV3_MODE=0|1 the
-// descriptor base-offset convention.
+// 3x3 convolutions go through conv3_gemm_kernel (one activation patch per K-chunk for all nine taps);
+// CARTSEG_CONV3=0 selects pix_gemm2_kernel (three patches per K-chunk) for same-box A/B runs.
 static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
 }
-static int conv3_enabled() { static const int v = env_int("CARTSEG_CONV3", 0); return v; }
-static int conv3_pw() { static const int v = env_int("CARTSEG_CONV3_PW", 10); return v; }
-static int conv3_mode() { static const int v = env_int("CARTSEG_CONV3_MODE", 0); return v; }
+static int conv3_enabled() { static const int v = env_int("CARTSEG_CONV3", 1); return v; }
 // TMA map over an NHWC buffer with a (64, pw, 18, 1) box: the whole halo patch of an 8 x 16 pixel tile.
 static int nhwc_patch_map(CUtensorMap* m, const bf16* base, int pitch, int B, int H, int W, int pw);
 
@@ -153,9 +150,7 @@ static int build_conv3x3(PixGemmParams& p, int* block_n, View in, int K, View ou
   CS_TRY(nhwc_map(&p.tmapO[0], out.p, out.pitch, B, H, W, 16));
   if (use_pair() && conv3_enabled()) {
     p.conv3 = 1;
-    p.conv3_pw = conv3_pw();
-    p.conv3_desc_mode = conv3_mode();
-    CS_TRY(nhwc_patch_map(&p.tmapA3, in.p, in.pitch, B, H, W, p.conv3_pw));
+    CS_TRY(nhwc_patch_map(&p.tmapA3, in.p, in.pitch, B, H, W, 10));
   }
   return 0;
 }
@@ -368,8 +363,14 @@ struct cs_unet_plan {
 
 namespace {
 // kernel classes reported by cs_unet_profile_read
-enum { kClsPix256 = 0, kClsPix128, kClsPix64, kClsWgrad128, kClsWgrad64, kNumCls };
+enum { kClsPix256 = 0, kClsPix128, kClsPix64, kClsWgrad128, kClsWgrad64, kClsConv256, kClsConv128, kClsConv64, kNumCls };
+static_assert(kNumCls == CS_UNET_NUM_PROFILE_CLASSES, "profile classes");
 int pix_class(int bn) { return bn == 256 ? kClsPix256 : (bn == 128 ? kClsPix128 : kClsPix64); }
+// 3x3 convolutions run on conv3_gemm_kernel unless CARTSEG_CONV3=0
+int conv_class(const PixGemmParams& p, int bn) {
+  if (!p.conv3) return pix_class(bn);
+  return bn == 256 ? kClsConv256 : (bn == 128 ? kClsConv128 : kClsConv64);
+}
 int wgrad_class(int bn) { return bn == 128 ? kClsWgrad128 : kClsWgrad64; }
 
 // Runs `launch` between two events on `s` when profiling is on.
@@ -717,7 +718,7 @@ int cs_unet_forward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* x, 
   auto run_conv = [&](int i) -> int {
     ConvL& c = pl->conv[i];
     if (training) {
-      CS_CUDA(timed(pl, pix_class(c.bn_f), c.flops, s, [&] { return launch_pix_gemm(c.fp_train, c.bn_f, pl->num_sms, s); }));
+      CS_CUDA(timed(pl, conv_class(c.fp_train, c.bn_f), c.flops, s, [&] { return launch_pix_gemm(c.fp_train, c.bn_f, pl->num_sms, s); }));
       BnFinalizeArgs f{};
       f.sum = c.st_sum; f.sq = c.st_sq; f.count = (double)c.P;
       f.gamma = t->param[c.pgamma]; f.beta = t->param[c.pbeta]; f.conv_bias = t->param[c.pb];
@@ -729,7 +730,7 @@ int cs_unet_forward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* x, 
       const HeadFwd head = (i == 17 && fuse_head()) ? HeadFwd{t->param[80], t->param[81], logits} : HeadFwd{nullptr, nullptr, nullptr};
       CS_CUDA(launch_bn_relu(c.y, B, c.H, c.W, c.cout, f, c.out.p, c.out.pitch, c.out.c0, c.pooled, head, s));
     } else {
-      CS_CUDA(timed(pl, pix_class(c.bn_f), c.flops, s, [&] { return launch_pix_gemm(c.fp_eval, c.bn_f, pl->num_sms, s); }));
+      CS_CUDA(timed(pl, conv_class(c.fp_eval, c.bn_f), c.flops, s, [&] { return launch_pix_gemm(c.fp_eval, c.bn_f, pl->num_sms, s); }));
       if (c.pooled) CS_CUDA(launch_maxpool(c.out.p, c.out.pitch, c.out.c0, B, c.H, c.W, c.cout, c.pooled, s));
     }
     return 0;
@@ -874,7 +875,7 @@ int cs_unet_backward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* dl
       // Decoder convs always run their dgrad: it is the only writer of the concat-gradient buffer that the conv-transpose
       // weight / bias gradients read.  An encoder conv needs it only if something below it still trains.
       if (idx >= 10 || (idx > 0 && idx > frozen_encoder_convs))
-        CS_CUDA(traced(pl, 300 + idx, s, [&] { return timed(pl, pix_class(c.bn_d), c.flops, s, [&] { return launch_pix_gemm(c.dg, c.bn_d, pl->num_sms, s); }); }));
+        CS_CUDA(traced(pl, 300 + idx, s, [&] { return timed(pl, conv_class(c.dg, c.bn_d), c.flops, s, [&] { return launch_pix_gemm(c.dg, c.bn_d, pl->num_sms, s); }); }));
     } else {
       UpL& u = pl->up[idx];
       if (overlap && (t->grad[u.pb] || t->grad[u.pw])) {  // g_out of the conv-transpose is final on the main stream

@@ -88,7 +88,8 @@ int cs_unet_backward(cs_unet_plan* plan, const cs_unet_tensors* t, const float* 
 /* Per-launch timing of the tensor-core kernels (bench.py's roofline): while enabled, every implicit-GEMM launch of
  * cs_unet_forward / cs_unet_backward is bracketed by CUDA events on the launch stream.  cs_unet_profile_read waits for
  * the recorded events and returns, per kernel class, the summed device time (ms), algorithmic FLOPs (2*MACs) and
- * launch count since the last read.  Classes: 0 pixel GEMM N=256, 1 N=128, 2 N=64, 3 weight-gradient GEMM N=128, 4 N=64. */
+ * launch count since the last read.  Classes: 0-2 pix_gemm2_kernel N=256 / 128 / 64 (conv-transposes, the stem),
+ * 3-4 wgrad_gemm_kernel N=128 / 64, 5-7 conv3_gemm_kernel N=256 / 128 / 64 (3x3 convolutions, fprop and dgrad). */
 /* cs_unet_backward runs the weight-gradient GEMMs on an internal lower-priority stream so that they overlap the
  * HBM-bound BatchNorm-backward passes of the following layers (forked from / joined into `stream` with events).
  * cs_unet_set_overlap(plan, 0) serialises everything on the caller's stream (used for per-kernel timing). */
@@ -104,7 +105,7 @@ int cs_unet_set_deferred_join(cs_unet_plan* plan, int enable);
  * CTA has to wait for a second wave (sms <= 0 restores the full device). */
 int cs_unet_plan_set_sm_limit(cs_unet_plan* plan, int sms);
 int cs_unet_backward_wait(cs_unet_plan* plan, cs_stream_t stream);
-#define CS_UNET_NUM_PROFILE_CLASSES 5
+#define CS_UNET_NUM_PROFILE_CLASSES 8
 int cs_unet_profile(cs_unet_plan* plan, int enable);
 int cs_unet_profile_read(cs_unet_plan* plan, int n_classes, double* ms, double* flops, long long* launches);
 /* Developer timeline of cs_unet_backward: while enabled, every launch of the backward pass (both internal streams) is

@@ -131,3 +131,44 @@ def test_train_step_full_k2_teacher_forced_stages_and_loss():
         print(f"   {n:40s} {e:.3e} / {tol:g}")
     bad = [(n, f"{e:.3e}", tol) for n, e, tol in rows if not e < tol]
     assert not bad, bad
+
+
+def test_gradients_full_k2_per_tensor_vs_both_oracles():
+    """End-to-end gradients AT K2 size (B=64 @224^2, focal-Dice, default init) against the fp32 oracle and the
+    bf16-emulating oracle, per tensor (tools/grad_parity.py; table committed as profiles/r2_grad_parity_per_tensor.json).
+    What holds, and is asserted:
+      * loss 1e-2 (measured 7e-6); logits 3e-2 (measured 1.1e-2);
+      * the ten tensors nearest the loss (final_conv, dconv1.*, upconv1) meet the north-star 3e-2 against the FP32
+        oracle (measured 1e-3 ... 2.4e-2);
+      * every tensor is as close to the fp32 oracle as the oracle's own bf16-storage emulation is (ratio <= 1.1): the
+        remaining deviation (up to 0.46 rel-L2 at the bottleneck, 14 layers from the loss) is what rounding stored
+        activations to bf16 does to ANY implementation of this network — a CPU-only fact (emu_vs_fp32) — not a kernel
+        error; DESIGN.md §1 states this deviation from north_star's 3e-2;
+      * whole gradient: cosine >= 0.99 vs fp32 (measured 0.9964), >= 0.997 vs the emulation (0.9989)."""
+    import argparse
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import grad_parity
+    out = grad_parity.compute(argparse.Namespace(batch=64, size=224, loss="focal_dice", seed=0))
+    print({k: out[k] for k in ("loss", "logits_rel_l2", "whole_gradient", "tensors_meeting_3e-2_vs_fp32")})
+    assert out["loss"]["rel_vs_fp32"] < 1e-2
+    assert out["logits_rel_l2"]["gpu_vs_fp32"] < 3e-2
+    wg = out["whole_gradient"]
+    assert wg["cos_gpu_fp32"] >= 0.99 and wg["cos_gpu_emu"] >= 0.997, wg
+    assert wg["gpu_vs_fp32"] <= 1.1 * wg["emu_vs_fp32"] + 5e-3, wg
+    near = ("final_conv.", "dconv1.", "upconv1.")
+    for r in out["per_tensor_backward_order"]:
+        if "gpu_vs_fp32" not in r:
+            assert r["gpu_absmax"] == 0.0, r                       # conv bias before a train-mode BN
+            continue
+        if r["tensor"].startswith(near):
+            assert r["gpu_vs_fp32"] < 3e-2, r
+        if r["tensor"].startswith("upconv") and r["tensor"].endswith(".bias"):
+            # Sum over pixels of an activation gradient that cancels to ~1e-3 of its terms (the BN backward above it
+            # removes the mean; only image-border pixels contribute): the bf16 storage of that gradient — which the
+            # emulation, with fp32 gradients, does not have — shows up here.  Measured 2.4e-2 ... 1.3e-1.
+            assert r["gpu_vs_fp32"] < 0.2, r
+            continue
+        assert r["gpu_vs_fp32"] <= 1.1 * r["emu_vs_fp32"] + 1e-2, r
+        assert r["gpu_vs_emu"] <= 0.8 * r["emu_vs_fp32"] + 2e-2, r

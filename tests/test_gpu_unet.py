@@ -154,8 +154,8 @@ def test_train_step_vs_oracle(B, H, W, loss):
         worst.append((e_emu, e_oo, c, k))
         if k.startswith("final_conv."):
             assert e_emu < GRAD_TOL, (k, e_emu)
-        assert e_emu <= 2.0 * e_oo + 5e-2, (k, e_emu, e_oo)
-        assert c >= 0.9, (k, c)
+        assert e_emu <= 1.0 * e_oo + 3e-2, (k, e_emu, e_oo)     # measured: e_emu ~ 0.63 e_oo on the worst tensors
+        assert c >= 0.93, (k, c)                                 # measured worst 0.951 (conv5.conv.1.bias, B = 2)
     worst.sort(reverse=True)
     print("per-tensor worst (rel-L2 GPU vs emu, emu vs fp32, cosine):",
           [(k, f"{a:.3f}", f"{b:.3f}", f"{c:.4f}") for a, b, c, k in worst[:5]])
@@ -367,17 +367,21 @@ def test_eval_packs_follow_data_updates_and_model_recreation():
         sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
         ref = O.unet_logits(x, sd, training=False)
     assert rel_l2(b.cpu(), ref) < 2e-2 and rel_l2(b, a) > 0.05
-    # opt-in: packs frozen -> the same .data edit is (by contract) NOT seen until freeze_packed is called again
+    # opt-in: packs frozen -> an edit of the PACKED tensors (3x3 conv / conv-transpose weights; BN parameters, biases and
+    # the 1x1 head are read live) is by contract NOT seen until freeze_packed is called again
     m.freeze_packed()
+    packed = [p for k, p in m.named_parameters() if p.dim() == 4 and not k.startswith("final_conv")]
     with torch.no_grad():
         c0 = m(xg).clone()
-        for p in m.parameters():
+        for p in packed:
             p.data.mul_(2.0)
         c1 = m(xg).clone()
         assert torch.equal(c0, c1)
         m.freeze_packed()
         c2 = m(xg).clone()
-    assert rel_l2(c2, a) < 1e-3
+        sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+        ref = O.unet_logits(x, sd, training=False)
+    assert rel_l2(c2.cpu(), ref) < 2e-2 and not torch.equal(c2, c0)
     # checkpoint loop: same addresses, same versions, different weights
     outs = []
     for seed in (1, 2, 3):

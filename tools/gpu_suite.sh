@@ -26,9 +26,10 @@ for part in "$@"; do
     layers) run test_gpu_layers 900 python -m pytest tests/test_gpu_layers.py -m gpu -q --tb=short -s --timeout 300 ;;
     stages) run test_gpu_unet_stages 1200 python -m pytest tests/test_gpu_unet_stages.py -m gpu -q --tb=short -s --timeout 600 ;;
     unet)   run test_gpu_unet 1200 python -m pytest tests/test_gpu_unet.py -m gpu -q --tb=short -s --timeout 600 ;;
-    conv3exp) for pw in 10 16; do for mode in 0 1; do
-              CARTSEG_CONV3=1 CARTSEG_CONV3_PW=$pw CARTSEG_CONV3_MODE=$mode run conv3_pw${pw}_mode${mode} 600 python -m pytest tests/test_gpu_layers.py -m gpu -q --tb=line -k "fprop or dgrad" --timeout 120
-            done; done ;;
+    layers_old) CARTSEG_CONV3=0 run test_gpu_layers_oldkernel 900 python -m pytest tests/test_gpu_layers.py -m gpu -q --tb=short --timeout 300 ;;
+    bench10_old) CARTSEG_CONV3=0 run bench10_old 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extra-workloads ;;
+    bench10q) run bench10q 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extra-workloads ;;
+    cpubase) run cpu_baseline 1500 python tools/cpu_baseline.py ;;
     loop)   run test_gpu_loop 900 python -m pytest tests/test_gpu_loop.py -m gpu -q --tb=short -s --timeout 600 ;;
     fullsize) run test_gpu_fullsize 1500 python -m pytest tests/test_gpu_fullsize.py -m gpu -q --tb=short -s --timeout 900 ;;
     gradparity) run grad_parity 1200 python tools/grad_parity.py --out gpurun_out/r2_grad_parity_per_tensor.json ;;

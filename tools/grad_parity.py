@@ -33,15 +33,7 @@ def cosine(a, b):
     return float(torch.dot(a, b) / max(float(a.norm() * b.norm()), 1e-300))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--batch", type=int, default=64)
-    ap.add_argument("--size", type=int, default=224)
-    ap.add_argument("--loss", default="focal_dice", choices=["focal_dice", "bce_dice", "composite"])
-    ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r2_grad_parity_per_tensor.json"))
-    args = ap.parse_args()
-
+def compute(args):
     import cartseg
     from cartseg import ops
     from oracle import unet_oracle as O
@@ -119,6 +111,19 @@ def main():
         "cpu_seconds": {"fp32_oracle": t_ref, "emu_oracle": t_emu, "threads": torch.get_num_threads()},
         "per_tensor_backward_order": rows,
     }
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--size", type=int, default=224)
+    ap.add_argument("--loss", default="focal_dice", choices=["focal_dice", "bce_dice", "composite"])
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r2_grad_parity_per_tensor.json"))
+    args = ap.parse_args()
+    out = compute(args)
+    live = [r for r in out["per_tensor_backward_order"] if "gpu_vs_fp32" in r]
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as fh:
         json.dump(out, fh, indent=1)
