@@ -391,7 +391,7 @@ def run_ours(args, wl):
     # ---- per-kernel roofline pass: the same steps again, weight-gradient overlap off so that every tensor-core
     # launch runs alone between its two CUDA events (in the timed region above the wgrad GEMMs share the GPU with
     # the BN-backward passes and dgrads, which is what makes the step faster but their own durations meaningless)
-    NC = 8
+    NC = 9
     k_ms, k_fl, k_n = (C.c_double * NC)(), (C.c_double * NC)(), (C.c_longlong * NC)()
     L.cs_unet_set_overlap(plan.handle, 0)
     step(x_d, t_d)
@@ -409,7 +409,8 @@ def run_ours(args, wl):
     k_names = ["pix_gemm2_kernel<256> (conv-transpose fprop+dgrad)", "pix_gemm2_kernel<128>",
                "pix_gemm2_kernel<64> (stem)", "wgrad_gemm_kernel<128>", "wgrad_gemm_kernel<64>",
                "conv3_gemm_kernel<256> (3x3 conv fprop+dgrad, N-side 256)", "conv3_gemm_kernel<128>",
-               "conv3_gemm_kernel<64> (weights resident in shared memory)"]
+               "conv3_gemm_kernel<64> (weights resident in shared memory)",
+               "wgrad9_gemm_kernel (3x3 weight gradients with Cout = 64, nine taps per CTA)"]
     kernels = [{"kernel": k_names[i], "launches_per_step": k_n[i] / args.steps, "ms_per_step": k_ms[i] / args.steps,
                 "avg_launch_us": 1e3 * k_ms[i] / max(1, k_n[i]), "tflops": k_fl[i] / max(1e-9, k_ms[i]) / 1e9}
                for i in range(NC) if k_n[i] > 0]

@@ -80,6 +80,7 @@ _SIGNATURES = {
     "cs_unet_set_deferred_join": (C.c_int, [_P, C.c_int]),
     "cs_unet_plan_set_sm_limit": (C.c_int, [_P, C.c_int]),
     "cs_unet_backward_wait": (C.c_int, [_P, _P]),
+    "cs_unet_backward_held_stages": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]),
     "cs_unet_profile": (C.c_int, [_P, C.c_int]),
     "cs_unet_profile_read": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "cs_unet_trace": (C.c_int, [_P, C.c_int]),

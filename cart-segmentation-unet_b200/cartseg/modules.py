@@ -94,6 +94,8 @@ class UNet(nn.Module):
     ``torch.sigmoid`` tail (:83) for the interactive tool.
     """
 
+    EVAL_CHUNK = 128         # eval-mode forwards of more images run in chunks of this many
+
     def __init__(self, in_channels: int = 3, out_channels: int = 1, final_sigmoid: bool = False):
         super().__init__()
         if out_channels != 1:
@@ -233,6 +235,19 @@ class UNet(nn.Module):
         params = self._flat_params()
         buffers = self._flat_buffers()
         grad_mode = torch.is_grad_enabled()
+        if (not self.training and not grad_mode and B > self.EVAL_CHUNK and not torch.compiler.is_compiling()):
+            # Large eval batches run as chunks: per-sample independent (running statistics), and a chunk's activations
+            # still overlap the 126 MB L2 between producer and consumer kernels — B = 512 in one piece measured 7 % slower
+            # per image than B = 64-128.
+            if not self._packed_frozen:
+                self._weights_epoch += 1
+            token = (self._uid << 40) | (self._weights_epoch & ((1 << 40) - 1))
+            logits = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
+            for i in range(0, B, self.EVAL_CHUNK):
+                n = min(self.EVAL_CHUNK, B - i)
+                plan = ops.get_plan(n, C, H, W, x.device, inference_only=True)
+                ops.unet_forward_impl(x[i:i + n], params, buffers, False, plan.id, token, out=logits[i:i + n])
+            return torch.sigmoid(logits) if self.final_sigmoid else logits
         wants_grad = grad_mode and any(p.requires_grad for p in params)
         need_grad = self.training and wants_grad
         plan = ops.get_plan(B, C, H, W, x.device, inference_only=not self.training)

@@ -168,14 +168,19 @@ def _ensure_packed(plan: Plan, params: List[Tensor], t: UnetTensors, pack_token:
 
 
 def unet_forward_impl(x: Tensor, params: List[Tensor], buffers: List[Tensor], training: bool, plan_id: int,
-                      pack_token: int) -> Tensor:
+                      pack_token: int, out: Optional[Tensor] = None) -> Tensor:
     """Body of ``cartseg::unet_forward``.  UNet.forward calls it directly for eager no-grad eval forwards: the
     dispatcher costs ~0.15 ms per call with 136 tensor arguments, as much as a batch-1 forward takes on the GPU."""
     plan = _plan(plan_id)
     B, Cin, H, W = plan.shape
     if tuple(x.shape) != (B, Cin, H, W) or x.dtype != torch.float32 or not x.is_contiguous():
         raise CartsegError(f"x must be a contiguous float32 tensor of shape {(B, Cin, H, W)}, got {tuple(x.shape)} {x.dtype}")
-    logits = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
+    if out is None:
+        logits = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
+    else:                                   # a contiguous [B,1,H,W] slice of a larger output (chunked eval forwards)
+        if tuple(out.shape) != (B, 1, H, W) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != x.device:
+            raise CartsegError("out must be a contiguous float32 [B,1,H,W] tensor on the input's device")
+        logits = out
     t = _fill_tensors(params, None, buffers)
     with torch.cuda.device(x.device):
         _ensure_packed(plan, params, t, pack_token)
@@ -186,7 +191,12 @@ def unet_forward_impl(x: Tensor, params: List[Tensor], buffers: List[Tensor], tr
     return logits
 
 
-unet_forward = torch.library.custom_op("cartseg::unet_forward", unet_forward_impl, mutates_args=("buffers",),
+def _unet_forward_op(x: Tensor, params: List[Tensor], buffers: List[Tensor], training: bool, plan_id: int,
+                     pack_token: int) -> Tensor:
+    return unet_forward_impl(x, params, buffers, training, plan_id, pack_token)
+
+
+unet_forward = torch.library.custom_op("cartseg::unet_forward", _unet_forward_op, mutates_args=("buffers",),
                                        device_types="cuda")
 
 
@@ -216,6 +226,15 @@ def stage_params() -> List[List[int]]:
 
 
 _DP_STATES: Dict[int, object] = {}         # handle -> parallel.GradSync (registered by cartseg.parallel)
+
+
+def held_stages() -> Tuple[int, set]:
+    """(flush stage, stages whose weight gradients are enqueued only when the flush stage is) — see
+    cs_unet_backward_held_stages."""
+    flush = C.c_int()
+    buf = (C.c_int * _lib.NUM_BWD_STAGES)()
+    n = _lib.lib().cs_unet_backward_held_stages(C.byref(flush), buf, _lib.NUM_BWD_STAGES)
+    return int(flush.value), {int(buf[i]) for i in range(n)}
 
 
 def grad_layout(params: List[Tensor]) -> Tuple[List[int], List[int], List[int]]:
@@ -273,13 +292,22 @@ def unet_backward(dlogits: Tensor, params: List[Tensor], plan_id: int, generatio
             # bucket by bucket; the join with the library's internal streams is deferred: only the communication
             # stream waits per bucket, the compute stream once at the end
             check(L.cs_unet_set_deferred_join(plan.handle, 1), "cs_unet_set_deferred_join")
+            wait = lambda cuda_stream: check(L.cs_unet_backward_wait(plan.handle, cuda_stream), "cs_unet_backward_wait")  # noqa: E731
+            flush_stage, held = held_stages()
+            postponed: List[Tuple[int, int]] = []       # buckets with weight gradients that are not enqueued yet
             try:
                 for (s0, s1) in sync.stage_buckets(stage_off):
                     check(L.cs_unet_backward(plan.handle, C.byref(t), ptr(dlogits), s0, s1, frozen_encoder_convs,
                                              stream), "cs_unet_backward")
-                    sync.reduce_async(flat[stage_off[s0]:stage_off[s1]],
-                                      wait=lambda cuda_stream: check(L.cs_unet_backward_wait(plan.handle, cuda_stream),
-                                                                     "cs_unet_backward_wait"))
+                    flushed = s1 > flush_stage
+                    if not flushed and any(st in held for st in range(s0, s1)):
+                        postponed.append((s0, s1))
+                        continue
+                    if flushed:
+                        for (p0, p1) in postponed:
+                            sync.reduce_async(flat[stage_off[p0]:stage_off[p1]], wait=wait)
+                        postponed.clear()
+                    sync.reduce_async(flat[stage_off[s0]:stage_off[s1]], wait=wait)
                 check(L.cs_unet_backward_wait(plan.handle, stream), "cs_unet_backward_wait")
             finally:
                 L.cs_unet_set_deferred_join(plan.handle, 0)

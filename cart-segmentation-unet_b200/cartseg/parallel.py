@@ -41,16 +41,25 @@ def plan_buckets(stage_off: Sequence[int], bucket_elems: int) -> List[Tuple[int,
 class GradSync:
     """Averages slices of the flat gradient buffer across the process group, asynchronously."""
 
-    def __init__(self, group: Optional[dist.ProcessGroup] = None, bucket_mb: float = 16.0):
+    def __init__(self, group: Optional[dist.ProcessGroup] = None, bucket_mb: float = 16.0,
+                 wire_dtype: torch.dtype = torch.float32):
+        """``wire_dtype=torch.bfloat16`` sends the gradients over NVLink as bf16 (62 MB instead of 124 MB per step for
+        this network): the NCCL kernels then hold their SMs for half as long next to the single-wave persistent GEMM
+        grids.  The fp32 gradients are rounded once before and the bf16 average once after the collective (relative
+        error <= 2^-8 per element; the optimizer still sees fp32 tensors)."""
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
+        if wire_dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("wire_dtype must be torch.float32 or torch.bfloat16")
         self.group = group
         self.world = dist.get_world_size(group)
         self.bucket_elems = max(1, int(bucket_mb * (1 << 20) / 4))
+        self.wire_dtype = wire_dtype
         self._comm_stream = None
         self._works = []
         self._use_avg = dist.get_backend(group) == "nccl"
         self._pending_scale: List[torch.Tensor] = []
+        self.trace = None                      # list of (label, begin event, end event) when tracing is on
 
     def stage_buckets(self, stage_off: Sequence[int]) -> List[Tuple[int, int]]:
         return plan_buckets(stage_off, self.bucket_elems)
@@ -70,10 +79,23 @@ class GradSync:
             if wait is not None:
                 wait(self._comm_stream.cuda_stream)
             with torch.cuda.stream(self._comm_stream):
+                if self.trace is not None:
+                    e0 = torch.cuda.Event(enable_timing=True)
+                    e0.record(self._comm_stream)
                 op = dist.ReduceOp.AVG if self._use_avg else dist.ReduceOp.SUM
-                dist.all_reduce(flat_slice, op=op, group=self.group)
+                if self.wire_dtype is torch.bfloat16:
+                    wire = flat_slice.to(torch.bfloat16)
+                    wire.record_stream(self._comm_stream)
+                    dist.all_reduce(wire, op=op, group=self.group)
+                    flat_slice.copy_(wire)
+                else:
+                    dist.all_reduce(flat_slice, op=op, group=self.group)
                 if not self._use_avg:
                     flat_slice.mul_(1.0 / self.world)
+                if self.trace is not None:
+                    e1 = torch.cuda.Event(enable_timing=True)
+                    e1.record(self._comm_stream)
+                    self.trace.append((flat_slice.numel(), e0, e1))
         else:                                           # CPU tensors (gloo): used by the host-logic tests
             self._works.append(dist.all_reduce(flat_slice, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
             self._pending_scale.append(flat_slice)
@@ -94,7 +116,7 @@ _next_handle = 1
 
 
 def init_data_parallel(model, group: Optional[dist.ProcessGroup] = None, bucket_mb: Optional[float] = None,
-                       broadcast_from: int = 0, reserve_sms: int = 0):
+                       broadcast_from: int = 0, reserve_sms: int = 0, wire_dtype: Optional[torch.dtype] = None):
     """Make ``model`` (a cartseg.UNet) data-parallel over ``group``: broadcast rank-``broadcast_from``'s
     parameters and BN buffers, and hook the bucketed gradient all-reduce into its backward.  Returns the model.
 
@@ -108,7 +130,9 @@ def init_data_parallel(model, group: Optional[dist.ProcessGroup] = None, bucket_
         bucket_mb = float(os.environ.get("CARTSEG_DP_BUCKET_MB", DEFAULT_BUCKET_MB))
     if not reserve_sms:
         reserve_sms = int(os.environ.get("CARTSEG_DP_RESERVE_SMS", "0"))
-    sync = GradSync(group, bucket_mb)
+    if wire_dtype is None:
+        wire_dtype = {"fp32": torch.float32, "bf16": torch.bfloat16}[os.environ.get("CARTSEG_DP_WIRE_DTYPE", "fp32")]
+    sync = GradSync(group, bucket_mb, wire_dtype)
     with torch.no_grad():
         for t in list(model.parameters()) + list(model.buffers()):
             dist.broadcast(t, src=broadcast_from, group=group)

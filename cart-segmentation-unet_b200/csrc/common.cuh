@@ -205,6 +205,29 @@ CS_DEVINL void umma_bf16_steps4_warp_hi(uint32_t tmem_d, uint32_t a_lo, uint32_t
 #undef CS_MMA_STEP2
 }
 
+// Eight K-steps (cta_group::1) with separate descriptor high words and per-step advances for A and B.
+template <int A_STEP, int B_STEP>
+CS_DEVINL void umma_bf16_steps8_warp_ab(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                        uint32_t idesc, uint32_t accumulate_first) {
+#define CS_MMA_STEP3(i, PRED)                                                                    \
+  "add.u32 al, %1, " #i "*%7;\n\t"                                                               \
+  "add.u32 bl, %2, " #i "*%8;\n\t"                                                               \
+  "mov.b64 da, {al, %3};\n\t"                                                                    \
+  "mov.b64 db, {bl, %4};\n\t"                                                                    \
+  "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, " PRED ";\n\t"
+  asm volatile(
+      "{\n\t.reg .pred p, q, t;\n\t.reg .b64 da, db;\n\t.reg .b32 al, bl;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.eq.b32 t, 0, 0;\n\t"
+      CS_MMA_STEP3(0, "p") CS_MMA_STEP3(1, "t") CS_MMA_STEP3(2, "t") CS_MMA_STEP3(3, "t")
+      CS_MMA_STEP3(4, "t") CS_MMA_STEP3(5, "t") CS_MMA_STEP3(6, "t") CS_MMA_STEP3(7, "t")
+      "}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(a_hi), "r"(b_hi), "r"(idesc), "r"(accumulate_first), "n"(A_STEP), "n"(B_STEP)
+      : "memory");
+#undef CS_MMA_STEP3
+}
+
 template <bool PAIR>
 CS_DEVINL void umma_commit_warp(uint64_t* bar) {
   if (PAIR) {

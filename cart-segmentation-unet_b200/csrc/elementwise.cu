@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(256, 4) bn_relu_kernel(const bf16* __restrict_
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
         const Vec8 stored = pack8(f);
-        st8(out + p * out_pitch + out_c0 + g * 8, stored);
+        if (!head.skip_store) st8(out + p * out_pitch + out_c0 + g * 8, stored);
         if (head.logits) {
           // fused 1x1 head (C == 64: the 8 lanes holding one pixel are adjacent): logits = <stored activation, w> + b.
           // total and the stride are multiples of 32 (H, W multiples of 16), so whole warps are in range together.
@@ -396,6 +396,25 @@ cudaError_t launch_bn_relu(const bf16* y, int B, int H, int W, int C, const BnFi
     bn_relu_kernel<false><<<grid_for((long long)B * H * W * (C / 8), 256 * 4, 148 * 8), 256, smem, s>>>(y, B, H, W, C, fin, out,
                                                                                             out_pitch, out_c0, pooled, head);
   }
+  return launched();
+}
+
+__global__ void bn_apply_relu_kernel(const bf16* __restrict__ y, long long P, int C, const float* __restrict__ scale,
+                                     const float* __restrict__ shift, bf16* __restrict__ out) {
+  const int cg = C >> 3;
+  const long long total = P * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    float f[8];
+    unpack8(ld8(y + i * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], __ldg(scale + g * 8 + j), __ldg(shift + g * 8 + j)), 0.f);
+    st8(out + i * 8, pack8(f));
+  }
+}
+cudaError_t launch_bn_apply_relu(const bf16* y, long long P, int C, const float* scale, const float* shift, bf16* out,
+                                 cudaStream_t s) {
+  bn_apply_relu_kernel<<<grid_for(P * (C / 8), 256), 256, 0, s>>>(y, P, C, scale, shift, out);
   return launched();
 }
 
@@ -464,7 +483,7 @@ CS_DEVINL void plain_load(const BnBwdArgs& a, int g, long long pix, PlainUnit<HE
 }
 // gm[j] = g[j] where the stored (bf16-rounded) activation is positive, else 0;  xh[j] = (y - mean) * invstd
 template <bool HEAD>
-CS_DEVINL void plain_compute(const BnCoef& k, const PlainUnit<HEAD>& u, float gm[8], float xh[8]) {
+CS_DEVINL void plain_compute(const BnCoef& k, const PlainUnit<HEAD>& u, float gm[8], float xh[8], float* act_out = nullptr) {
   float yv[8], t[8], act[8];
   unpack8(u.y, yv);
   if constexpr (HEAD) {
@@ -482,6 +501,7 @@ CS_DEVINL void plain_compute(const BnCoef& k, const PlainUnit<HEAD>& u, float gm
   for (int j = 0; j < 8; ++j) {
     xh[j] = (yv[j] - k.mu[j]) * k.is[j];
     if (!(act[j] > 0.f)) gm[j] = 0.f;
+    if (act_out) act_out[j] = act[j];
   }
 }
 
@@ -557,9 +577,10 @@ __global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(REGS) bn_bwd_reduce
   const long long units = POOL ? (long long)a.B * (a.H >> 1) * (a.W >> 1) : (long long)a.B * a.H * a.W;
   BnCoef k;
   load_coef(a, g, k);
-  float s1[8], s2[8];
+  float s1[8], s2[8], s3[8], sb = 0.f;      // s3 / sb: the 1x1 head's weight / bias gradient (HEAD only)
 #pragma unroll
-  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = s3[j] = 0.f;
+  const bool head_grads = HEAD && (a.head_grad_w != nullptr || a.head_grad_b != nullptr);
   if (POOL) {
     for (long long u = (long long)blockIdx.x * rpb + ri; u < units; u += (long long)gridDim.x * rpb) {
       long long pix[4];
@@ -577,7 +598,17 @@ __global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(REGS) bn_bwd_reduce
       for (int i = 0; i < U; ++i) {
         if (u0 + i * stride >= units) break;
         float gm[8], xh[8];
-        plain_compute<HEAD>(k, pu[i], gm, xh);
+        if constexpr (HEAD) {
+          float act[8];
+          plain_compute<HEAD>(k, pu[i], gm, xh, act);
+          if (head_grads) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s3[j] = fmaf(pu[i].dl, act[j], s3[j]);
+            sb += pu[i].dl;
+          }
+        } else {
+          plain_compute<HEAD>(k, pu[i], gm, xh);
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) { s1[j] += gm[j]; s2[j] = fmaf(gm[j], xh[j], s2[j]); }
       }
@@ -598,6 +629,16 @@ __global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(REGS) bn_bwd_reduce
         }
       }
     }
+    if (head_grads) {
+#pragma unroll
+      for (int o = 16; o >= 8; o >>= 1) {
+        if (o >= cg) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s3[j] += __shfl_xor_sync(0xffffffffu, s3[j], o);
+          sb += __shfl_xor_sync(0xffffffffu, sb, o);
+        }
+      }
+    }
     rows_per_block = kBnBwdThreads / 32;
     my_row = threadIdx.x >> 5;
     writer = (threadIdx.x & 31) < cg;
@@ -614,7 +655,9 @@ __global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(REGS) bn_bwd_reduce
     for (int j = 0; j < 8; ++j) {
       a.partial[(size_t)(g * 8 + j) * rows_total + r] = s1[j];
       a.partial[(size_t)(a.C + g * 8 + j) * rows_total + r] = s2[j];
+      if (head_grads) a.partial[(size_t)(2 * a.C + g * 8 + j) * rows_total + r] = s3[j];
     }
+    if (head_grads && g == 0) a.partial[(size_t)(3 * a.C) * rows_total + r] = sb;
   }
 }
 
@@ -622,26 +665,42 @@ __global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(REGS) bn_bwd_reduce
 // partials of rows t, t+256, ... (contiguous in the channel-major layout) in fp64; warps and then the 8 warp sums are
 // combined in a fixed order (deterministic).
 __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(BnBwdArgs a, int rows) {
-  __shared__ double st[2][8];
+  __shared__ double st[4][8];
   const int c = blockIdx.x;
   const float* p1 = a.partial + (size_t)c * rows;
   const float* p2 = a.partial + (size_t)(a.C + c) * rows;
-  double t1 = 0.0, t2 = 0.0;
+  // the 1x1 head's parameter gradients ride along (HEAD reduce only): channel c's weight gradient, and block 0 the bias
+  const bool head = a.head_dlogits != nullptr && (a.head_grad_w != nullptr || a.head_grad_b != nullptr);
+  const float* p3 = a.partial + (size_t)(2 * a.C + c) * rows;
+  const float* p4 = a.partial + (size_t)(3 * a.C) * rows;
+  double t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0;
   for (int r = threadIdx.x; r < rows; r += 256) {
     t1 += (double)__ldg(p1 + r);
     t2 += (double)__ldg(p2 + r);
+    if (head) {
+      t3 += (double)__ldg(p3 + r);
+      if (c == 0) t4 += (double)__ldg(p4 + r);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     t1 += __shfl_xor_sync(0xffffffffu, t1, o);
     t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+    t3 += __shfl_xor_sync(0xffffffffu, t3, o);
+    t4 += __shfl_xor_sync(0xffffffffu, t4, o);
   }
-  if ((threadIdx.x & 31) == 0) { st[0][threadIdx.x >> 5] = t1; st[1][threadIdx.x >> 5] = t2; }
+  if ((threadIdx.x & 31) == 0) {
+    st[0][threadIdx.x >> 5] = t1; st[1][threadIdx.x >> 5] = t2; st[2][threadIdx.x >> 5] = t3; st[3][threadIdx.x >> 5] = t4;
+  }
   __syncthreads();
   if (threadIdx.x != 0) return;
-  t1 = t2 = 0.0;
+  t1 = t2 = t3 = t4 = 0.0;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) { t1 += st[0][k]; t2 += st[1][k]; }
+  for (int k = 0; k < 8; ++k) { t1 += st[0][k]; t2 += st[1][k]; t3 += st[2][k]; t4 += st[3][k]; }
+  if (head) {
+    if (a.head_grad_w) a.head_grad_w[c] = (float)t3;
+    if (c == 0 && a.head_grad_b) *a.head_grad_b = (float)t4;
+  }
   const double inv_n = 1.0 / ((double)a.B * a.H * a.W);
   a.c1[c] = (float)(t1 * inv_n);
   a.c2[c] = (float)(t2 * inv_n);
@@ -658,7 +717,7 @@ cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t s) {
     if (a.head_dlogits) return cudaErrorInvalidValue;
     bn_bwd_reduce_kernel<true, false, 1, 128><<<grid, kBnBwdThreads, 0, s>>>(a);
   } else if (a.head_dlogits) {
-    bn_bwd_reduce_kernel<false, true, 6, 128><<<grid, kBnBwdThreads, 0, s>>>(a);
+    bn_bwd_reduce_kernel<false, true, 5, 128><<<grid, kBnBwdThreads, 0, s>>>(a);
   } else {
     bn_bwd_reduce_kernel<false, false, 4, 104><<<grid, kBnBwdThreads, 0, s>>>(a);
   }

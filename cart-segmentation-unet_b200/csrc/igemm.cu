@@ -1171,7 +1171,166 @@ static cudaError_t launch_wg(const WgradParams& p, cudaStream_t stream) {
   return launched();
 }
 
+// =============================================================================================
+//                     weight gradient of a 3x3 convolution with Cout == 64: nine taps per CTA
+// =============================================================================================
+// wgrad_gemm_kernel puts Cout on the M = 128 rows: with Cout = 64 half of every MMA is wasted, and its three horizontal
+// taps live in three CTAs that each re-read dY and an 8 x 18 patch of X (the kernel runs at the L2 -> SM bandwidth cap).
+// Here the roles are swapped: D[(tap, cin)][cout] = sum_pixels X[pixel + tap, cin] * dY[pixel, cout].  ONE (8+2) x (16+2)
+// patch of X serves all nine taps (tap (r, g) = row offset r*10 + g, row-group stride 1280 B — cf. conv3_gemm_kernel); an
+// M = 128 MMA covers two taps (the second 64-row block is the same patch `LBO` bytes further: +128 B = next horizontal tap,
+// +1280 B = next vertical tap), so nine taps are five MMAs per 16-pixel K-step (the last with a duplicated block), N = 64.
+// Per 128-pixel tile: 39 KB of loads for 9 taps x 64 x 64 outputs, instead of 3 x 34 KB.
+template <int STAGES>
+struct Wg9Layout {
+  static constexpr int kDY = 16 * kAtomBytes;                     // 128 pixels x 64 output channels
+  static constexpr int kXPatch = 18 * 10 * 128;
+  static constexpr int kX = (kXPatch + 1023) & ~1023;
+  static constexpr int kStageSz = kDY + kX;
+  static constexpr int kBar = STAGES * kStageSz;
+  static constexpr int kNumBar = 2 * STAGES + 1;
+  static constexpr int kTmemPtr = kBar + kNumBar * 8;
+  static constexpr int kTotal = kTmemPtr + 16;
+  static constexpr int kDyn = kTotal + 1024;
+  static constexpr int kTmemCols = 512;                           // five 64-column accumulators
+};
+
+template <int STAGES>
+__global__ void __launch_bounds__(kThreads, 1) wgrad9_gemm_kernel(const __grid_constant__ WgradParams p) {
+  using L = Wg9Layout<STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kBar);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtr);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // work item: blockIdx = split * n_blocks + nb   (nb = 64-channel block of Cin)
+  const int nb = blockIdx.x % p.n_blocks;
+  const int split = blockIdx.x / p.n_blocks;
+  const int total_tiles = p.tiles_w * p.tiles_h * p.batch;
+  const int t_begin = (int)(((long long)total_tiles * split) / p.splits);
+  const int t_end = (int)(((long long)total_tiles * (split + 1)) / p.splits);
+  const int per_img = p.tiles_w * p.tiles_h;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&p.tmapDY[0]);
+    tma_prefetch_desc(&p.tmapX9);
+  }
+  if (warp == 2) tmem_alloc<L::kTmemCols>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    int s = 0, ph = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      const int b = t / per_img, rem = t - b * per_img;
+      const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
+      const int w0 = tw * 8, h0 = th * 16;
+      mbar_wait(&empty[s], ph ^ 1);
+      if (lane == 0) {
+        uint8_t* st = smem + s * L::kStageSz;
+        mbar_arrive_expect_tx(&full[s], L::kDY + L::kXPatch);
+        tma_load_4d(st, &p.tmapDY[0], &full[s], p.dy_chan0, w0, h0, b);
+        tma_load_4d(st + L::kDY, &p.tmapX9, &full[s], p.x_chan0 + nb * 64, w0 - 1, h0 - 1, b);
+      }
+      __syncwarp();
+      if (++s == STAGES) { s = 0; ph ^= 1; }
+    }
+  } else if (warp == 1) {
+    // A = X patch (MN-major: rows = pixels, 64 input channels per 128-byte row), M = 128 = two taps; B = dY (MN-major).
+    constexpr uint32_t idesc = make_idesc(128, 64, 1, 1);
+    constexpr uint32_t a_hi = ((uint32_t)(10 * 128) >> 4) | (1u << 14) | (2u << 29);   // SBO = one patch row group
+    constexpr uint32_t b_hi = kDescHiSw128;
+    const uint32_t base = smem_u32(smem) >> 4;
+    // accumulator q: first tap (r, g) and the distance to the second one
+    //   q0..q2: (r, 0) + (r, 1)   LBO = 128 B      q3: (0, 2) + (1, 2)   LBO = 1280 B      q4: (2, 2), duplicated (LBO = 0)
+    int s = 0, ph = 0;
+    uint32_t accumulate = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      const uint32_t dy_lo = (base + (uint32_t)(s * (L::kStageSz >> 4))) | ((1024u >> 4) << 16);
+      const uint32_t x_lo = base + (uint32_t)((s * L::kStageSz + L::kDY) >> 4);
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        const uint32_t row0 = q < 3 ? (uint32_t)(q * 10) : (q == 3 ? 2u : 22u);
+        const uint32_t lbo = q < 3 ? 128u : (q == 3 ? 1280u : 0u);
+        // eight K-steps of 16 pixels: two image rows of the patch (2 x 1280 B) / of the dY tile (2 x 1024 B) per step
+        umma_bf16_steps8_warp_ab<2 * 1280 / 16, 2 * 1024 / 16>(tmem_base + q * 64, (x_lo + row0 * 8u) | ((lbo >> 4) << 16), a_hi,
+                                                               dy_lo, b_hi, idesc, accumulate);
+      }
+      accumulate = 1;
+      umma_commit_warp<false>(&empty[s]);
+      if (++s == STAGES) { s = 0; ph ^= 1; }
+    }
+    umma_commit_warp<false>(tmem_full);
+  } else {
+    const int sub = warp & 3;
+    const int row = sub * 32 + lane;           // accumulator row = (which tap of the pair) * 64 + input channel
+    const int half = row >> 6, cin = row & 63;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    if (t_end > t_begin) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16);
+#pragma unroll 1
+      for (int q = 0; q < 5; ++q) {
+        // packed tap index = g * 3 + r
+        int r, g;
+        if (q < 3) { r = q; g = half; }
+        else if (q == 3) { r = half; g = 2; }
+        else { r = 2; g = 2; }
+        const bool live = !(q == 4 && half == 1);
+        float* dst = p.dw + ((size_t)(g * 3 + r) * p.Mtot) * p.Ntot + nb * 64 + cin;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + q * 64 + c0, v);
+          tmem_ld_wait();
+          if (live) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + (size_t)(c0 + i) * p.Ntot), "f"(__uint_as_float(v[i])) : "memory");
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<L::kTmemCols>(tmem_base);
+  }
+}
+
+static cudaError_t launch_wgrad9(const WgradParams& p, cudaStream_t stream) {
+  constexpr int STAGES = 5;
+  using L = Wg9Layout<STAGES>;
+  static_assert(L::kDyn <= 232448, "shared memory budget exceeded");
+  auto kern = wgrad9_gemm_kernel<STAGES>;
+  static std::atomic<unsigned long long> attr_done{0};
+  {
+    cudaError_t ae = ensure_dynamic_smem(kern, L::kDyn, attr_done);
+    if (ae != cudaSuccess) return ae;
+  }
+  if (p.Mtot != 64 || p.G != 3 || p.R != 3) return cudaErrorInvalidValue;
+  const int grid = p.n_blocks * p.splits;
+  if (grid <= 0) return cudaSuccess;
+  kern<<<grid, kThreads, L::kDyn, stream>>>(p);
+  return launched();
+}
+
 cudaError_t launch_wgrad_gemm(const WgradParams& p, int block_n, cudaStream_t stream) {
+  if (p.nine) return launch_wgrad9(p, stream);
   switch (block_n) {
     case 64: return launch_wg<64, 4>(p, stream);
     case 128: return launch_wg<128, 3>(p, stream);

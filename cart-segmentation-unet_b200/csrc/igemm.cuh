@@ -66,6 +66,9 @@ struct WgradParams {
   int tiles_w, tiles_h, batch;
   int splits;              // split-K factor over pixel tiles
   float* dw;               // [G*R][Mtot][Ntot] fp32, accumulated atomically
+  // wgrad9_gemm_kernel (3x3 convolutions with Cout == 64): all nine taps in one CTA from ONE (8+2) x (16+2) patch of X
+  int nine;                // 1: use wgrad9_gemm_kernel with tmapX9
+  CUtensorMap tmapX9;      // box (64 ch, 10, 18, 1)
 };
 
 cudaError_t launch_wgrad_gemm(const WgradParams& p, int block_n, cudaStream_t stream);

@@ -66,7 +66,11 @@ cudaError_t launch_bn_fold_eval(const BnFoldBatch& a, cudaStream_t s);
 // out[p][out_c0 + c] = relu(y[p][c]*scale[c] + shift[c]); optional 2x2 max-pooled copy (pitch C)
 // head.logits != NULL (last layer, C == 64, no pooling): the 1x1 head is evaluated in the same pass,
 // logits[p] = sum_c out[p][c] * w[c] + b  on the bf16 values as stored.
-struct HeadFwd { const float* w; const float* b; float* logits; };
+struct HeadFwd { const float* w; const float* b; float* logits; int skip_store; };   // skip_store: `out` is not written
+// out[p][c] = relu(y[p][c] * scale[c] + shift[c]) from the coefficients a training forward published (test hook:
+// materialises the last layer's activation, which the training path never stores)
+cudaError_t launch_bn_apply_relu(const bf16* y, long long P, int C, const float* scale, const float* shift, bf16* out,
+                                 cudaStream_t s);
 cudaError_t launch_bn_relu(const bf16* y, int B, int H, int W, int C, const BnFinalizeArgs& fin, bf16* out,
                            int out_pitch, int out_c0, bf16* pooled, const HeadFwd& head, cudaStream_t s);
 // relu/bn already applied (eval path): plain 2x2 max-pool of in[p][c0 + c] (pitch in_pitch) -> pooled (pitch C)
@@ -77,6 +81,9 @@ struct BnBwdArgs {
   const bf16* g; int g_pitch, g_c0;        // gradient w.r.t. the post-ReLU activation
   const float* head_dlogits;               // optional (no pooling): g[p][c] = bf16(head_dlogits[p] * head_w[c]) instead of `g`
   const float* head_w;
+  float* head_grad_w; float* head_grad_b;  // optional with head_dlogits: the 1x1 head's parameter gradients
+                                           //   grad_w[c] = sum_p dlogits[p] * act[p][c], grad_b = sum_p dlogits[p]
+                                           //   (act recomputed from y: the head's input is never stored)
   const bf16* g_pool;                      // optional: gradient w.r.t. the 2x2-pooled activation (pitch C)
   const bf16* y;                           // raw conv output (pitch C)
   const float* scale; const float* shift; const float* mean; const float* invstd;

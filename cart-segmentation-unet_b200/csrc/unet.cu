@@ -117,6 +117,7 @@ static int env_int(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 static int conv3_enabled() { static const int v = env_int("CARTSEG_CONV3", 1); return v; }
+static int wgrad9_enabled() { static const int v = env_int("CARTSEG_WGRAD9", 1); return v; }
 // TMA map over an NHWC buffer with a (64, pw, 18, 1) box: the whole halo patch of an 8 x 16 pixel tile.
 static int nhwc_patch_map(CUtensorMap* m, const bf16* base, int pitch, int B, int H, int W, int pw);
 
@@ -262,6 +263,12 @@ static int build_conv3x3_wgrad(WgradParams& p, int* block_n, View x, int Cin, Vi
   p.x_chan0 = x.c0;
   CS_TRY(nhwc_map(&p.tmapDY[0], dy.p, dy.pitch, B, H, W, 16));
   CS_TRY(nhwc_map(&p.tmapX[0], x.p, x.pitch, B, H, W, 18));
+  if (Cout == 64 && wgrad9_enabled()) {                  // all nine taps per CTA from one 10 x 18 patch (wgrad9_gemm_kernel)
+    p.nine = 1;
+    p.n_blocks = Cin / 64;
+    p.splits = choose_wgrad_splits(p.n_blocks, p.tiles_w * p.tiles_h * B, 148);
+    CS_TRY(nhwc_patch_map(&p.tmapX9, x.p, x.pitch, B, H, W, 10));
+  }
   return 0;
 }
 // dW[co][k] = sum_pixels dy[pixel, co] * col[pixel, k]   (first conv on its im2col matrix)
@@ -350,6 +357,12 @@ struct cs_unet_plan {
   cudaStream_t s_hi, s_lo;
   cudaEvent_t ev_fork, ev_hi, ev_lo, ev_stage[CS_UNET_NUM_BWD_STAGES];
   bool profiling, no_overlap, deferred_join, join_pending;
+  // weight-gradient GEMMs held back until the main stream reaches the encoder's high-resolution levels (see
+  // cs_unet_backward): (kind 1 conv / 2 up, layer index, gradient pointers of that launch)
+  struct HeldWgrad { int kind, idx, stage; float* gw; float* gb; };
+  std::vector<HeldWgrad> held;
+  std::vector<HeldWgrad> late;     // wgrads of dconvL.0 that wait for the conv-transpose dgrad right after them
+  cudaEvent_t ev_flush;
   std::vector<cudaEvent_t> prof_events;   // pairs (begin, end)
   std::vector<int> prof_class;
   std::vector<double> prof_flops;
@@ -363,7 +376,7 @@ struct cs_unet_plan {
 
 namespace {
 // kernel classes reported by cs_unet_profile_read
-enum { kClsPix256 = 0, kClsPix128, kClsPix64, kClsWgrad128, kClsWgrad64, kClsConv256, kClsConv128, kClsConv64, kNumCls };
+enum { kClsPix256 = 0, kClsPix128, kClsPix64, kClsWgrad128, kClsWgrad64, kClsConv256, kClsConv128, kClsConv64, kClsWgrad9, kNumCls };
 static_assert(kNumCls == CS_UNET_NUM_PROFILE_CLASSES, "profile classes");
 int pix_class(int bn) { return bn == 256 ? kClsPix256 : (bn == 128 ? kClsPix128 : kClsPix64); }
 // 3x3 convolutions run on conv3_gemm_kernel unless CARTSEG_CONV3=0
@@ -372,6 +385,7 @@ int conv_class(const PixGemmParams& p, int bn) {
   return bn == 256 ? kClsConv256 : (bn == 128 ? kClsConv128 : kClsConv64);
 }
 int wgrad_class(int bn) { return bn == 128 ? kClsWgrad128 : kClsWgrad64; }
+int wgrad_class(const WgradParams& w, int bn) { return w.nine ? kClsWgrad9 : wgrad_class(bn); }
 
 // Runs `launch` between two events on `s` when profiling is on.
 template <typename F>
@@ -630,6 +644,7 @@ void cs_unet_plan_destroy(cs_unet_plan* plan) {
     cudaEventDestroy(plan->ev_fork);
     cudaEventDestroy(plan->ev_hi);
     cudaEventDestroy(plan->ev_lo);
+    cudaEventDestroy(plan->ev_flush);
     for (cudaEvent_t e : plan->ev_stage) cudaEventDestroy(e);
   }
   delete plan;
@@ -727,7 +742,9 @@ int cs_unet_forward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* x, 
       f.momentum = 0.1f; f.eps = 1e-5f;
       f.scale = c.scale; f.shift = c.shift; f.mean = c.mean; f.invstd = c.invstd; f.C = c.cout;
       // the last layer's pass also evaluates the 1x1 head (final_conv) on the activations it has just produced
-      const HeadFwd head = (i == 17 && fuse_head()) ? HeadFwd{t->param[80], t->param[81], logits} : HeadFwd{nullptr, nullptr, nullptr};
+      // — and does not store them at all: nothing reads the head's input in the training path (the BN backward of this
+      // layer recomputes it from y for the head's weight gradient), 0.4 GB less traffic at K2
+      const HeadFwd head = (i == 17 && fuse_head()) ? HeadFwd{t->param[80], t->param[81], logits, 1} : HeadFwd{nullptr, nullptr, nullptr, 0};
       CS_CUDA(launch_bn_relu(c.y, B, c.H, c.W, c.cout, f, c.out.p, c.out.pitch, c.out.c0, c.pooled, head, s));
     } else {
       CS_CUDA(timed(pl, conv_class(c.fp_eval, c.bn_f), c.flops, s, [&] { return launch_pix_gemm(c.fp_eval, c.bn_f, pl->num_sms, s); }));
@@ -768,10 +785,16 @@ static void stage_decode(int stage, int* kind, int* idx) {
 
 int cs_unet_stage_params(int stage, int* out_indices, int capacity) {
   if (stage < 0 || stage >= CS_UNET_NUM_BWD_STAGES) return fail("stage %d out of range", stage);
-  int kind, idx, n = 0, tmp[4];
+  int kind, idx, n = 0, tmp[6];
   stage_decode(stage, &kind, &idx);
-  if (kind == 0) { tmp[0] = 80; tmp[1] = 81; n = 2; }
-  else if (kind == 1) { const int pb = conv_param_base(idx); for (int j = 0; j < 4; ++j) tmp[j] = pb + j; n = 4; }
+  // the head's parameter gradients are produced by the BN-backward reduction of dconv1.3 (stage 1) unless the
+  // stand-alone head kernels are selected (CARTSEG_FUSE_HEAD=0)
+  if (kind == 0) { if (!fuse_head()) { tmp[0] = 80; tmp[1] = 81; n = 2; } }
+  else if (kind == 1) {
+    const int pb = conv_param_base(idx);
+    if (idx == 17 && fuse_head()) { tmp[n++] = 80; tmp[n++] = 81; }
+    for (int j = 0; j < 4; ++j) tmp[n++] = pb + j;
+  }
   else { tmp[0] = 40 + 2 * idx; tmp[1] = 41 + 2 * idx; n = 2; }
   for (int j = 0; j < n && j < capacity; ++j) out_indices[j] = tmp[j];
   return n;
@@ -800,9 +823,93 @@ static int ensure_streams(cs_unet_plan* pl) {
   CS_CUDA(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
   CS_CUDA(cudaEventCreateWithFlags(&pl->ev_hi, cudaEventDisableTiming));
   CS_CUDA(cudaEventCreateWithFlags(&pl->ev_lo, cudaEventDisableTiming));
+  CS_CUDA(cudaEventCreateWithFlags(&pl->ev_flush, cudaEventDisableTiming));
   for (int i = 0; i < CS_UNET_NUM_BWD_STAGES; ++i)
     CS_CUDA(cudaEventCreateWithFlags(&pl->ev_stage[i], cudaEventDisableTiming));
   return 0;
+}
+
+// Which weight-gradient GEMMs are held back, and until when.  Two one-CTA-per-SM persistent GEMM kernels cannot share an
+// SM, so a tensor-bound wgrad issued next to the tensor-bound dgrads of the deep levels only time-slices with them — and
+// because CTAs are not preemptible, every dgrad that becomes ready while a wgrad wave is resident waits for it (the
+// round-1 timeline shows the conv-transpose dgrads taking 0.23-0.67 ms instead of 0.07-0.15 ms).  The HBM-bound
+// BatchNorm-backward passes of the high-resolution encoder levels at the END of the backward pass, on the other hand,
+// do share SMs with a resident wgrad CTA (no shared memory, <= 104 registers) and leave the tensor pipe idle.  So the
+// deep, HBM-light wgrads (levels 3-5: conv 4..13, upconv4/3) CAN be enqueued only when the main stream reaches conv
+// `flush_conv` (CARTSEG_DEFER_WGRAD=1, CARTSEG_DEFER_FLUSH_CONV=n).  Measured on B200 (round 2, k2,
+// profiles/r2_k2_backward_timeline_deferred.txt): the main stream then finishes at 10.1 ms instead of 11.4 ms — every
+// conv-transpose dgrad runs in 0.07 ms — but the held wgrads run 1.6-2.5x slower next to the BatchNorm passes they were
+// meant to hide under (one issuing warp against 16 memory-bound warps per SM) and nine of them are still queued when the
+// main stream ends: 11.60 ms either way, step 18.08 vs 17.93 ms.  Default OFF.
+static bool defer_enabled() { static const int v = env_int("CARTSEG_DEFER_WGRAD", 0); return v != 0; }
+static int defer_flush_conv() { static const int v = env_int("CARTSEG_DEFER_FLUSH_CONV", 5); return v; }
+static bool held_conv(int idx) { return defer_enabled() && idx >= 4 && idx <= 13 && idx > defer_flush_conv(); }
+static bool held_up(int k) { return defer_enabled() && k <= 1; }
+// Priority inversion at the conv-transposes: dgrad(dconvL.0) is followed at once by the short conv-transpose dgrad, but the
+// one-wave wgrad of dconvL.0 (0.3-0.6 ms, not preemptible) takes the SMs as the conv dgrad drains, and the conv-transpose
+// dgrad waits for it (round-1 timeline: 0.23-0.67 ms instead of 0.07-0.15 ms).  With CARTSEG_WGRAD_AFTER_UP=1 (default)
+// those four wgrads, and the conv-transpose's own wgrad / bias sum, are enqueued behind the conv-transpose dgrad: they
+// start when the next BatchNorm-backward passes do.
+static bool after_up_enabled() { static const int v = env_int("CARTSEG_WGRAD_AFTER_UP", 1); return v != 0; }
+static bool late_conv(int idx) { return after_up_enabled() && idx >= 10 && idx % 2 == 0; }
+
+static int launch_conv_wgrad(cs_unet_plan* pl, int idx, float* gw, cudaStream_t sw) {
+  ConvL& c = pl->conv[idx];
+  const size_t e = (size_t)(idx == 0 ? 1 : 9) * c.cout * c.cin;
+  CS_CUDA(cudaMemsetAsync(pl->dwp, 0, e * sizeof(float), sw));
+  CS_CUDA(traced(pl, 400 + idx, sw, [&] { return timed(pl, wgrad_class(c.wg, c.bn_w), c.flops, sw, [&] { return launch_wgrad_gemm(c.wg, c.bn_w, sw); }); }));
+  if (idx == 0) CS_CUDA(launch_unpack_first(pl->dwp, c.cout, pl->Cin, gw, sw));
+  else CS_CUDA(launch_unpack_pairs(pl->dwp, c.cout, c.cin, 9, kTapWgrad, gw, sw));
+  return 0;
+}
+static int launch_up_wgrad(cs_unet_plan* pl, int idx, float* gw, float* gb, cudaStream_t sw) {
+  UpL& u = pl->up[idx];
+  if (gb) CS_CUDA(traced(pl, 900 + idx, sw, [&] { return launch_channel_sum(u.g_out.p, u.g_out.pitch, u.g_out.c0, 4 * u.P, u.cout, gb, sw); }));
+  if (gw) {
+    CS_CUDA(cudaMemsetAsync(pl->dwp, 0, (size_t)4 * u.cin * u.cout * sizeof(float), sw));
+    CS_CUDA(traced(pl, 800 + idx, sw, [&] { return timed(pl, wgrad_class(u.bn_w), u.flops, sw, [&] { return launch_wgrad_gemm(u.wg, u.bn_w, sw); }); }));
+    CS_CUDA(launch_unpack_pairs(pl->dwp, u.cin, u.cout, 4, kTapIdent, gw, sw));
+  }
+  return 0;
+}
+// Enqueue everything that was held back: the side stream first waits for the main stream's current position.
+static int flush_held(cs_unet_plan* pl, cudaStream_t s, cudaStream_t sw, bool overlap) {
+  if (pl->held.empty()) return 0;
+  if (overlap) {
+    CS_CUDA(cudaEventRecord(pl->ev_flush, s));
+    CS_CUDA(cudaStreamWaitEvent(sw, pl->ev_flush, 0));
+  }
+  for (const cs_unet_plan::HeldWgrad& h : pl->held) {
+    if (h.kind == 1) CS_TRY(launch_conv_wgrad(pl, h.idx, h.gw, sw));
+    else CS_TRY(launch_up_wgrad(pl, h.idx, h.gw, h.gb, sw));
+  }
+  pl->held.clear();
+  return 0;
+}
+
+// The side stream waits for the main stream's current position, then runs the wgrads in `late` (always on two streams).
+static int flush_late(cs_unet_plan* pl, cudaStream_t s, cudaStream_t sw, cudaEvent_t ev) {
+  CS_CUDA(cudaEventRecord(ev, s));
+  CS_CUDA(cudaStreamWaitEvent(sw, ev, 0));
+  for (const cs_unet_plan::HeldWgrad& h : pl->late) CS_TRY(launch_conv_wgrad(pl, h.idx, h.gw, sw));
+  pl->late.clear();
+  return 0;
+}
+
+int cs_unet_backward_held_stages(int* flush_stage, int* stages, int capacity) {
+  // stages whose weight gradients are final only after stage `*flush_stage` has been enqueued (or after the last stage)
+  int n = 0;
+  *flush_stage = CS_UNET_NUM_BWD_STAGES - 1;
+  for (int st = 0; st < CS_UNET_NUM_BWD_STAGES; ++st) {
+    int kind, idx;
+    stage_decode(st, &kind, &idx);
+    if ((kind == 1 && held_conv(idx)) || (kind == 2 && held_up(idx))) {
+      if (n < capacity) stages[n] = st;
+      ++n;
+    }
+    if (kind == 1 && idx == defer_flush_conv()) *flush_stage = st;
+  }
+  return n;
 }
 
 int cs_unet_backward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* dlogits, int stage_begin, int stage_end,
@@ -838,15 +945,17 @@ int cs_unet_backward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* dl
         CS_CUDA(launch_head_bwd(last.out.p, dlogits, last.P, 64, t->param[80], last.g_out.p, t->grad[80], t->grad[81], s));
         continue;
       }
+      // The head's parameter gradients come out of the BN-backward reduction of the last layer (stage 1), which
+      // recomputes the head's input from y: nothing to launch here.
       if (overlap) {
         CS_CUDA(cudaEventRecord(pl->ev_stage[stage], s));
         CS_CUDA(cudaStreamWaitEvent(sw, pl->ev_stage[stage], 0));
       }
-      CS_CUDA(traced(pl, 600, sw, [&] { return launch_head_bwd(last.out.p, dlogits, last.P, 64, t->param[80], nullptr, t->grad[80], t->grad[81], sw); }));
       CS_CUDA(cudaMemcpyAsync(pl->dlogits_keep, dlogits, (size_t)last.P * sizeof(float), cudaMemcpyDeviceToDevice, sw));
       pl->head_w_keep = t->param[80];
     } else if (kind == 1) {
       ConvL& c = pl->conv[idx];
+      if (idx == defer_flush_conv()) CS_TRY(flush_held(pl, s, sw, overlap));
       if (idx < frozen_encoder_convs) continue;          // nothing below a frozen prefix needs gradients
       BnBwdArgs a{};
       a.g = c.g_out.p; a.g_pitch = c.g_out.pitch; a.g_c0 = c.g_out.c0;
@@ -854,6 +963,7 @@ int cs_unet_backward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* dl
       if (idx == 17 && fuse_head()) {
         if (!dlogits) return fail("dlogits is null");
         a.head_dlogits = dlogits; a.head_w = t->param[80];
+        a.head_grad_w = t->grad[80]; a.head_grad_b = t->grad[81];
       }
       a.scale = c.scale; a.shift = c.shift; a.mean = c.mean; a.invstd = c.invstd;
       a.partial = pl->bn_partial; a.c1 = c.bc1; a.c2 = c.bc2; a.dy = c.dy;
@@ -862,15 +972,17 @@ int cs_unet_backward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* dl
       CS_CUDA(traced(pl, 100 + idx, s, [&] { return launch_bn_bwd_reduce(a, s); }));
       CS_CUDA(traced(pl, 200 + idx, s, [&] { return launch_bn_bwd_apply(a, s); }));
       if (t->grad[c.pw]) {
-        if (overlap) {                                    // dy is final: the wgrad may start on the side stream
-          CS_CUDA(cudaEventRecord(pl->ev_stage[stage], s));
-          CS_CUDA(cudaStreamWaitEvent(sw, pl->ev_stage[stage], 0));
+        if (overlap && held_conv(idx)) {
+          pl->held.push_back(cs_unet_plan::HeldWgrad{1, idx, stage, t->grad[c.pw], nullptr});
+        } else if (overlap && late_conv(idx)) {
+          pl->late.push_back(cs_unet_plan::HeldWgrad{1, idx, stage, t->grad[c.pw], nullptr});
+        } else {
+          if (overlap) {                                  // dy is final: the wgrad may start on the side stream
+            CS_CUDA(cudaEventRecord(pl->ev_stage[stage], s));
+            CS_CUDA(cudaStreamWaitEvent(sw, pl->ev_stage[stage], 0));
+          }
+          CS_TRY(launch_conv_wgrad(pl, idx, t->grad[c.pw], sw));
         }
-        const size_t e = (size_t)(idx == 0 ? 1 : 9) * c.cout * c.cin;
-        CS_CUDA(cudaMemsetAsync(pl->dwp, 0, e * sizeof(float), sw));
-        CS_CUDA(traced(pl, 400 + idx, sw, [&] { return timed(pl, wgrad_class(c.bn_w), c.flops, sw, [&] { return launch_wgrad_gemm(c.wg, c.bn_w, sw); }); }));
-        if (idx == 0) CS_CUDA(launch_unpack_first(pl->dwp, c.cout, pl->Cin, t->grad[c.pw], sw));
-        else CS_CUDA(launch_unpack_pairs(pl->dwp, c.cout, c.cin, 9, kTapWgrad, t->grad[c.pw], sw));
       }
       // Decoder convs always run their dgrad: it is the only writer of the concat-gradient buffer that the conv-transpose
       // weight / bias gradients read.  An encoder conv needs it only if something below it still trains.
@@ -878,21 +990,28 @@ int cs_unet_backward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* dl
         CS_CUDA(traced(pl, 300 + idx, s, [&] { return timed(pl, conv_class(c.dg, c.bn_d), c.flops, s, [&] { return launch_pix_gemm(c.dg, c.bn_d, pl->num_sms, s); }); }));
     } else {
       UpL& u = pl->up[idx];
-      if (overlap && (t->grad[u.pb] || t->grad[u.pw])) {  // g_out of the conv-transpose is final on the main stream
-        CS_CUDA(cudaEventRecord(pl->ev_stage[stage], s));
-        CS_CUDA(cudaStreamWaitEvent(sw, pl->ev_stage[stage], 0));
-      }
-      if (t->grad[u.pb]) CS_CUDA(traced(pl, 900 + idx, sw, [&] { return launch_channel_sum(u.g_out.p, u.g_out.pitch, u.g_out.c0, 4 * u.P, u.cout, t->grad[u.pb], sw); }));
-      if (t->grad[u.pw]) {
-        CS_CUDA(cudaMemsetAsync(pl->dwp, 0, (size_t)4 * u.cin * u.cout * sizeof(float), sw));
-        CS_CUDA(traced(pl, 800 + idx, sw, [&] { return timed(pl, wgrad_class(u.bn_w), u.flops, sw, [&] { return launch_wgrad_gemm(u.wg, u.bn_w, sw); }); }));
-        CS_CUDA(launch_unpack_pairs(pl->dwp, u.cin, u.cout, 4, kTapIdent, t->grad[u.pw], sw));
+      const bool want = t->grad[u.pb] || t->grad[u.pw];
+      const bool after = overlap && after_up_enabled();   // side-stream work of this stage goes behind the dgrad
+      if (want && overlap && held_up(idx)) {
+        pl->held.push_back(cs_unet_plan::HeldWgrad{2, idx, stage, t->grad[u.pw], t->grad[u.pb]});
+      } else if (want && !after) {
+        if (overlap) {                                    // g_out of the conv-transpose is final on the main stream
+          CS_CUDA(cudaEventRecord(pl->ev_stage[stage], s));
+          CS_CUDA(cudaStreamWaitEvent(sw, pl->ev_stage[stage], 0));
+        }
+        CS_TRY(launch_up_wgrad(pl, idx, t->grad[u.pw], t->grad[u.pb], sw));
       }
       // upconv4's input gradient only feeds conv5.3: nothing reads it when the whole encoder is frozen
       if (!(idx == 0 && frozen_encoder_convs >= 10))
         CS_CUDA(traced(pl, 700 + idx, s, [&] { return timed(pl, pix_class(u.bn_d), u.flops, s, [&] { return launch_pix_gemm(u.dg, u.bn_d, pl->num_sms, s); }); }));
+      if (after) {
+        CS_TRY(flush_late(pl, s, sw, pl->ev_stage[stage]));
+        if (want && !held_up(idx)) CS_TRY(launch_up_wgrad(pl, idx, t->grad[u.pw], t->grad[u.pb], sw));
+      }
     }
   }
+  if (!pl->late.empty()) CS_TRY(flush_late(pl, s, sw, pl->ev_flush));   // stage range ended between dconvL.0 and its up-conv
+  if (stage_end == CS_UNET_NUM_BWD_STAGES) CS_TRY(flush_held(pl, s, sw, overlap));
   if (overlap) {                                          // join: the caller's stream continues after both
     CS_CUDA(cudaEventRecord(pl->ev_hi, s));
     CS_CUDA(cudaEventRecord(pl->ev_lo, sw));
@@ -911,7 +1030,8 @@ int cs_unet_plan_set_sm_limit(cs_unet_plan* pl, int sms) {
   if (pl->num_sms < 2) pl->num_sms = 2;
   if (!pl->infer) {                                       // the single-wave weight-gradient grids follow the limit too
     auto refit = [&](WgradParams& w) {
-      w.splits = choose_wgrad_splits(w.m_blocks * w.n_blocks * w.G, w.tiles_w * w.tiles_h * w.batch, pl->num_sms);
+      w.splits = choose_wgrad_splits(w.nine ? w.n_blocks : w.m_blocks * w.n_blocks * w.G, w.tiles_w * w.tiles_h * w.batch,
+                                     pl->num_sms);
     };
     for (int i = 0; i < 18; ++i) refit(pl->conv[i].wg);
     for (int k = 0; k < 4; ++k) refit(pl->up[k].wg);
@@ -1018,6 +1138,11 @@ int cs_unet_debug_read(cs_unet_plan* pl, int kind, int index, int dims_out[4], f
   if (dims_out) { dims_out[0] = pl->B; dims_out[1] = C; dims_out[2] = H; dims_out[3] = W; }
   if (!dst) return 0;
   if (!v.p) return fail("tensor (kind %d, index %d) does not exist in this plan", kind, index);
+  if (kind == 1 && index == 17 && fuse_head() && !pl->infer && pl->forward_done) {
+    // the training path never stores the last activation: rebuild it from y and the coefficients the forward published
+    const ConvL& c = pl->conv[17];
+    CS_CUDA(launch_bn_apply_relu(c.y, c.P, c.cout, c.scale, c.shift, c.out.p, static_cast<cudaStream_t>(stream)));
+  }
   if (kind == 3 && index == 17 && fuse_head()) {
     // never written by the training path: materialise dlogits * w from the copies kept by the last backward
     if (!pl->head_w_keep) return fail("no backward pass has run on this plan yet");

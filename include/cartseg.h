@@ -89,7 +89,8 @@ int cs_unet_backward(cs_unet_plan* plan, const cs_unet_tensors* t, const float* 
  * cs_unet_forward / cs_unet_backward is bracketed by CUDA events on the launch stream.  cs_unet_profile_read waits for
  * the recorded events and returns, per kernel class, the summed device time (ms), algorithmic FLOPs (2*MACs) and
  * launch count since the last read.  Classes: 0-2 pix_gemm2_kernel N=256 / 128 / 64 (conv-transposes, the stem),
- * 3-4 wgrad_gemm_kernel N=128 / 64, 5-7 conv3_gemm_kernel N=256 / 128 / 64 (3x3 convolutions, fprop and dgrad). */
+ * 3-4 wgrad_gemm_kernel N=128 / 64, 5-7 conv3_gemm_kernel N=256 / 128 / 64 (3x3 convolutions, fprop and dgrad),
+ * 8 wgrad9_gemm_kernel (3x3 weight gradients with Cout = 64). */
 /* cs_unet_backward runs the weight-gradient GEMMs on an internal lower-priority stream so that they overlap the
  * HBM-bound BatchNorm-backward passes of the following layers (forked from / joined into `stream` with events).
  * cs_unet_set_overlap(plan, 0) serialises everything on the caller's stream (used for per-kernel timing). */
@@ -105,7 +106,12 @@ int cs_unet_set_deferred_join(cs_unet_plan* plan, int enable);
  * CTA has to wait for a second wave (sms <= 0 restores the full device). */
 int cs_unet_plan_set_sm_limit(cs_unet_plan* plan, int sms);
 int cs_unet_backward_wait(cs_unet_plan* plan, cs_stream_t stream);
-#define CS_UNET_NUM_PROFILE_CLASSES 8
+/* The weight-gradient GEMMs of the deep levels are enqueued late (when the main stream reaches the encoder's level-3
+ * stage `*flush_stage`), where they overlap HBM-bound BatchNorm-backward passes instead of time-slicing with tensor-bound
+ * dgrads.  A caller that consumes gradients stage by stage (data parallel) must treat the parameter gradients of the
+ * returned stages as final only once stage `*flush_stage` has been enqueued.  Returns the number of such stages. */
+int cs_unet_backward_held_stages(int* flush_stage, int* stages, int capacity);
+#define CS_UNET_NUM_PROFILE_CLASSES 9
 int cs_unet_profile(cs_unet_plan* plan, int enable);
 int cs_unet_profile_read(cs_unet_plan* plan, int n_classes, double* ms, double* flops, long long* launches);
 /* Developer timeline of cs_unet_backward: while enabled, every launch of the backward pass (both internal streams) is

@@ -28,21 +28,8 @@ OUT = os.path.join(ROOT, "tests", "golden")
 
 
 def lift(relpath: str, names, extra=None):
-    src = open(os.path.join(REF, relpath)).read()
-    tree = ast.parse(src)
-    ns = {"torch": torch, "nn": nn, "np": np, "F": torch.nn.functional}
-    ns.update(extra or {})
-    from scipy.ndimage import distance_transform_edt
-    ns["distance_transform_edt"] = distance_transform_edt
-    got = []
-    for node in tree.body:
-        if isinstance(node, (ast.ClassDef, ast.FunctionDef)) and node.name in names:
-            code = compile(ast.Module(body=[node], type_ignores=[]), relpath, "exec")
-            exec(code, ns)
-            got.append(node.name)
-    missing = set(names) - set(got)
-    assert not missing, f"{relpath}: missing {missing}"
-    return ns
+    from oracle import ref_lift
+    return ref_lift.lift(relpath, names, extra)
 
 
 def lift_with(relpath, names, extra):
@@ -71,6 +58,60 @@ def edge_masks(H, W, seed=0):
     m = np.zeros((H, W), bool); m[2:H - 2, 2:W - 2] = True; m[H // 2 - 2:H // 2 + 2, W // 2 - 3:W // 2 + 3] = False
     ms["box_with_hole"] = m
     return ms
+
+
+def grad_probe(n: int, salt: int) -> torch.Tensor:
+    """Deterministic closed-form probe vector: a gradient tensor is pinned as a whole by its dot product with it."""
+    i = torch.arange(n, dtype=torch.float64)
+    return torch.sin(i * 0.7390851332 + 0.113 * salt) + 0.5 * torch.cos(i * 1.1447298858 + 0.071 * salt)
+
+
+def make_model():
+    """The reference's UNet (src/create_testset.py:40-83) + BCEDiceLoss (train_bce_dice.py:186-199) on seeded inputs:
+    eval / train logits, loss, and for EVERY parameter the gradient norm, its first 8 elements, its projection on a
+    closed-form probe vector (pins the whole tensor) and — for tensors of <= 4096 elements — the full gradient; all BN
+    running statistics in full."""
+    tb = lift("train_bce_dice.py", ["BCEDiceLoss", "dice_metric", "iou_metric"])
+    ct = lift("src/create_testset.py", ["DoubleConv", "UNet"])
+    model = {}
+    for tag, (B, H, W) in {"a": (2, 32, 32), "b": (1, 48, 16), "c": (3, 64, 96)}.items():
+        net = ct["UNet"](in_channels=3, out_channels=1)
+        sd = O.synth_state_dict(seed=1)
+        net.load_state_dict(sd, strict=True)
+        keys = list(net.state_dict().keys())
+        assert keys == [k for k, _ in O.state_dict_spec()], "state-dict key order drifted"
+        x, tgt = O.synth_batch(B, H, W, seed=5)
+
+        def logits_of(n, inp):                        # forward minus the trailing sigmoid (:83)
+            acts = {}
+            hnd = n.final_conv.register_forward_hook(lambda m, i, o: acts.__setitem__("z", o))
+            n(inp)
+            hnd.remove()
+            return acts["z"]
+
+        net.eval()
+        with torch.no_grad():
+            model[f"{tag}_eval_logits"] = logits_of(net, x).numpy()
+        net.train()
+        z = logits_of(net, x)
+        model[f"{tag}_train_logits"] = z.detach().numpy()
+        loss = tb["BCEDiceLoss"]()(z, tgt)
+        loss.backward()
+        model[f"{tag}_train_loss"] = np.float64(loss.item())
+        for j, (k, p) in enumerate(net.named_parameters()):
+            g = p.grad.detach().double()
+            model[f"{tag}_gnorm/{k}"] = np.float64(g.norm().item())
+            model[f"{tag}_ghead/{k}"] = p.grad.detach().flatten()[:8].numpy()
+            model[f"{tag}_gproj/{k}"] = np.float64(torch.dot(g.flatten(), grad_probe(g.numel(), j)).item())
+            if g.numel() <= 4096:
+                model[f"{tag}_gfull/{k}"] = p.grad.detach().numpy()
+        for k, b in net.named_buffers():
+            if k.endswith("running_mean") or k.endswith("running_var"):
+                model[f"{tag}_buf/{k}"] = b.detach().flatten()[:8].numpy()
+                model[f"{tag}_buffull/{k}"] = b.detach().numpy()
+        model[f"{tag}_shape"] = np.array([B, 3, H, W])
+    model["n_params"] = np.int64(sum(p.numel() for p in net.parameters()))
+    np.savez_compressed(os.path.join(OUT, "model.npz"), **model)
 
 
 def load_reference_abl():
@@ -332,43 +373,7 @@ def main():
     losses["sweep13"] = np.array(sw)
     np.savez_compressed(os.path.join(OUT, "losses.npz"), **losses)
 
-    # ---------------- model -------------------------------------------------------------
-    ct = lift("src/create_testset.py", ["DoubleConv", "UNet"])
-    model = {}
-    for tag, (B, H, W) in {"a": (2, 32, 32), "b": (1, 48, 16)}.items():
-        net = ct["UNet"](in_channels=3, out_channels=1)
-        sd = O.synth_state_dict(seed=1)
-        net.load_state_dict(sd, strict=True)
-        keys = list(net.state_dict().keys())
-        assert keys == [k for k, _ in O.state_dict_spec()], "state-dict key order drifted"
-        x, tgt = O.synth_batch(B, H, W, seed=5)
-
-        def logits_of(n, inp):                        # forward minus the trailing sigmoid (:83)
-            acts = {}
-            hnd = n.final_conv.register_forward_hook(lambda m, i, o: acts.__setitem__("z", o))
-            n(inp)
-            hnd.remove()
-            return acts["z"]
-
-        net.eval()
-        with torch.no_grad():
-            model[f"{tag}_eval_logits"] = logits_of(net, x).numpy()
-        net.train()
-        z = logits_of(net, x)
-        model[f"{tag}_train_logits"] = z.detach().numpy()
-        loss = tb["BCEDiceLoss"]()(z, tgt)
-        loss.backward()
-        model[f"{tag}_train_loss"] = np.float64(loss.item())
-        for k, p in net.named_parameters():
-            g = p.grad.detach().double()
-            model[f"{tag}_gnorm/{k}"] = np.float64(g.norm().item())
-            model[f"{tag}_ghead/{k}"] = p.grad.detach().flatten()[:8].numpy()
-        for k, b in net.named_buffers():
-            if k.endswith("running_mean") or k.endswith("running_var"):
-                model[f"{tag}_buf/{k}"] = b.detach().flatten()[:8].numpy()
-        model[f"{tag}_shape"] = np.array([B, 3, H, W])
-    model["n_params"] = np.int64(sum(p.numel() for p in net.parameters()))
-    np.savez_compressed(os.path.join(OUT, "model.npz"), **model)
+    make_model()
     make_abl()
     make_postproc()
     make_preproc()

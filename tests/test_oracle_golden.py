@@ -121,7 +121,7 @@ def test_state_dict_spec_is_136_keys_31M_params(golden_dir):
     assert len(O.param_keys(sd)) == 82
 
 
-@pytest.mark.parametrize("tag", ["a", "b"])
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
 def test_model_forward_backward(golden_dir, tag):
     g = _load(golden_dir, "model.npz")
     B, C, H, W = (int(v) for v in g[f"{tag}_shape"])
@@ -149,6 +149,15 @@ def test_model_forward_backward(golden_dir, tag):
         assert got == pytest.approx(ref, rel=2e-3, abs=1e-7), k
         np.testing.assert_allclose(sd[k].grad.flatten()[:8].numpy(), g[f"{tag}_ghead/{k}"],
                                    rtol=5e-3, atol=1e-6 + 1e-3 * ref / max(1.0, sd[k].numel() ** 0.5))
+        # the whole tensor: projection on the closed-form probe of oracle/make_golden.py (+ full copy of small tensors)
+        from oracle.make_golden import grad_probe
+        probe = grad_probe(sd[k].numel(), keys.index(k))
+        proj = torch.dot(sd[k].grad.double().flatten(), probe).item()
+        assert proj == pytest.approx(float(g[f"{tag}_gproj/{k}"]), abs=2e-3 * ref * probe.norm().item() + 1e-9), k
+        if f"{tag}_gfull/{k}" in g:
+            full = g[f"{tag}_gfull/{k}"]
+            np.testing.assert_allclose(sd[k].grad.numpy(), full, rtol=5e-3, atol=2e-3 * np.abs(full).max() + 1e-9)
     for k in sd:
         if k.endswith("running_mean") or k.endswith("running_var"):
             np.testing.assert_allclose(sd[k].flatten()[:8].numpy(), g[f"{tag}_buf/{k}"], rtol=1e-4, atol=1e-6)
+            np.testing.assert_allclose(sd[k].numpy(), g[f"{tag}_buffull/{k}"], rtol=1e-4, atol=1e-6)

@@ -28,6 +28,14 @@ for part in "$@"; do
     unet)   run test_gpu_unet 1200 python -m pytest tests/test_gpu_unet.py -m gpu -q --tb=short -s --timeout 600 ;;
     layers_old) CARTSEG_CONV3=0 run test_gpu_layers_oldkernel 900 python -m pytest tests/test_gpu_layers.py -m gpu -q --tb=short --timeout 300 ;;
     bench10_old) CARTSEG_CONV3=0 run bench10_old 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extra-workloads ;;
+    bench10_nodefer) CARTSEG_DEFER_WGRAD=0 run bench10_nodefer 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extra-workloads ;;
+    bench10_nofuse) CARTSEG_FUSE_HEAD=0 run bench10_nofuse 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extra-workloads ;;
+    bench10_flush3) CARTSEG_DEFER_FLUSH_CONV=3 run bench10_flush3 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extra-workloads ;;
+    bench10_flush7) CARTSEG_DEFER_FLUSH_CONV=7 run bench10_flush7 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extra-workloads ;;
+    ab_*) # A/B of an environment knob inside one box: ab_<ENVVAR>=<value>  (20 steps each, no CPU leg)
+            kv=${part#ab_}; env "$kv" bash -c 'true' && \
+            run "bench_${kv//[^A-Za-z0-9_=]/_}" 900 env "$kv" python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-extra-workloads ;;
+    bench20q) run bench20q 900 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-extra-workloads ;;
     bench10q) run bench10q 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extra-workloads ;;
     cpubase) run cpu_baseline 1500 python tools/cpu_baseline.py ;;
     loop)   run test_gpu_loop 900 python -m pytest tests/test_gpu_loop.py -m gpu -q --tb=short -s --timeout 600 ;;
@@ -35,6 +43,17 @@ for part in "$@"; do
     gradparity) run grad_parity 1200 python tools/grad_parity.py --out gpurun_out/r2_grad_parity_per_tensor.json ;;
     gradparity512) run grad_parity512 1200 python tools/grad_parity.py --batch 8 --size 512 --out gpurun_out/r2_grad_parity_per_tensor_512.json ;;
     hostinfo) (free -g; nproc; lscpu | grep -E "Model name|^CPU\(s\)|Thread|Socket"; nvidia-smi) > gpurun_out/hostinfo.txt 2>&1 ;;
+    sanitize) SEL='2-16-16-64-64 or 3-16-8-128-64 or 2-14-14-128-256 or 1-28-28-256-128 or 2-8-8-128-64'
+            for tool in memcheck racecheck synccheck; do
+              run sanitizer_$tool 1500 compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_gpu_layers.py -m gpu -q --tb=line -k "$SEL" --timeout 1200
+            done
+            run sanitizer_memcheck_smoke 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" ;;
+    ncucalib) run cublas_plain 300 python tools/cublas_calib.py
+            run ncu_cublas 900 ncu --set full --clock-control none -k regex:'gemm|nvjet|cutlass|sm100|sm90' -s 3 -c 2 -f -o gpurun_out/prof_cublas python tools/cublas_calib.py
+            run ncu_conv3 1500 ncu --profile-from-start off --set full --clock-control none --import-source on \
+                -k regex:conv3_gemm -c 22 -f -o gpurun_out/prof_conv3 python tools/profile_step.py ;;
+    tracedp2) run trace_dp_2gpu 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29551 tools/trace_dp.py ;;
+    infer_small) run bench_infer_small 900 python tools/bench_infer.py --batches 1,2,4,8,16 ;;
     smoke)  run smoke 600 python -c "import __graft_entry__ as g; g.smoke()" ;;
     bench)  run bench 900 python bench.py --steps 5 --warmup 3 ;;
     bench_nohead) CARTSEG_FUSE_HEAD=0 run bench_nohead 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline ;;
