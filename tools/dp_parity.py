@@ -86,7 +86,11 @@ def main():
                "loss_dp_mean": float(loss_mean), "loss_shard_mean": sum(losses) / world,
                "grad_rel_l2_whole": (num / max(den, 1e-300)) ** 0.5, "grad_rel_l2_worst_tensor": worst,
                "worst_tensor": worst_key, "max_abs_spread_between_ranks": worst_spread}
-        out["ok"] = bool(out["grad_rel_l2_whole"] < 1e-4 and worst_spread == 0.0 and
+        # fp32 on the wire: exact up to atomics; bf16 on the wire (CARTSEG_DP_WIRE_DTYPE=bf16): two bf16 roundings
+        wire = os.environ.get("CARTSEG_DP_WIRE_DTYPE", "fp32")
+        out["wire_dtype"] = wire
+        tol = 1e-4 if wire == "fp32" else 8e-3
+        out["ok"] = bool(out["grad_rel_l2_whole"] < tol and worst_spread == 0.0 and
                          abs(out["loss_dp_mean"] - out["loss_shard_mean"]) < 1e-5 * abs(out["loss_shard_mean"]) + 1e-7)
         print(json.dumps(out), flush=True)
     dist.barrier()

@@ -35,6 +35,16 @@ for part in "$@"; do
     ab_*) # A/B of an environment knob inside one box: ab_<ENVVAR>=<value>  (20 steps each, no CPU leg)
             kv=${part#ab_}; env "$kv" bash -c 'true' && \
             run "bench_${kv//[^A-Za-z0-9_=]/_}" 900 env "$kv" python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-extra-workloads ;;
+    scale_*) # scale_<workload>_<N>[_bf16]: bench of one workload on N GPUs of this box, 20 steps
+            spec=${part#scale_}; wl=${spec%%_*}; rest=${spec#*_}; n=${rest%%_*}; wire=fp32; [[ "$rest" == *_bf16 ]] && wire=bf16
+            if [ "$n" = 1 ]; then
+              run "bench_${wl}_1gpu" 900 python bench.py --workload $wl --steps 20 --warmup 3 --no-cpu-baseline --no-extra-workloads
+            else
+              CARTSEG_DP_WIRE_DTYPE=$wire run "bench_${wl}_${n}gpu_${wire}" 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n \
+                --master-addr 127.0.0.1 --master-port $((29600 + n + ${#wl} + ${#wire})) bench.py --gpus $n --workload $wl --steps 20 --warmup 3 --no-cpu-baseline --no-extra-workloads
+            fi ;;
+    tracedp8) run trace_dp_8gpu 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29552 tools/trace_dp.py
+              run trace_dp_8gpu_bf16 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29553 tools/trace_dp.py --wire bf16 ;;
     bench20q) run bench20q 900 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-extra-workloads ;;
     bench10q) run bench10q 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extra-workloads ;;
     cpubase) run cpu_baseline 1500 python tools/cpu_baseline.py ;;
