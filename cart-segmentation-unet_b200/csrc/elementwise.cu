@@ -302,6 +302,7 @@ __global__ void __launch_bounds__(256, 4) bn_relu_kernel(const bf16* __restrict_
   if (blockIdx.x == 0 && threadIdx.x == 0 && fin.num_batches_tracked) *fin.num_batches_tracked += 1;
   __syncthreads();
   const int cg = C >> 3;
+  const int cg_shift = 31 - __clz(cg);
   if (!POOL) {
     // The stride of the grid-stride loop is a multiple of the channel-group count (256 % cg == 0): a thread keeps its
     // channel group, so its coefficients live in registers; four 16-byte loads are in flight before the first use.
@@ -324,11 +325,11 @@ __global__ void __launch_bounds__(256, 4) bn_relu_kernel(const bf16* __restrict_
       Vec8 v[U];
 #pragma unroll
       for (int k = 0; k < U; ++k)
-        if (i + k * stride < total) v[k] = ld8_nc(y + ((i + k * stride) / cg) * C + g * 8);
+        if (i + k * stride < total) v[k] = ld8_nc(y + (i + k * stride) * 8);   // dense rows: (i / cg) * C + g * 8 == i * 8
 #pragma unroll
       for (int k = 0; k < U; ++k) {
         if (i + k * stride >= total) break;
-        const long long p = (i + k * stride) / cg;
+        const long long p = (i + k * stride) >> cg_shift;    // channel counts are powers of two
         float f[8];
         unpack8(v[k], f);
 #pragma unroll
@@ -387,6 +388,7 @@ __global__ void __launch_bounds__(256, 4) bn_relu_kernel(const bf16* __restrict_
 cudaError_t launch_bn_relu(const bf16* y, int B, int H, int W, int C, const BnFinalizeArgs& fin, bf16* out,
                            int out_pitch, int out_c0, bf16* pooled, const HeadFwd& head, cudaStream_t s) {
   const size_t smem = (size_t)2 * C * sizeof(float);
+  if (C < 8 || (C & (C - 1))) return cudaErrorInvalidValue;          // power-of-two channel counts (shift instead of divide)
   if (head.logits && (pooled || C != 64 || ((long long)B * H * W) % 4 != 0)) return cudaErrorInvalidValue;
   if (pooled) {
     bn_relu_kernel<true><<<grid_for((long long)B * (H / 2) * (W / 2) * (C / 8), 256), 256, smem, s>>>(

@@ -1,9 +1,10 @@
 // tcgen05 / TMA implicit-GEMM kernels for sm_100a (see igemm.cuh for the operand model).
 //
-// Warp roles (192 threads, one CTA per SM):
+// Warp roles (one CTA per SM):
 //   warp 0      TMA producer   (lane 0 issues; whole warp walks the pipeline)
-//   warp 1      MMA issuer     (lane 0 issues tcgen05.mma / tcgen05.commit)
-//   warps 2..5  epilogue       (TMEM -> registers -> swizzled smem -> TMA store / red.global)
+//   warp 1      MMA issuer     (one elected lane issues tcgen05.mma / tcgen05.commit)
+//   warps 2..   epilogue       (TMEM -> registers -> swizzled smem -> TMA store / red.global); the pixel GEMMs have one or
+//               two groups of four epilogue warps
 // Pipelines: smem full/empty mbarriers (TMA <-> MMA), TMEM full/empty mbarriers (MMA <-> epilogue,
 // double-buffered accumulators), persistent static tile schedule.
 #include "igemm.cuh"
@@ -38,301 +39,10 @@ CS_DEVINL void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" 
 // =============================================================================================
 //                                   pixel-major GEMM
 // =============================================================================================
-// PAIR = true: two CTAs (a cluster on one TPC) run ONE tcgen05.mma.cta_group::2 of M = 256 pixels: each CTA stages
-// its own 128-pixel A patches and HALF of the BLOCK_N weight rows, which halves the weight traffic from L2 and the
-// B-operand shared-memory reads per CTA; each CTA's TMEM holds the accumulator rows of its own pixels, so the
-// epilogue is unchanged.
-template <int BLOCK_N, int SA, int SB, bool PAIR>
-struct PixLayout {
-  static constexpr int kBRows = PAIR ? BLOCK_N / 2 : BLOCK_N;
-  static constexpr int kBSlot = kBRows * 128;
-  static constexpr int kA = 0;
-  static constexpr int kB = kA + SA * kASlotBytes;
-  static constexpr int kStage = kB + SB * kBSlot;
-  static constexpr int kVec = kStage + 2 * kStageBytes;      // 2 x 1024 floats
-  static constexpr int kRed = kVec + 2 * 1024 * 4;           // 4 x 64 x 2 floats
-  static constexpr int kBar = kRed + 4 * 64 * 2 * 4;
-  static constexpr int kNumBar = 2 * SA + 2 * SB + 4;
-  static constexpr int kTmemPtr = kBar + kNumBar * 8;
-  static constexpr int kTotal = kTmemPtr + 16;
-  static constexpr int kDyn = kTotal + 1024;                 // slack for manual 1024-B alignment
-  static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
-};
-
-template <int BLOCK_N, int SA, int SB, bool PAIR>
-__global__ void __launch_bounds__(kThreads, 1) pix_gemm_kernel(const __grid_constant__ PixGemmParams p) {
-  using L = PixLayout<BLOCK_N, SA, SB, PAIR>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBar);
-  uint64_t* fullA = bars;
-  uint64_t* emptyA = fullA + SA;
-  uint64_t* fullB = emptyA + SA;
-  uint64_t* emptyB = fullB + SB;
-  uint64_t* tmem_full = emptyB + SB;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtr);
-  float* vec = reinterpret_cast<float*>(smem + L::kVec);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;       // CTA rank inside the pair
-  const bool leader = rank == 0;
-  const int m_tiles = p.tiles_w * p.tiles_h * p.batch;
-  // work unit: PAIR ? (two consecutive m-tiles) x one n-block : one m-tile x one n-block
-  const int m_units = PAIR ? (m_tiles + 1) / 2 : m_tiles;
-  const int num_units = m_units * p.n_blocks;
-  const int first_unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int unit_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const bool want_stats = p.stat_sum != nullptr;
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < SA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
-    for (int i = 0; i < SB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], PAIR ? 8 : 4); }
-    fence_barrier_init();
-    for (int g = 0; g < p.G; ++g) tma_prefetch_desc(&p.tmapA[p.a_map[g]]);
-    tma_prefetch_desc(&p.tmapB);
-    tma_prefetch_desc(&p.tmapO[0]);
-  }
-  if (warp == 2) {
-    if (PAIR) tmem_alloc_pair<L::kTmemCols>(tmem_ptr);
-    else tmem_alloc<L::kTmemCols>(tmem_ptr);
-  }
-  {
-    const int nvec = p.o_blocks_per_map * BLOCK_N;           // <= 1024
-    for (int i = threadIdx.x; i < 1024; i += kThreads) {
-      float a = 0.f, b = 0.f;
-      if (!want_stats && i < nvec) {
-        a = p.scale ? p.scale[i] : 1.f;
-        b = p.shift ? p.shift[i] : 0.f;
-      }
-      vec[i] = a;
-      vec[1024 + i] = b;
-    }
-  }
-  tc_fence_before();
-  if (PAIR) cluster_sync();                                  // both CTAs: barriers initialised, TMEM allocated
-  else __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  const int per_img = p.tiles_w * p.tiles_h;
-  // Decodes work unit u into this CTA's tile; a CTA whose m-tile does not exist (odd tile count) gets batch
-  // coordinate == batch: every TMA load is zero-filled and every store clipped away.
-  auto decode = [&](int u, int& nb, int& b, int& w0, int& h0) -> bool {
-    const int m_unit = u / p.n_blocks;
-    nb = u - m_unit * p.n_blocks;
-    const int m_tile = PAIR ? 2 * m_unit + (int)rank : m_unit;
-    const bool valid = m_tile < m_tiles;
-    b = valid ? m_tile / per_img : p.batch;
-    const int rem = valid ? m_tile - b * per_img : 0;
-    const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
-    w0 = tw * 8;
-    h0 = th * 16;
-    return valid;
-  };
-
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    int sa = 0, pa = 0, sb = 0, pb = 0;
-    const uint32_t a_bytes = (16 + p.R - 1) * kAtomBytes;
-    for (int u = first_unit; u < num_units; u += unit_stride) {
-      int nb, b, w0, h0;
-      decode(u, nb, b, w0, h0);
-      const int n0 = nb * BLOCK_N + (PAIR ? (int)rank * L::kBRows : 0);
-      for (int kc = 0; kc < p.kchunks; ++kc) {
-        for (int g = 0; g < p.G; ++g) {
-          mbar_wait(&emptyA[sa], pa ^ 1);
-          if (lane == 0) {
-            void* dst = smem + L::kA + sa * kASlotBytes;
-            const CUtensorMap* map = &p.tmapA[p.a_map[g]];
-            if (PAIR) {
-              if (leader) mbar_arrive_expect_tx(&fullA[sa], 2 * a_bytes);
-              tma_load_4d_pair(dst, map, mapa_cluster(smem_u32(&fullA[sa]), 0), p.a_chan0 + kc * 64, w0 + p.a_dw[g],
-                               h0 + p.a_dh[g], b);
-            } else {
-              mbar_arrive_expect_tx(&fullA[sa], a_bytes);
-              tma_load_4d(dst, map, &fullA[sa], p.a_chan0 + kc * 64, w0 + p.a_dw[g], h0 + p.a_dh[g], b);
-            }
-          }
-          if (++sa == SA) { sa = 0; pa ^= 1; }
-          for (int r = 0; r < p.R; ++r) {
-            mbar_wait(&emptyB[sb], pb ^ 1);
-            if (lane == 0) {
-              void* dst = smem + L::kB + sb * L::kBSlot;
-              const int row = (g * p.R + r) * p.Ntot + n0;
-              if (PAIR) {
-                if (leader) mbar_arrive_expect_tx(&fullB[sb], 2 * L::kBSlot);
-                tma_load_2d_pair(dst, &p.tmapB, mapa_cluster(smem_u32(&fullB[sb]), 0), kc * 64, row);
-              } else {
-                mbar_arrive_expect_tx(&fullB[sb], L::kBSlot);
-                tma_load_2d(dst, &p.tmapB, &fullB[sb], kc * 64, row);
-              }
-            }
-            if (++sb == SB) { sb = 0; pb ^= 1; }
-          }
-          __syncwarp();
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (leader) {
-      // Every lane runs this (warp-uniform) code; one elected lane issues each tcgen05 instruction.
-      constexpr uint32_t idesc = make_idesc(PAIR ? 256 : 128, BLOCK_N, 0, 0);
-      static_assert((uint32_t)(make_smem_desc_c(0, 16, kAtomBytes) >> 32) == kDescHiSw128, "descriptor high word");
-      const uint32_t lbo_lo = (16u >> 4) << 16;                             // LBO field lives in the low word
-      const uint32_t a_base = (smem_u32(smem + L::kA) >> 4) | lbo_lo, b_base = (smem_u32(smem + L::kB) >> 4) | lbo_lo;
-      int sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, acc_phase = 0;
-      for (int u = first_unit; u < num_units; u += unit_stride) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        uint32_t accumulate = 0;
-        for (int kc = 0; kc < p.kchunks; ++kc) {
-          for (int g = 0; g < p.G; ++g) {
-            mbar_wait(&fullA[sa], pa);
-            for (int r = 0; r < p.R; ++r) {
-              mbar_wait(&fullB[sb], pb);
-              tc_fence_after();
-              // four K-steps of 16 channels: +32 bytes = +2 in the descriptor start field per step
-              umma_bf16_steps_warp<PAIR, 4, 2>(d_tmem, a_base + (uint32_t)(sa * (kASlotBytes >> 4) + r * (kAtomBytes >> 4)),
-                                               b_base + (uint32_t)(sb * (L::kBSlot >> 4)), idesc,
-                                               accumulate);
-              accumulate = 1;
-              umma_commit_warp<PAIR>(&emptyB[sb]);
-              if (++sb == SB) { sb = 0; pb ^= 1; }
-            }
-            umma_commit_warp<PAIR>(&emptyA[sa]);
-            if (++sa == SA) { sa = 0; pa ^= 1; }
-          }
-        }
-        umma_commit_warp<PAIR>(&tmem_full[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
-      }
-    }
-  } else {
-    // ------------------------------------------------------------------ epilogue (128 threads)
-    const int et = threadIdx.x - 64;
-    const int sub = warp & 3;                  // TMEM sub-partition this warp may read
-    const int ewarp = warp - 2;
-    const int row = sub * 32 + lane;           // pixel row of the tile held by this thread
-    float* red = reinterpret_cast<float*>(smem + L::kRed);
-    int acc = 0, acc_phase = 0;
-    uint32_t buf_ctr = 0;
-    const bool affine = !want_stats && (p.scale != nullptr || p.shift != nullptr || p.relu);
-    for (int u = first_unit; u < num_units; u += unit_stride) {
-      int nb, b, w0, h0;
-      const bool valid = decode(u, nb, b, w0, h0);
-      const int omap = nb / p.o_blocks_per_map;
-      const int n_in_map0 = (nb - omap * p.o_blocks_per_map) * BLOCK_N;
-
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + acc * BLOCK_N;
-#pragma unroll 1
-      for (int cb = 0; cb < BLOCK_N / 64; ++cb) {
-        uint8_t* sbuf = smem + L::kStage + (buf_ctr & 1) * kStageBytes;
-        ++buf_ctr;
-        if (et == 0) tma_store_wait_read<1>();           // the store issued 2 blocks ago has drained
-        bar_sync(1, 128);
-        uint32_t v[64];
-        tmem_ld32(taddr + cb * 64, v);
-        tmem_ld32(taddr + cb * 64 + 32, v + 32);
-        tmem_ld_wait();
-        if (cb == BLOCK_N / 64 - 1) {                    // accumulator fully read: hand it back to the MMA issuer
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (PAIR) mbar_arrive_cluster(mapa_cluster(smem_u32(&tmem_empty[acc]), 0));
-            else mbar_arrive(&tmem_empty[acc]);
-          }
-        }
-        uint32_t packed[32];
-        if (affine) {
-          const float* sc = vec + n_in_map0 + cb * 64;
-          const float* sh = vec + 1024 + n_in_map0 + cb * 64;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float a = __uint_as_float(v[2 * i]) * sc[2 * i] + sh[2 * i];
-            float c = __uint_as_float(v[2 * i + 1]) * sc[2 * i + 1] + sh[2 * i + 1];
-            if (p.relu) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
-            packed[i] = pack_bf16x2(a, c);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) packed[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-        }
-        {
-          uint8_t* rowp = sbuf + row * 128;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            uint4 q = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-            *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = q;
-          }
-        }
-        fence_proxy_async();
-        bar_sync(2, 128);
-        if (et == 0 && valid) {
-          tma_store_4d(&p.tmapO[omap], sbuf, p.o_chan0 + n_in_map0 + cb * 64, w0, h0, b);
-          tma_store_commit();
-        }
-        if (want_stats) {
-          // Column sums over the staged bf16 tile: this warp covers rows [32*sub, 32*sub+32), lane
-          // covers the channel pair (2*lane, 2*lane+1).  Tile rows that lie outside the image hold
-          // values the store clips away; they are masked out here.
-          const uint32_t* s32 = reinterpret_cast<const uint32_t*>(sbuf);
-          const int chunk = lane >> 2, word = lane & 3;
-          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-          if (valid) {
-#pragma unroll 8
-            for (int rr = 0; rr < 32; ++rr) {
-              const int r2 = sub * 32 + rr;
-              if (w0 + (r2 & 7) >= p.W || h0 + (r2 >> 3) >= p.H) continue;
-              const uint32_t w = s32[r2 * 32 + (((chunk ^ (r2 & 7)) << 2) | word)];
-              const float f0 = bf16_lo(w), f1 = bf16_hi(w);
-              s0 += f0; q0 += f0 * f0; s1 += f1; q1 += f1 * f1;
-            }
-          }
-          float* rw = red + (ewarp * 64 + 2 * lane) * 2;
-          rw[0] = s0; rw[1] = q0; rw[2] = s1; rw[3] = q1;
-          bar_sync(3, 128);
-          const int c = et & 63, which = et >> 6;
-          float tot = 0.f;
-#pragma unroll
-          for (int w4 = 0; w4 < 4; ++w4) tot += red[(w4 * 64 + c) * 2 + which];
-          vec[which * 1024 + n_in_map0 + cb * 64 + c] += tot;
-        }
-      }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
-    }
-    if (et == 0) tma_store_wait_all<0>();
-    if (want_stats) {
-      bar_sync(1, 128);
-      const int nvec = p.o_blocks_per_map * BLOCK_N;
-      for (int i = et; i < nvec; i += 128) {
-        const float s = vec[i], q = vec[1024 + i];
-        if (q != 0.f) {
-          atomicAdd(&p.stat_sum[i], (double)s);
-          atomicAdd(&p.stat_sq[i], (double)q);
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  if (PAIR) cluster_sync();                                  // the peer's smem / TMEM / barriers stay alive until here
-  else __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    if (PAIR) tmem_dealloc_pair<L::kTmemCols>(tmem_base);
-    else tmem_dealloc<L::kTmemCols>(tmem_base);
-  }
-}
-
+// The pixel GEMMs are CTA-pair kernels: two CTAs (a cluster on one TPC) run ONE tcgen05.mma.cta_group::2 of M = 256
+// pixels; each CTA stages its own 128-pixel A patches and HALF of the BLOCK_N weight rows, which halves the weight traffic
+// from L2 and the B-operand shared-memory reads per CTA; each CTA's TMEM holds the accumulator rows of its own pixels.
+// (Round 1's single-CTA kernel, kept then behind CARTSEG_PAIR=0, was removed in round 2: no test exercised it.)
 // Epilogue of the CTA-pair pixel GEMMs (EG groups of 128 threads, warps 2..): TMEM -> registers -> (affine / ReLU) -> bf16 ->
 // 128B-swizzled staging tile -> TMA store; train-mode BN statistics (sum, sum of squares) from the staged bf16 tile.
 // Shared by pix_gemm2_kernel and conv3_gemm_kernel.
@@ -958,55 +668,13 @@ static cudaError_t launch_pix2(const PixGemmParams& p, int num_sms, cudaStream_t
   return launched();
 }
 
-template <int BLOCK_N, int SA, int SB, bool PAIR>
-static cudaError_t launch_pix(const PixGemmParams& p, int num_sms, cudaStream_t stream) {
-  using L = PixLayout<BLOCK_N, SA, SB, PAIR>;
-  static_assert(L::kDyn <= 232448, "shared memory budget exceeded");
-  auto kern = pix_gemm_kernel<BLOCK_N, SA, SB, PAIR>;
-  static std::atomic<unsigned long long> attr_done{0};   // per device: function attributes belong to the context
-  {
-    cudaError_t ae = ensure_dynamic_smem(kern, L::kDyn, attr_done);
-    if (ae != cudaSuccess) return ae;
-  }
-  const int m_tiles = p.tiles_w * p.tiles_h * p.batch;
-  const int units = (PAIR ? (m_tiles + 1) / 2 : m_tiles) * p.n_blocks;
-  if (units <= 0) return cudaSuccess;
-  cudaLaunchConfig_t cfg{};
-  cudaLaunchAttribute attr[1];
-  if (PAIR) {
-    const int clusters = units < num_sms / 2 ? units : num_sms / 2;
-    cfg.gridDim = dim3(2 * clusters);
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-  } else {
-    cfg.gridDim = dim3(units < num_sms ? units : num_sms);
-  }
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = L::kDyn;
-  cfg.stream = stream;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
-  if (e != cudaSuccess) return e;
-  return launched();
-}
-
 cudaError_t launch_pix_gemm(const PixGemmParams& p, int block_n, int num_sms, cudaStream_t stream) {
+  if (!p.pair) return cudaErrorInvalidValue;
   if (p.conv3) return launch_conv3_gemm(p, block_n, num_sms, stream);
-  if (p.pair) {
-    switch (block_n) {
-      case 64: return launch_pix2<64, 5, 2, 2>(p, num_sms, stream);
-      case 128: return launch_pix2<128, 4, 2, 2>(p, num_sms, stream);
-      case 256: return launch_pix2<256, 3, 1, 1>(p, num_sms, stream);
-      default: return cudaErrorInvalidValue;
-    }
-  }
   switch (block_n) {
-    case 64: return launch_pix<64, 6, 8, false>(p, num_sms, stream);
-    case 128: return launch_pix<128, 3, 7, false>(p, num_sms, stream);
-    case 256: return launch_pix<256, 3, 4, false>(p, num_sms, stream);
+    case 64: return launch_pix2<64, 5, 2, 2>(p, num_sms, stream);
+    case 128: return launch_pix2<128, 4, 2, 2>(p, num_sms, stream);
+    case 256: return launch_pix2<256, 3, 1, 1>(p, num_sms, stream);
     default: return cudaErrorInvalidValue;
   }
 }

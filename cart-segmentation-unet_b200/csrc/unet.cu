@@ -92,14 +92,8 @@ static int nhwc_patch_map(CUtensorMap* m, const bf16* base, int pitch, int B, in
   if (r != 0) return fail("cuTensorMapEncodeTiled (NHWC patch %dx%dx%dx%d, pitch %d) failed: %d", B, H, W, pitch, pitch, r);
   return 0;
 }
-// CTA-pair (cta_group::2) pixel GEMMs are the default; CARTSEG_PAIR=0 selects the single-CTA kernels (debugging).
-static bool use_pair() {
-  static const bool v = [] {
-    const char* e = getenv("CARTSEG_PAIR");
-    return !(e && e[0] == '0');
-  }();
-  return v;
-}
+// The pixel GEMMs are CTA-pair kernels (cta_group::2): each CTA of the pair stages half of the weight rows.
+static bool use_pair() { return true; }
 
 static int weight_map(CUtensorMap* m, const bf16* base, int K, int rows, int block_n) {
   const int box_rows = use_pair() ? block_n / 2 : block_n;
