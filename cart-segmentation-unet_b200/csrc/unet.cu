@@ -47,6 +47,19 @@ static int fail(const char* fmt, ...) {
     if (r__ != 0) return r__;       \
   } while (0)
 
+static int device_sm_count(int* out);
+// SM count used by the single-layer entry points; CARTSEG_LAYER_SMS=n (read on every call) caps it, so that a test can run
+// the same layer with different persistent-grid sizes in one process.
+static int layer_sm_count(int* out) {
+  int r = device_sm_count(out);
+  if (r != 0) return r;
+  const char* e = getenv("CARTSEG_LAYER_SMS");
+  if (e) {
+    int n = atoi(e) & ~1;
+    if (n >= 2 && n < *out) *out = n;
+  }
+  return 0;
+}
 static int device_sm_count(int* out) {
   int dev = 0;
   CS_CUDA(cudaGetDevice(&dev));
@@ -1380,7 +1393,7 @@ int cs_conv3x3_fprop(const void* x, int batch, int height, int width, int cin, c
   CS_TRY(check_layer(x, y, scratch, batch, height, width, cin, cout));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int sms, bn;
-  CS_TRY(device_sm_count(&sms));
+  CS_TRY(layer_sm_count(&sms));
   LayerScratch ls = carve(scratch, cin, cout);
   CS_CUDA(launch_pack_pairs(w_oihw, cout, cin, 9, ls.wf, kTapFprop, ls.wd, kTapDgrad, s));
   PixGemmParams p;
@@ -1396,7 +1409,7 @@ int cs_conv3x3_dgrad(const void* dy, int batch, int height, int width, int cin, 
   CS_TRY(check_layer(dy, dx, scratch, batch, height, width, cin, cout));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int sms, bn;
-  CS_TRY(device_sm_count(&sms));
+  CS_TRY(layer_sm_count(&sms));
   LayerScratch ls = carve(scratch, cin, cout);
   CS_CUDA(launch_pack_pairs(w_oihw, cout, cin, 9, ls.wf, kTapFprop, ls.wd, kTapDgrad, s));
   PixGemmParams p;
@@ -1426,7 +1439,7 @@ int cs_convT2x2_fprop(const void* x, int batch, int height, int width, int cin, 
   if (y_pitch < cout || y_pitch % 8) return fail("layer op: bad output pitch %d", y_pitch);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int sms, bn;
-  CS_TRY(device_sm_count(&sms));
+  CS_TRY(layer_sm_count(&sms));
   LayerScratch ls = carve(scratch, cin, cout);
   CS_CUDA(launch_pack_pairs(w_iohw, cin, cout, 4, ls.wd, kTapIdent, ls.wf, kTapIdent, s));
   PixGemmParams p;
@@ -1442,7 +1455,7 @@ int cs_convT2x2_dgrad(const void* dy, int dy_pitch, int batch, int height, int w
   if (dy_pitch < cout || dy_pitch % 8) return fail("layer op: bad gradient pitch %d", dy_pitch);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int sms, bn;
-  CS_TRY(device_sm_count(&sms));
+  CS_TRY(layer_sm_count(&sms));
   LayerScratch ls = carve(scratch, cin, cout);
   CS_CUDA(launch_pack_pairs(w_iohw, cin, cout, 4, ls.wd, kTapIdent, ls.wf, kTapIdent, s));
   PixGemmParams p;

@@ -203,3 +203,71 @@ def test_cuda_graph_inference_matches_eager_and_is_one_launch():
     with torch.no_grad():
         a = g_frozen(xg).clone()
         assert torch.equal(a, model(xg))
+
+
+def test_results_do_not_depend_on_the_persistent_grid_size():
+    """Race / pipeline-phase check that needs no external tool (compute-sanitizer is closed on this pool): the persistent
+    GEMM kernels take their tiles in a static round-robin, so capping the grid changes the tile -> CTA assignment, the
+    number of tiles per CTA, and with them every ring phase / accumulator parity / staging-buffer rotation of every CTA.
+    (1) single layers through the C ABI (CARTSEG_LAYER_SMS): conv fprop and dgrad outputs bit-identical for every grid
+    size; (2) the whole eval-mode forward (no batch statistics: nothing may depend on the partition) bit-identical;
+    (3) a training step: the per-CTA fp32 partial sums of the BN statistics do depend on the partition (last-bit changes
+    of scale / shift), so loss to 1e-5 and gradients to cosine 0.999."""
+    import os
+    import cartseg
+    from cartseg import _lib
+    from gpu_util import layer_scratch, stream, to_nhwc_bf16
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(11)
+    for (B, H, W, Cin, Cout) in [(4, 56, 56, 64, 64), (2, 28, 28, 256, 128), (2, 14, 14, 512, 512), (3, 40, 24, 128, 64)]:
+        x = to_nhwc_bf16(torch.randn(B, Cin, H, W, generator=g))
+        dy = to_nhwc_bf16(torch.randn(B, Cout, H, W, generator=g))
+        w = (torch.randn(Cout, Cin, 3, 3, generator=g) * (2.0 / (9 * Cin)) ** 0.5).cuda()
+        buf, scratch = layer_scratch(Cin, Cout)
+        outs = []
+        for sms in ("148", "146", "96", "36", "2"):
+            os.environ["CARTSEG_LAYER_SMS"] = sms
+            y = torch.full((B, H, W, Cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+            dx = torch.full((B, H, W, Cin), float("nan"), dtype=torch.bfloat16, device="cuda")
+            ssum = torch.zeros(Cout, dtype=torch.float64, device="cuda")
+            ssq = torch.zeros(Cout, dtype=torch.float64, device="cuda")
+            _lib.check(L.cs_conv3x3_fprop(x.data_ptr(), B, H, W, Cin, w.data_ptr(), Cout, y.data_ptr(), ssum.data_ptr(),
+                                          ssq.data_ptr(), scratch, stream()), "cs_conv3x3_fprop")
+            _lib.check(L.cs_conv3x3_dgrad(dy.data_ptr(), B, H, W, Cin, w.data_ptr(), Cout, dx.data_ptr(), scratch, stream()),
+                       "cs_conv3x3_dgrad")
+            torch.cuda.synchronize()
+            outs.append((y, dx, ssum))
+        os.environ.pop("CARTSEG_LAYER_SMS")
+        for y, dx, ssum in outs[1:]:
+            assert torch.equal(y.view(torch.int16), outs[0][0].view(torch.int16)), (B, H, W, Cin, Cout)
+            assert torch.equal(dx.view(torch.int16), outs[0][1].view(torch.int16)), (B, H, W, Cin, Cout)
+            assert torch.allclose(ssum, outs[0][2], rtol=1e-5, atol=1e-3)
+    torch.manual_seed(6)
+    model = cartseg.UNet().cuda()
+    crit = cartseg.FocalDiceLoss(0.5, 2.0, 1.0, 0.7)
+    (x, t), = _loader(1, 3, 96, seed=30)
+    xg, tg = x.cuda(), t.cuda()
+    ref_eval = ref_train = None
+    model.eval()
+    for reserve in (0, 2, 52, 112, 146):                 # eval first: training steps move the running statistics
+        model._reserve_sms = reserve
+        with torch.no_grad():
+            ze = model(xg).clone()
+        if ref_eval is None:
+            ref_eval = ze
+        assert torch.equal(ze, ref_eval), reserve
+    model.train()
+    for reserve in (0, 2, 52, 112, 146):
+        model._reserve_sms = reserve
+        model.zero_grad(set_to_none=True)
+        loss = crit(model(xg), tg)
+        loss.backward()
+        torch.cuda.synchronize()
+        flat = torch.cat([p.grad.flatten() for p in model.parameters()]).double()
+        if ref_train is None:
+            ref_train = (float(loss), flat)
+            continue
+        assert abs(float(loss) - ref_train[0]) <= 1e-5 * abs(ref_train[0]), reserve
+        cos = float(torch.dot(flat, ref_train[1]) / (flat.norm() * ref_train[1].norm()))
+        assert cos > 0.999, (reserve, cos)
+    model._reserve_sms = 0
