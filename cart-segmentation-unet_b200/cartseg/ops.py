@@ -330,13 +330,16 @@ class UNetFunction(torch.autograd.Function):
         logits = torch.ops.cartseg.unet_forward(x, [p.detach() for p in params], buffers, training, plan_id,
                                                 pack_token)
         ctx.plan_id = plan_id
+        ctx.x_version = x._version
         ctx.generation = _plan(plan_id).generation
         ctx.training = training
         ctx.frozen = frozen
         ctx.dp_handle = dp_handle
         ctx.n_params = n_params
         ctx.n_buffers = len(buffers)
-        ctx.save_for_backward(*params)
+        # x is saved too: the backward pass re-reads the image for the first convolution's weight gradient
+        # (include/cartseg.h, cs_unet_forward) — this only keeps the caller's tensor alive, nothing is copied
+        ctx.save_for_backward(x, *params)
         return logits
 
     @staticmethod
@@ -344,7 +347,11 @@ class UNetFunction(torch.autograd.Function):
         if not ctx.training:
             raise CartsegError("backward through an eval-mode forward is not available: call model.train() "
                                "(batch-statistics BN) for training steps")
-        params = [p.detach() for p in ctx.saved_tensors]
+        x = ctx.saved_tensors[0]
+        if x._version != ctx.x_version:
+            raise CartsegError("the input image was modified in place between forward and backward; the backward pass "
+                               "re-reads it for the first convolution's weight gradient")
+        params = [p.detach() for p in ctx.saved_tensors[1:]]
         need = ctx.needs_input_grad[7:7 + ctx.n_params]
         flat = torch.ops.cartseg.unet_backward(dlogits, params, ctx.plan_id, ctx.generation, ctx.frozen, ctx.dp_handle,
                                                [i for i in range(ctx.n_params) if not need[i]])

@@ -290,6 +290,11 @@ CS_DEVINL void mbar_arrive_cluster(uint32_t cluster_addr) {
   // MEMBAR.ALL.GPU per arrive (it was the top stall of the epilogue warps in ncu)
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Release at CLUSTER scope: for arrivals that publish data written by this CTA's threads to a consumer that acts on
+// behalf of both CTAs of the pair (the stem's A builders -> the leader's MMA warp).
+CS_DEVINL void mbar_arrive_cluster_release(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 CS_DEVINL void tma_load_2d_pair(void* smem, const CUtensorMap* m, uint32_t leader_bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"

@@ -625,6 +625,238 @@ static cudaError_t launch_conv3(const PixGemmParams& p, int num_sms, cudaStream_
   return launched();
 }
 
+// =============================================================================================
+//                                   stem: first convolution (Cin <= 7)
+// =============================================================================================
+// K = 9 * Cin <= 63: one 64-wide K chunk.  Round 1 wrote the im2col matrix [pixels][64] bf16 to HBM (347 MB for a 38 MB
+// image at K2) and read it back through the pointwise GEMM: 0.16 + 0.19 ms.  Here two builder warps construct each
+// 128-pixel A tile directly in (128B-swizzled) shared memory from the fp32 NCHW image — the image is small and
+// L2-resident — and hand it to the MMA warp through an mbarrier; the 64 x 64 weight tile is resident; the epilogue (bf16
+// store + BN statistics) is the shared pix_pair_epilogue.  The kernel is paced by its 411 MB output.
+// One im2col row of the stem: k = (kh*3 + kw) * Cin + c, zero beyond 9 * Cin and outside the image.  CIN > 0: compile-time
+// channel count (everything stays in registers); CIN == 0: generic 1..7 channels.
+template <int CIN>
+CS_DEVINL void stem_build_row(const float* __restrict__ x, int b, int h, int w, int H, int W, int cin_rt, bool inside,
+                              uint32_t packed[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) packed[i] = 0u;
+  if (!inside) return;
+  if (CIN > 0) {
+    float vals[64];
+#pragma unroll
+    for (int k = 0; k < 64; ++k) vals[k] = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+      const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
+      const float* src = x + (((size_t)b * CIN) * H + (ok ? hh : 0)) * W + (ok ? ww : 0);
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) vals[tap * CIN + c] = ok ? __ldg(src + (size_t)c * H * W) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) packed[i] = pack_bf16x2(vals[2 * i], vals[2 * i + 1]);
+  } else {
+    const int K = 9 * cin_rt;
+    for (int k = 0; k < K; ++k) {
+      const int tap = k / cin_rt, c = k - tap * cin_rt;
+      const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+      float v = 0.f;
+      if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(x + (((size_t)b * cin_rt + c) * H + hh) * W + ww);
+      const uint32_t hbits = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(v));
+      // packed[] is indexed with a run-time k only here (local memory); the generic path is not the benchmarked one
+      packed[k >> 1] |= (k & 1) ? (hbits << 16) : hbits;
+    }
+  }
+}
+
+template <int SA, int EG>
+struct StemLayout {
+  static constexpr int kASlot = 128 * 128;                   // 128 pixels x 64 k (bf16)
+  static constexpr int kBTile = 32 * 128;                    // this CTA's half of the 64 output channels
+  static constexpr int kA = 0;
+  static constexpr int kB = kA + SA * kASlot;
+  static constexpr int kStage = kB + kBTile;
+  static constexpr int kVec = kStage + EG * kStageBytes;
+  static constexpr int kRed = kVec + EG * 2 * 1024 * 4;
+  static constexpr int kBar = kRed + EG * 4 * 64 * 2 * 4;
+  static constexpr int kBuilderWarps = 2;
+  static constexpr int kThreadsTotal = 64 + 128 * EG + 32 * kBuilderWarps;
+  static constexpr int kNumBar = 2 * SA + 1 + 4;
+  static constexpr int kTmemPtr = kBar + kNumBar * 8;
+  static constexpr int kTotal = kTmemPtr + 16;
+  static constexpr int kDyn = kTotal + 1024;
+  static constexpr int kTmemCols = 128;                      // two 64-column accumulators
+};
+
+template <int SA, int EG>
+__global__ void __launch_bounds__(64 + 128 * EG + 64, 1) stem_gemm_kernel(const __grid_constant__ PixGemmParams p) {
+  using L = StemLayout<SA, EG>;
+  constexpr int BLOCK_N = 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBar);
+  uint64_t* fullA = bars;
+  uint64_t* emptyA = fullA + SA;
+  uint64_t* fullB = emptyA + SA;
+  uint64_t* tmem_full = fullB + 1;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtr);
+  float* vec = reinterpret_cast<float*>(smem + L::kVec);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int m_tiles = p.tiles_w * p.tiles_h * p.batch;
+  const int num_units = (m_tiles + 1) / 2;                   // n_blocks == 1
+  const int first_unit = (int)(blockIdx.x >> 1);
+  const int unit_stride = (int)(gridDim.x >> 1);
+  const bool want_stats = p.stat_sum != nullptr;
+
+  if (threadIdx.x == 0) {
+    // a tile is complete when the builder warps of BOTH CTAs have arrived on the leader's barrier
+    for (int i = 0; i < SA; ++i) { mbar_init(&fullA[i], 2 * L::kBuilderWarps); mbar_init(&emptyA[i], 1); }
+    mbar_init(fullB, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
+    fence_barrier_init();
+    tma_prefetch_desc(&p.tmapB);
+    tma_prefetch_desc(&p.tmapO[0]);
+  }
+  if (warp == 2) tmem_alloc_pair<L::kTmemCols>(tmem_ptr);
+  {
+    const int nvec = p.cols_per_map;
+    for (int i = threadIdx.x; i < 1024; i += L::kThreadsTotal) {
+      float a = 0.f, b = 0.f;
+      if (!want_stats && i < nvec) {
+        a = p.scale ? p.scale[i] : 1.f;
+        b = p.shift ? p.shift[i] : 0.f;
+      }
+      vec[i] = a;
+      vec[1024 + i] = b;
+      if (EG == 2) { vec[2048 + i] = 0.f; vec[3072 + i] = 0.f; }
+    }
+  }
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int per_img = p.tiles_w * p.tiles_h;
+  auto decode = [&](int u, int& nb, int& b, int& w0, int& h0) -> bool {
+    nb = 0;
+    const int m_tile = 2 * u + (int)rank;
+    const bool valid = m_tile < m_tiles;
+    b = valid ? m_tile / per_img : p.batch;
+    const int rem = valid ? m_tile - b * per_img : 0;
+    const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
+    w0 = tw * 8;
+    h0 = th * 16;
+    return valid;
+  };
+
+  constexpr int kFirstBuilderWarp = 2 + 4 * EG;
+  if (warp == 0) {
+    // ------------------------------------------------------------------ weights: one TMA load for the whole kernel
+    if (lane == 0 && first_unit < num_units) {
+      if (leader) mbar_arrive_expect_tx(fullB, 2 * L::kBTile);
+      tma_load_2d_pair(smem + L::kB, &p.tmapB, mapa_cluster(smem_u32(fullB), 0), 0, (int)rank * 32);
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader && first_unit < num_units) {
+      constexpr uint32_t idesc = make_idesc(256, BLOCK_N, 0, 0);
+      const uint32_t lbo_lo = (16u >> 4) << 16;
+      const uint32_t s_base = (smem_u32(smem) >> 4) | lbo_lo;
+      const uint32_t b_lo = s_base + (uint32_t)(L::kB >> 4);
+      mbar_wait(fullB, 0);
+      tc_fence_after();
+      int st = 0, ph = 0, acc = 0, acc_phase = 0;
+      for (int u = first_unit; u < num_units; u += unit_stride) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        mbar_wait(&fullA[st], ph);
+        tc_fence_after();
+        umma_bf16_steps_warp<true, 4, 2>(tmem_base + acc * BLOCK_N, s_base + (uint32_t)((L::kA + st * L::kASlot) >> 4), b_lo, idesc, 0);
+        umma_commit_warp<true>(&emptyA[st]);
+        umma_commit_warp<true>(&tmem_full[acc]);
+        if (++st == SA) { st = 0; ph ^= 1; }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= kFirstBuilderWarp) {
+    // ------------------------------------------------------------------ A builders: 64 threads, two pixel rows each
+    const int bt = threadIdx.x - kFirstBuilderWarp * 32;     // 0..63
+    const int Cin = p.stem_cin;
+    const float* __restrict__ x = p.stem_x;
+    int st = 0, ph = 0;
+    for (int u = first_unit; u < num_units; u += unit_stride) {
+      int nb, b, w0, h0;
+      const bool valid = decode(u, nb, b, w0, h0);
+      mbar_wait(&emptyA[st], ph ^ 1);
+      uint8_t* slot = smem + L::kA + st * L::kASlot;
+#pragma unroll 1
+      for (int rr = 0; rr < 2; ++rr) {
+        const int row = bt + 64 * rr;
+        const int h = h0 + (row >> 3), w = w0 + (row & 7);
+        uint32_t packed[32];                                  // 64 bf16 = k 0..63
+        const bool inside = valid && h < p.H && w < p.W;
+        if (Cin == 3) stem_build_row<3>(x, b, h, w, p.H, p.W, Cin, inside, packed);
+        else stem_build_row<0>(x, b, h, w, p.H, p.W, Cin, inside, packed);
+        uint8_t* rowp = slot + row * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) =
+              make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+      }
+      fence_proxy_async();                                    // generic-proxy writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster_release(mapa_cluster(smem_u32(&fullA[st]), 0));
+      if (++st == SA) { st = 0; ph ^= 1; }
+    }
+  } else {
+    pix_pair_epilogue<BLOCK_N, EG, 1>(p, smem + L::kStage, vec, reinterpret_cast<float*>(smem + L::kRed), tmem_full, tmem_empty,
+                                      tmem_base, warp, lane, first_unit, unit_stride, num_units, want_stats, decode);
+  }
+  tc_fence_before();
+  cluster_sync();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair<L::kTmemCols>(tmem_base);
+  }
+}
+
+static cudaError_t launch_stem_gemm(const PixGemmParams& p, int num_sms, cudaStream_t stream) {
+  constexpr int SA = 4, EG = 2;
+  using L = StemLayout<SA, EG>;
+  static_assert(L::kDyn <= 232448, "shared memory budget exceeded");
+  auto kern = stem_gemm_kernel<SA, EG>;
+  static std::atomic<unsigned long long> attr_done{0};
+  {
+    cudaError_t ae = ensure_dynamic_smem(kern, L::kDyn, attr_done);
+    if (ae != cudaSuccess) return ae;
+  }
+  if (p.n_blocks != 1 || p.Ntot != 64 || p.kchunks != 1 || p.stem_cin < 1 || p.stem_cin > 7) return cudaErrorInvalidValue;
+  const int m_tiles = p.tiles_w * p.tiles_h * p.batch;
+  const int units = (m_tiles + 1) / 2;
+  if (units <= 0) return cudaSuccess;
+  const int clusters = units < num_sms / 2 ? units : num_sms / 2;
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  cfg.gridDim = dim3(2 * clusters);
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cfg.blockDim = dim3(L::kThreadsTotal);
+  cfg.dynamicSmemBytes = L::kDyn;
+  cfg.stream = stream;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+  if (e != cudaSuccess) return e;
+  return launched();
+}
+
 static cudaError_t launch_conv3_gemm(const PixGemmParams& p, int block_n, int num_sms, cudaStream_t stream) {
   if (p.G != 3 || p.R != 3 || !p.pair) return cudaErrorInvalidValue;
   const bool resident = block_n == 64 && p.n_blocks == 1 && p.kchunks <= 2;
@@ -670,6 +902,7 @@ static cudaError_t launch_pix2(const PixGemmParams& p, int num_sms, cudaStream_t
 
 cudaError_t launch_pix_gemm(const PixGemmParams& p, int block_n, int num_sms, cudaStream_t stream) {
   if (!p.pair) return cudaErrorInvalidValue;
+  if (p.stem_x) return launch_stem_gemm(p, num_sms, stream);
   if (p.conv3) return launch_conv3_gemm(p, block_n, num_sms, stream);
   switch (block_n) {
     case 64: return launch_pix2<64, 5, 2, 2>(p, num_sms, stream);

@@ -44,6 +44,10 @@ struct PixGemmParams {
   // taps (the three horizontal taps are 128-byte row offsets into it) instead of three 8 x 18 patches.
   int conv3;            // 1: use conv3_gemm_kernel with tmapA3
   CUtensorMap tmapA3;   // box (64 ch, 10, 18, 1)
+  // stem_gemm_kernel (first convolution, Cin <= 7): the im2col rows [pixel][k = (kh*3+kw)*Cin + c] are built in shared
+  // memory from the fp32 NCHW image by two builder warps — no im2col matrix in HBM on the forward path.
+  const float* stem_x;  // fp32 NCHW input image (non-null selects stem_gemm_kernel)
+  int stem_cin;
 };
 
 cudaError_t launch_pix_gemm(const PixGemmParams& p, int block_n, int num_sms, cudaStream_t stream);

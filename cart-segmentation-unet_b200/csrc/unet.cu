@@ -125,6 +125,9 @@ static int env_int(const char* name, int dflt) {
 }
 static int conv3_enabled() { static const int v = env_int("CARTSEG_CONV3", 1); return v; }
 static int wgrad9_enabled() { static const int v = env_int("CARTSEG_WGRAD9", 1); return v; }
+// First convolution through stem_gemm_kernel (im2col rows built in shared memory); CARTSEG_STEM=0 restores
+// im2col_first_kernel + the pointwise GEMM on the forward path.
+static int stem_enabled() { static const int v = env_int("CARTSEG_STEM", 1); return v; }
 // TMA map over an NHWC buffer with a (64, pw, 18, 1) box: the whole halo patch of an 8 x 16 pixel tile.
 static int nhwc_patch_map(CUtensorMap* m, const bf16* base, int pitch, int B, int H, int W, int pw);
 
@@ -370,6 +373,7 @@ struct cs_unet_plan {
   std::vector<HeldWgrad> held;
   std::vector<HeldWgrad> late;     // wgrads of dconvL.0 that wait for the conv-transpose dgrad right after them
   cudaEvent_t ev_flush;
+  const float* x_keep;               // input image of the last training forward (the stem's weight gradient re-reads it)
   std::vector<cudaEvent_t> prof_events;   // pairs (begin, end)
   std::vector<int> prof_class;
   std::vector<double> prof_flops;
@@ -735,7 +739,17 @@ int cs_unet_forward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* x, 
     }
     CS_CUDA(launch_bn_fold_eval(f, s));
   }
-  CS_CUDA(launch_im2col_first(x, B, pl->Cin, pl->H, pl->W, pl->col, s));
+  const bool stem = stem_enabled() != 0;
+  if (!stem) {
+    CS_CUDA(launch_im2col_first(x, B, pl->Cin, pl->H, pl->W, pl->col, s));
+  } else {
+    // The forward path builds the im2col rows inside stem_gemm_kernel.  The matrix itself is only needed by the first
+    // convolution's weight gradient: cs_unet_backward writes it on its side stream, off the critical path — which is why
+    // x has to stay valid until then (include/cartseg.h).
+    pl->conv[0].fp_train.stem_x = x; pl->conv[0].fp_train.stem_cin = pl->Cin;
+    pl->conv[0].fp_eval.stem_x = x; pl->conv[0].fp_eval.stem_cin = pl->Cin;
+    pl->x_keep = training ? x : nullptr;
+  }
 
   auto run_conv = [&](int i) -> int {
     ConvL& c = pl->conv[i];
@@ -948,6 +962,10 @@ int cs_unet_backward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* dl
       // fly (BnBwdArgs::head_dlogits).  What is left of the head backward only produces parameter gradients, so it
       // goes to the weight-gradient stream, off the critical path.
       if (!t->param[80]) return fail("final_conv.weight is null");
+      // the im2col matrix of the input image, for the first convolution's weight gradient (last kernel of the pass):
+      // written now, on the side stream, while the main stream works on the decoder
+      if (pl->x_keep && frozen_encoder_convs == 0 && t->grad[pl->conv[0].pw])
+        CS_CUDA(traced(pl, 500, sw, [&] { return launch_im2col_first(pl->x_keep, B, pl->Cin, pl->H, pl->W, pl->col, sw); }));
       if (!fuse_head()) {
         CS_CUDA(launch_head_bwd(last.out.p, dlogits, last.P, 64, t->param[80], last.g_out.p, t->grad[80], t->grad[81], s));
         continue;

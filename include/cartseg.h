@@ -73,7 +73,10 @@ int cs_unet_plan_bind(cs_unet_plan* plan, void* workspace, size_t bytes);
 int cs_unet_pack_weights(cs_unet_plan* plan, const cs_unet_tensors* t, cs_stream_t stream);
 /* x fp32 [B,Cin,H,W] -> logits fp32 [B,1,H,W].  training != 0: batch statistics, running buffers
  * updated (momentum 0.1, eps 1e-5), activations kept for backward.  training == 0: running
- * statistics folded into the convolution epilogues. */
+ * statistics folded into the convolution epilogues.
+ * After a training-mode forward, `x` must stay valid and unchanged until the work of the following cs_unet_backward has
+ * completed: the first convolution's weight gradient re-reads the image (the forward path builds its im2col rows in
+ * shared memory and keeps no copy of it in HBM). */
 int cs_unet_forward(cs_unet_plan* plan, const cs_unet_tensors* t, const float* x, int training, float* logits,
                     cs_stream_t stream);
 /* Backward of the last training forward.  Stages [stage_begin, stage_end) in reverse execution
@@ -116,7 +119,7 @@ int cs_unet_profile(cs_unet_plan* plan, int enable);
 int cs_unet_profile_read(cs_unet_plan* plan, int n_classes, double* ms, double* flops, long long* launches);
 /* Developer timeline of cs_unet_backward: while enabled, every launch of the backward pass (both internal streams) is
  * bracketed by timing events.  cs_unet_trace_read waits for them and returns, per launch, a label (kind * 100 + layer:
- * 1 BN-backward reduce, 2 BN-backward apply, 3 conv dgrad, 4 conv wgrad, 6 head, 7 conv-transpose dgrad, 8 its wgrad,
+ * 1 BN-backward reduce, 2 BN-backward apply, 3 conv dgrad, 4 conv wgrad, 5 im2col of the input image, 6 head, 7 conv-transpose dgrad, 8 its wgrad,
  * 9 its bias gradient) and begin / end times in ms relative to the first launch.  Returns the number of entries. */
 int cs_unet_trace(cs_unet_plan* plan, int enable);
 int cs_unet_trace_read(cs_unet_plan* plan, int capacity, int* labels, double* begin_ms, double* end_ms);

@@ -46,12 +46,12 @@ N = 512
 lab, t0, t1 = (C.c_int * N)(), (C.c_double * N)(), (C.c_double * N)()
 n = L.cs_unet_trace_read(plan.handle, N, lab, t0, t1)
 L.cs_unet_trace(plan.handle, 0)
-KIND = {1: "bn_reduce", 2: "bn_apply", 3: "dgrad", 4: "wgrad", 6: "head_bwd", 7: "up_dgrad", 8: "up_wgrad", 9: "up_bias"}
+KIND = {1: "bn_reduce", 2: "bn_apply", 3: "dgrad", 4: "wgrad", 5: "im2col", 6: "head_bwd", 7: "up_dgrad", 8: "up_wgrad", 9: "up_bias"}
 rows = sorted((t0[i], t1[i], lab[i]) for i in range(n))
 end = max(r[1] for r in rows)
 print(f"# backward timeline, {n} launches, {end:.3f} ms from first launch to last completion")
 print("#   begin     end     dur  stream  kernel        overlap with the other stream (ms)")
-side = {4, 6, 8, 9}
+side = {4, 5, 6, 8, 9}
 for b, e, l in rows:
     k, idx = l // 100, l % 100
     other = [(b2, e2) for b2, e2, l2 in rows if ((l2 // 100) in side) != (k in side)]
