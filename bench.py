@@ -407,7 +407,7 @@ def run_ours(args, wl):
     L.cs_unet_profile(plan.handle, 0)
     L.cs_unet_set_overlap(plan.handle, 1)
     k_names = ["pix_gemm2_kernel<256> (conv-transpose fprop+dgrad)", "pix_gemm2_kernel<128>",
-               "pix_gemm2_kernel<64> (stem)", "wgrad_gemm_kernel<128>", "wgrad_gemm_kernel<64>",
+               "stem_gemm_kernel (first conv, im2col rows built in shared memory)", "wgrad_gemm_kernel<128>", "wgrad_gemm_kernel<64>",
                "conv3_gemm_kernel<256> (3x3 conv fprop+dgrad, N-side 256)", "conv3_gemm_kernel<128>",
                "conv3_gemm_kernel<64> (weights resident in shared memory)",
                "wgrad9_gemm_kernel (3x3 weight gradients with Cout = 64, nine taps per CTA)"]

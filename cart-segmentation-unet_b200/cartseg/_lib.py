@@ -111,6 +111,8 @@ _SIGNATURES = {
     "cs_preproc_masks": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "cs_layer_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "cs_conv3x3_fprop": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P, _P, _P]),
+    "cs_conv3x3_fprop_bnrelu": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P, _P, _P]),
+    "cs_conv3x3_wgrad_bnrelu": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "cs_conv3x3_dgrad": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P]),
     "cs_conv3x3_wgrad": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "cs_convT2x2_fprop": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, _P, C.c_int, _P, _P]),

@@ -290,8 +290,9 @@ CS_DEVINL void mbar_arrive_cluster(uint32_t cluster_addr) {
   // MEMBAR.ALL.GPU per arrive (it was the top stall of the epilogue warps in ncu)
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// Release at CLUSTER scope: for arrivals that publish data written by this CTA's threads to a consumer that acts on
-// behalf of both CTAs of the pair (the stem's A builders -> the leader's MMA warp).
+// Release at CLUSTER scope.  NOT used on any hot path: it compiles to a MEMBAR.ALL.GPU per arrive (~1 us), which paced
+// the first stem kernel (one arrive per 128-pixel tile).  The operand builders / transform warps publish their
+// shared-memory writes with fence.proxy.async + the plain remote arrive above, like CUTLASS' 2-SM transform pipelines.
 CS_DEVINL void mbar_arrive_cluster_release(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }

@@ -287,6 +287,19 @@ cudaError_t launch_bn_fold_eval(const BnFoldBatch& a, cudaStream_t s) {
   return launched();
 }
 
+// Statistics -> affine step alone: for the layers whose BatchNorm + ReLU is applied by the CONSUMING convolution
+// (conv3_gemm_kernel's transform warps), so that no elementwise pass over the activation exists at all.
+__global__ void bn_finalize_kernel(const BnFinalizeArgs fin) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  float sc, sh;
+  if (c < fin.C) bn_channel_coef(fin, c, true, &sc, &sh);
+  if (c == 0 && fin.num_batches_tracked) *fin.num_batches_tracked += 1;
+}
+cudaError_t launch_bn_finalize(const BnFinalizeArgs& fin, cudaStream_t s) {
+  bn_finalize_kernel<<<(fin.C + 127) / 128, 128, 0, s>>>(fin);
+  return launched();
+}
+
 // ============================================================================ BN apply + ReLU (+ 2x2 max-pool)
 template <bool POOL>
 __global__ void __launch_bounds__(256, 4) bn_relu_kernel(const bf16* __restrict__ y, int B, int H, int W, int C, const BnFinalizeArgs fin,

@@ -37,6 +37,111 @@ static cudaError_t ensure_dynamic_smem(K kern, int bytes, std::atomic<unsigned l
 CS_DEVINL void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // =============================================================================================
+//              BatchNorm + ReLU of an activation patch, in place in shared memory
+// =============================================================================================
+// The consumer of a convolution's RAW output applies the producer's BatchNorm + ReLU itself: the post-activation tensor
+// is never written to (or read from) HBM.  `slot` holds `nrows` pixel rows of 64 channels (128 bytes each, 128B-swizzled
+// by TMA: 16-byte chunk j of row r sits at ((j ^ (r & 7)) << 4)), row r = pixel (h_first + r / PW, w_first + r % PW).
+// NT threads (a multiple of 64) sweep NT / 8 rows at a time; a thread keeps its channel chunk, so its coefficients live
+// in registers and its swizzled chunk position is constant.  The arithmetic is bn_relu_kernel's: fmaxf(fmaf(y, sc, sh), 0)
+// rounded to bf16 — the backward pass recomputes the same mask from y.  Pixels outside the image are set to zero (TMA
+// zero-fills them in y space, but the convolution's padding is zero in activation space).
+// Eight channels: two packed fp32 FMAs per 32-bit word pair (fma.rn.f32x2, sm_100) and one cvt.rn.relu.bf16x2.f32 per
+// word — the same values as fmaxf(fmaf(y, sc, sh), 0) rounded to nearest-even.
+struct BnCoef8 { uint64_t sc[4], sh[4]; };                  // (sc[2j], sc[2j+1]) and (sh[2j], sh[2j+1]) as f32x2
+CS_DEVINL uint64_t f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+CS_DEVINL uint64_t bf16x2_to_f32x2(uint32_t w) {
+  uint64_t r;
+  asm("{\n\t.reg .b32 a, b;\n\tshl.b32 a, %1, 16;\n\tand.b32 b, %1, 0xffff0000;\n\tmov.b64 %0, {a, b};\n\t}" : "=l"(r) : "r"(w));
+  return r;
+}
+CS_DEVINL uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+CS_DEVINL uint32_t relu_pack_bf16x2(uint64_t v) {
+  uint32_t r;
+  asm("{\n\t.reg .f32 lo, hi;\n\tmov.b64 {lo, hi}, %1;\n\tcvt.rn.relu.bf16x2.f32 %0, hi, lo;\n\t}" : "=r"(r) : "l"(v));
+  return r;
+}
+// N vectors (16 bytes = 8 channels each) at p + i * STRIDE: all loads, then all unpacks, all FMAs, all packs, all stores
+// — written stage by stage so that the N x 4 independent word chains are interleaved: the warps that run this have a
+// scheduler to themselves, so every dependent instruction pair costs its full pipeline latency (ncu on the first version,
+// one chain per vector with a branch in between: 6 cycles per instruction, 190 cycles per vector, and the MMA warp
+// waiting for the transform a third of the time).  mask[i] = 0 zeroes vector i (pixel outside the image).
+template <int N, int STRIDE, bool MASKED>
+CS_DEVINL void bnrelu_vectors(uint8_t* p, const BnCoef8& k, const uint32_t* mask) {
+  uint4 v[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = *reinterpret_cast<const uint4*>(p + i * STRIDE);
+  uint64_t x[N][4];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    x[i][0] = bf16x2_to_f32x2(v[i].x); x[i][1] = bf16x2_to_f32x2(v[i].y);
+    x[i][2] = bf16x2_to_f32x2(v[i].z); x[i][3] = bf16x2_to_f32x2(v[i].w);
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x[i][j] = fma_f32x2(x[i][j], k.sc[j], k.sh[j]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    uint4 o = make_uint4(relu_pack_bf16x2(x[i][0]), relu_pack_bf16x2(x[i][1]), relu_pack_bf16x2(x[i][2]), relu_pack_bf16x2(x[i][3]));
+    if (MASKED) { o.x &= mask[i]; o.y &= mask[i]; o.z &= mask[i]; o.w &= mask[i]; }
+    *reinterpret_cast<uint4*>(p + i * STRIDE) = o;
+  }
+}
+// NROWS rows swept by NT threads, BATCH vectors per thread at a time; trip counts are compile-time constants (no branch
+// between vectors); the NROWS % (NT / 8) rows left over are done by the first threads.
+template <int PW, int NT, int NROWS, int BATCH>
+CS_DEVINL void bnrelu_patch(uint8_t* slot, int t, const float* __restrict__ sc_g, const float* __restrict__ sh_g,
+                            int h_first, int w_first, int H, int W, bool tile_valid) {
+  static_assert(NT % 64 == 0, "rows per sweep must be a multiple of 8 (constant swizzle phase per thread)");
+  constexpr int RS = NT / 8, NFULL = NROWS / RS, TAIL = NROWS - NFULL * RS;
+  const int c = t & 7, r0 = t >> 3;
+  BnCoef8 k;
+  {
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(sc_g + c * 8)), s1 = __ldg(reinterpret_cast<const float4*>(sc_g + c * 8 + 4));
+    const float4 h0 = __ldg(reinterpret_cast<const float4*>(sh_g + c * 8)), h1 = __ldg(reinterpret_cast<const float4*>(sh_g + c * 8 + 4));
+    k.sc[0] = f32x2(s0.x, s0.y); k.sc[1] = f32x2(s0.z, s0.w); k.sc[2] = f32x2(s1.x, s1.y); k.sc[3] = f32x2(s1.z, s1.w);
+    k.sh[0] = f32x2(h0.x, h0.y); k.sh[1] = f32x2(h0.z, h0.w); k.sh[2] = f32x2(h1.x, h1.y); k.sh[3] = f32x2(h1.z, h1.w);
+  }
+  uint8_t* p = slot + r0 * 128 + ((c ^ (r0 & 7)) << 4);
+  const bool interior = tile_valid && h_first >= 0 && h_first + NROWS / PW <= H && w_first >= 0 && w_first + PW <= W;
+  auto inside = [&](int r) -> uint32_t {                        // all ones if pixel row r lies inside the image
+    const int ph = PW == 8 ? (r >> 3) : (r * 205) >> 11;        // r / 10 for r < 1029
+    const int pw = r - ph * PW;
+    return (tile_valid && (unsigned)(h_first + ph) < (unsigned)H && (unsigned)(w_first + pw) < (unsigned)W) ? 0xffffffffu : 0u;
+  };
+  if (interior) {
+#pragma unroll
+    for (int b0 = 0; b0 < NFULL; b0 += BATCH) {
+      if (NFULL - b0 >= BATCH) bnrelu_vectors<BATCH, RS * 128, false>(p + b0 * RS * 128, k, nullptr);
+      else bnrelu_vectors<(NFULL % BATCH ? NFULL % BATCH : BATCH), RS * 128, false>(p + b0 * RS * 128, k, nullptr);
+    }
+    if (TAIL && r0 < TAIL) bnrelu_vectors<1, RS * 128, false>(p + NFULL * RS * 128, k, nullptr);
+  } else {
+#pragma unroll
+    for (int b0 = 0; b0 < NFULL; b0 += BATCH) {
+      uint32_t m[BATCH];
+#pragma unroll
+      for (int i = 0; i < BATCH; ++i) m[i] = inside(r0 + (b0 + i) * RS);
+      if (NFULL - b0 >= BATCH) bnrelu_vectors<BATCH, RS * 128, true>(p + b0 * RS * 128, k, m);
+      else bnrelu_vectors<(NFULL % BATCH ? NFULL % BATCH : BATCH), RS * 128, true>(p + b0 * RS * 128, k, m);
+    }
+    if (TAIL && r0 < TAIL) {
+      const uint32_t m = inside(r0 + NFULL * RS);
+      bnrelu_vectors<1, RS * 128, true>(p + NFULL * RS * 128, k, &m);
+    }
+  }
+}
+
+// =============================================================================================
 //                                   pixel-major GEMM
 // =============================================================================================
 // The pixel GEMMs are CTA-pair kernels: two CTAs (a cluster on one TPC) run ONE tcgen05.mma.cta_group::2 of M = 256
@@ -127,18 +232,44 @@ CS_DEVINL void pix_pair_epilogue(const PixGemmParams& p, uint8_t* stage_base, fl
         // Column sums over the staged bf16 tile: this warp covers rows [32*sub, 32*sub+32), lane
         // covers the channel pair (2*lane, 2*lane+1).  Tile rows that lie outside the image hold
         // values the store clips away; they are masked out here.
+        // Packed fp32 arithmetic (add / fma .f32x2) on the (even, odd) channel pair, four independent accumulator pairs,
+        // and no per-row branch when the tile lies inside the image: ncu showed this loop — 32 dependent, branchy rows of
+        // 10 instructions — to be a third of the epilogue warps' time in the Cout = 64 kernels, which are paced by it.
         const uint32_t* s32 = reinterpret_cast<const uint32_t*>(sbuf);
         const int chunk = lane >> 2, word = lane & 3;
-        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        uint64_t s2[4], q2[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) { s2[a] = 0ull; q2[a] = 0ull; }
+        const uint64_t one2 = f32x2(1.f, 1.f);
         if (valid) {
+          const bool full = w0 + 8 <= p.W && h0 + 16 <= p.H;
+          if (full) {
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) {
+              const int r2 = sub * 32 + rr;
+              const uint64_t x2 = bf16x2_to_f32x2(s32[r2 * 32 + (((chunk ^ (rr & 7)) << 2) | word)]);   // (32*sub + rr) & 7 == rr & 7
+              s2[rr & 3] = fma_f32x2(x2, one2, s2[rr & 3]);
+              q2[rr & 3] = fma_f32x2(x2, x2, q2[rr & 3]);
+            }
+          } else {
 #pragma unroll 8
-          for (int rr = 0; rr < 32; ++rr) {
-            const int r2 = sub * 32 + rr;
-            if (w0 + (r2 & 7) >= p.W || h0 + (r2 >> 3) >= p.H) continue;
-            const uint32_t w = s32[r2 * 32 + (((chunk ^ (r2 & 7)) << 2) | word)];
-            const float f0 = bf16_lo(w), f1 = bf16_hi(w);
-            s0 += f0; q0 += f0 * f0; s1 += f1; q1 += f1 * f1;
+            for (int rr = 0; rr < 32; ++rr) {
+              const int r2 = sub * 32 + rr;
+              const bool in = w0 + (r2 & 7) < p.W && h0 + (r2 >> 3) < p.H;
+              const uint32_t w = s32[r2 * 32 + (((chunk ^ (rr & 7)) << 2) | word)];
+              const uint64_t x2 = bf16x2_to_f32x2(in ? w : 0u);
+              s2[rr & 3] = fma_f32x2(x2, one2, s2[rr & 3]);
+              q2[rr & 3] = fma_f32x2(x2, x2, q2[rr & 3]);
+            }
           }
+        }
+        float s0, s1, q0, q1;
+        {
+          const uint64_t sa = fma_f32x2(s2[1], one2, s2[0]), sb = fma_f32x2(s2[3], one2, s2[2]);
+          const uint64_t qa = fma_f32x2(q2[1], one2, q2[0]), qb = fma_f32x2(q2[3], one2, q2[2]);
+          const uint64_t st = fma_f32x2(sb, one2, sa), qt = fma_f32x2(qb, one2, qa);
+          asm("mov.b64 {%0, %1}, %2;" : "=f"(s0), "=f"(s1) : "l"(st));
+          asm("mov.b64 {%0, %1}, %2;" : "=f"(q0), "=f"(q1) : "l"(qt));
         }
         float* rw = red + (ewarp * 64 + 2 * lane) * 2;
         rw[0] = s0; rw[1] = q0; rw[2] = s1; rw[3] = q1;
@@ -369,7 +500,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) pix_gemm2_kernel(const __gri
 // the shared-memory address, so the view stays consistent with what TMA wrote.  Weights: a ring of 3-tap groups
 // (RESIDENT = false), or, for the Cout = 64 layers (n_blocks == 1, K <= 128), ALL taps resident in shared memory for the
 // whole kernel (73 KB): per work unit only the 23 KB patch moves.
-template <int BLOCK_N, int PW, int SA, int SB, int NSTG, int EG, bool RESIDENT>
+template <int BLOCK_N, int PW, int SA, int SB, int NSTG, int EG, bool RESIDENT, bool XF = false>
 struct Conv3Layout {
   static constexpr int kAPatch = 18 * PW * 128;
   static constexpr int kASlot = (kAPatch + 1023) & ~1023;
@@ -385,8 +516,9 @@ struct Conv3Layout {
   static constexpr int kVec = kStage + NSTG * kStageBytes;   // EG x (2 x 1024 floats)
   static constexpr int kRed = kVec + EG * 2 * 1024 * 4;      // EG x (4 x 64 x 2 floats)
   static constexpr int kBar = kRed + EG * 4 * 64 * 2 * 4;
-  static constexpr int kThreadsTotal = 64 + 128 * EG;
-  static constexpr int kNumBar = 2 * SA + 2 * kNumB + 4;
+  static constexpr int kXfWarps = XF ? (EG == 2 ? 4 : 2) : 0;                // transform warps (BatchNorm + ReLU of every A patch)
+  static constexpr int kThreadsTotal = 64 + 128 * EG + 32 * kXfWarps;
+  static constexpr int kNumBar = 2 * SA + 2 * kNumB + 4 + (XF ? SA : 0);
   static constexpr int kTmemPtr = kBar + kNumBar * 8;
   static constexpr int kTotal = kTmemPtr + 16;
   static constexpr int kDyn = kTotal + 1024;                 // slack for manual 1024-B alignment
@@ -394,9 +526,9 @@ struct Conv3Layout {
   static_assert(RESIDENT || (3 * SA) % SB == 0, "the weight-ring slot of (A slot, tap group) must be a compile-time constant");
 };
 
-template <int BLOCK_N, int PW, int SA, int SB, int NSTG, int EG, bool RESIDENT>
-__global__ void __launch_bounds__(64 + 128 * EG, 1) conv3_gemm_kernel(const __grid_constant__ PixGemmParams p) {
-  using L = Conv3Layout<BLOCK_N, PW, SA, SB, NSTG, EG, RESIDENT>;
+template <int BLOCK_N, int PW, int SA, int SB, int NSTG, int EG, bool RESIDENT, bool XF>
+__global__ void __launch_bounds__(64 + 128 * EG + (XF ? (EG == 2 ? 128 : 64) : 0), 1) conv3_gemm_kernel(const __grid_constant__ PixGemmParams p) {
+  using L = Conv3Layout<BLOCK_N, PW, SA, SB, NSTG, EG, RESIDENT, XF>;
   static_assert(NSTG % EG == 0, "every epilogue group owns NSTG / EG staging buffers");
   constexpr int BPG = NSTG / EG;
   extern __shared__ uint8_t smem_raw[];
@@ -409,6 +541,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) conv3_gemm_kernel(const __gr
   uint64_t* emptyB = fullB + L::kNumB;
   uint64_t* tmem_full = emptyB + L::kNumB;
   uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* landA = tmem_empty + 2;                          // XF: this CTA's patch has landed (local), fullA = transformed
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtr);
   float* vec = reinterpret_cast<float*>(smem + L::kVec);
 
@@ -424,7 +557,9 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) conv3_gemm_kernel(const __gr
   const bool want_stats = p.stat_sum != nullptr;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < SA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
+    // XF: a patch is ready for the MMAs when the transform warps of BOTH CTAs have arrived on the leader's barrier
+    for (int i = 0; i < SA; ++i) { mbar_init(&fullA[i], XF ? 2 * L::kXfWarps : 1); mbar_init(&emptyA[i], 1); }
+    if (XF) for (int i = 0; i < SA; ++i) mbar_init(&landA[i], 1);
     for (int i = 0; i < L::kNumB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
     fence_barrier_init();
@@ -476,9 +611,14 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) conv3_gemm_kernel(const __gr
       decode(a_u, nb, b, w0, h0);
       mbar_wait(&emptyA[sa], pa ^ 1);
       if (lane == 0) {
-        if (leader) mbar_arrive_expect_tx(&fullA[sa], 2 * L::kAPatch);
-        tma_load_4d_pair(smem + L::kA + sa * L::kASlot, &p.tmapA3, mapa_cluster(smem_u32(&fullA[sa]), 0),
-                         p.a_chan0 + a_kc * 64, w0 - 1, h0 - 1, b);
+        if (XF) {                                              // lands on this CTA's own barrier: its transform warps wait there
+          mbar_arrive_expect_tx(&landA[sa], L::kAPatch);
+          tma_load_4d(smem + L::kA + sa * L::kASlot, &p.tmapA3, &landA[sa], p.a_chan0 + a_kc * 64, w0 - 1, h0 - 1, b);
+        } else {
+          if (leader) mbar_arrive_expect_tx(&fullA[sa], 2 * L::kAPatch);
+          tma_load_4d_pair(smem + L::kA + sa * L::kASlot, &p.tmapA3, mapa_cluster(smem_u32(&fullA[sa]), 0),
+                           p.a_chan0 + a_kc * 64, w0 - 1, h0 - 1, b);
+        }
       }
       __syncwarp();
       if (++sa == SA) { sa = 0; pa ^= 1; }
@@ -582,6 +722,23 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) conv3_gemm_kernel(const __gr
         phA ^= 1;
       }
     }
+  } else if (XF && warp >= 2 + 4 * EG) {
+    // ------------------------------------------------------------------ transform warps (both CTAs): BN + ReLU of each patch
+    const int tt = threadIdx.x - (2 + 4 * EG) * 32;          // 0..63
+    int sa = 0, pa = 0;
+    for (int u = first_unit; u < num_units; u += unit_stride) {
+      int nb, b, w0, h0;
+      const bool valid = decode(u, nb, b, w0, h0);
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        mbar_wait(&landA[sa], pa);
+        bnrelu_patch<PW, (XF ? 32 * L::kXfWarps : 64), 18 * PW, 6>(smem + L::kA + sa * L::kASlot, tt, p.in_scale + kc * 64, p.in_shift + kc * 64,
+                                           h0 - 1, w0 - 1, p.H, p.W, valid);
+        fence_proxy_async();                                  // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&fullA[sa]), 0));
+        if (++sa == SA) { sa = 0; pa ^= 1; }
+      }
+    }
   } else {
     pix_pair_epilogue<BLOCK_N, EG, BPG>(p, smem + L::kStage, vec, reinterpret_cast<float*>(smem + L::kRed), tmem_full, tmem_empty,
                                         tmem_base, warp, lane, first_unit, unit_stride, num_units, want_stats, decode);
@@ -594,11 +751,11 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) conv3_gemm_kernel(const __gr
   }
 }
 
-template <int BLOCK_N, int PW, int SA, int SB, int NSTG, int EG, bool RESIDENT>
+template <int BLOCK_N, int PW, int SA, int SB, int NSTG, int EG, bool RESIDENT, bool XF>
 static cudaError_t launch_conv3(const PixGemmParams& p, int num_sms, cudaStream_t stream) {
-  using L = Conv3Layout<BLOCK_N, PW, SA, SB, NSTG, EG, RESIDENT>;
+  using L = Conv3Layout<BLOCK_N, PW, SA, SB, NSTG, EG, RESIDENT, XF>;
   static_assert(L::kDyn <= 232448, "shared memory budget exceeded");
-  auto kern = conv3_gemm_kernel<BLOCK_N, PW, SA, SB, NSTG, EG, RESIDENT>;
+  auto kern = conv3_gemm_kernel<BLOCK_N, PW, SA, SB, NSTG, EG, RESIDENT, XF>;
   static std::atomic<unsigned long long> attr_done{0};
   {
     cudaError_t ae = ensure_dynamic_smem(kern, L::kDyn, attr_done);
@@ -629,75 +786,55 @@ static cudaError_t launch_conv3(const PixGemmParams& p, int num_sms, cudaStream_
 //                                   stem: first convolution (Cin <= 7)
 // =============================================================================================
 // K = 9 * Cin <= 63: one 64-wide K chunk.  Round 1 wrote the im2col matrix [pixels][64] bf16 to HBM (347 MB for a 38 MB
-// image at K2) and read it back through the pointwise GEMM: 0.16 + 0.19 ms.  Here two builder warps construct each
-// 128-pixel A tile directly in (128B-swizzled) shared memory from the fp32 NCHW image — the image is small and
-// L2-resident — and hand it to the MMA warp through an mbarrier; the 64 x 64 weight tile is resident; the epilogue (bf16
-// store + BN statistics) is the shared pix_pair_epilogue.  The kernel is paced by its 411 MB output.
-// One im2col row of the stem: k = (kh*3 + kw) * Cin + c, zero beyond 9 * Cin and outside the image.  CIN > 0: compile-time
-// channel count (everything stays in registers); CIN == 0: generic 1..7 channels.
-template <int CIN>
-CS_DEVINL void stem_build_row(const float* __restrict__ x, int b, int h, int w, int H, int W, int cin_rt, bool inside,
-                              uint32_t packed[32]) {
-#pragma unroll
-  for (int i = 0; i < 32; ++i) packed[i] = 0u;
-  if (!inside) return;
-  if (CIN > 0) {
-    float vals[64];
-#pragma unroll
-    for (int k = 0; k < 64; ++k) vals[k] = 0.f;
-#pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
-      const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
-      const float* src = x + (((size_t)b * CIN) * H + (ok ? hh : 0)) * W + (ok ? ww : 0);
-#pragma unroll
-      for (int c = 0; c < CIN; ++c) vals[tap * CIN + c] = ok ? __ldg(src + (size_t)c * H * W) : 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < 32; ++i) packed[i] = pack_bf16x2(vals[2 * i], vals[2 * i + 1]);
-  } else {
-    const int K = 9 * cin_rt;
-    for (int k = 0; k < K; ++k) {
-      const int tap = k / cin_rt, c = k - tap * cin_rt;
-      const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
-      float v = 0.f;
-      if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = __ldg(x + (((size_t)b * cin_rt + c) * H + hh) * W + ww);
-      const uint32_t hbits = (uint32_t)__bfloat16_as_ushort(__float2bfloat16(v));
-      // packed[] is indexed with a run-time k only here (local memory); the generic path is not the benchmarked one
-      packed[k >> 1] |= (k & 1) ? (hbits << 16) : hbits;
-    }
-  }
-}
+// image at K2) and read it back through the pointwise GEMM: 0.16 + 0.19 ms.  Here each 128-pixel A tile is built
+// directly in (128B-swizzled) shared memory: warp 0 brings the fp32 patch of the tile — (8+8) x (16+2) pixels of every
+// input channel, through a 4-D TMA map over the NCHW image whose out-of-bounds zero fill is the convolution padding —
+// into a small ring, two builder warps turn it into im2col rows (27 shared-memory reads per pixel instead of 27 scattered
+// global loads: the first version of this kernel, which read the image with __ldg, took 0.55 ms) and hand the tile to
+// the MMA warp through an mbarrier; the 64 x 64 weight tile is resident; the epilogue (bf16 store + BN statistics) is the
+// shared pix_pair_epilogue.  The kernel is paced by its 411 MB output.
+// im2col row: k = (kh*3 + kw) * Cin + c, zero beyond 9 * Cin.  The 16-byte chunks past ceil(9*Cin / 8) are zeroed once
+// per kernel and never rewritten (their swizzled position depends on the tile row only).
+// 10 columns (w0-1 .. w0+8) are needed; the box starts at w0-4 and is 16 wide so that the innermost TMA coordinate is a
+// multiple of 16 bytes (a box starting at w0-1 — 12 columns — faults with "illegal instruction" on B200)
+static constexpr int kStemPatchW = 16;
+static constexpr int kStemPatchX0 = 3;                       // column of tap kw = 0 for tile pixel w = 0
+static constexpr int kStemPatchH = 18;
 
-template <int SA, int EG>
+template <int SA, int SX, int EG>
 struct StemLayout {
   static constexpr int kASlot = 128 * 128;                   // 128 pixels x 64 k (bf16)
   static constexpr int kBTile = 32 * 128;                    // this CTA's half of the 64 output channels
+  static constexpr int kXSlot = ((kStemPatchW * kStemPatchH * 7 * 4) + 1023) & ~1023;  // fp32 patch, Cin <= 7; keeps kStage 1024-aligned
   static constexpr int kA = 0;
   static constexpr int kB = kA + SA * kASlot;
-  static constexpr int kStage = kB + kBTile;
+  static constexpr int kX = kB + kBTile;
+  static constexpr int kStage = kX + SX * kXSlot;
   static constexpr int kVec = kStage + EG * kStageBytes;
   static constexpr int kRed = kVec + EG * 2 * 1024 * 4;
   static constexpr int kBar = kRed + EG * 4 * 64 * 2 * 4;
   static constexpr int kBuilderWarps = 2;
   static constexpr int kThreadsTotal = 64 + 128 * EG + 32 * kBuilderWarps;
-  static constexpr int kNumBar = 2 * SA + 1 + 4;
+  static constexpr int kNumBar = 2 * SA + 2 * SX + 1 + 4;
   static constexpr int kTmemPtr = kBar + kNumBar * 8;
   static constexpr int kTotal = kTmemPtr + 16;
   static constexpr int kDyn = kTotal + 1024;
   static constexpr int kTmemCols = 128;                      // two 64-column accumulators
+  static_assert(kStage % 1024 == 0 && kB % 1024 == 0, "128B-swizzled tiles must start on a 1024-byte boundary");
 };
 
-template <int SA, int EG>
+template <int SA, int SX, int EG>
 __global__ void __launch_bounds__(64 + 128 * EG + 64, 1) stem_gemm_kernel(const __grid_constant__ PixGemmParams p) {
-  using L = StemLayout<SA, EG>;
+  using L = StemLayout<SA, SX, EG>;
   constexpr int BLOCK_N = 64;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBar);
   uint64_t* fullA = bars;
   uint64_t* emptyA = fullA + SA;
-  uint64_t* fullB = emptyA + SA;
+  uint64_t* fullX = emptyA + SA;
+  uint64_t* emptyX = fullX + SX;
+  uint64_t* fullB = emptyX + SX;
   uint64_t* tmem_full = fullB + 1;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtr);
@@ -716,11 +853,13 @@ __global__ void __launch_bounds__(64 + 128 * EG + 64, 1) stem_gemm_kernel(const 
   if (threadIdx.x == 0) {
     // a tile is complete when the builder warps of BOTH CTAs have arrived on the leader's barrier
     for (int i = 0; i < SA; ++i) { mbar_init(&fullA[i], 2 * L::kBuilderWarps); mbar_init(&emptyA[i], 1); }
+    for (int i = 0; i < SX; ++i) { mbar_init(&fullX[i], 1); mbar_init(&emptyX[i], L::kBuilderWarps); }
     mbar_init(fullB, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
     fence_barrier_init();
     tma_prefetch_desc(&p.tmapB);
     tma_prefetch_desc(&p.tmapO[0]);
+    tma_prefetch_desc(&p.tmapX);
   }
   if (warp == 2) tmem_alloc_pair<L::kTmemCols>(tmem_ptr);
   {
@@ -735,6 +874,10 @@ __global__ void __launch_bounds__(64 + 128 * EG + 64, 1) stem_gemm_kernel(const 
       vec[1024 + i] = b;
       if (EG == 2) { vec[2048 + i] = 0.f; vec[3072 + i] = 0.f; }
     }
+    // zero the A ring once: the builders only ever write the chunks that hold k < 9 * Cin
+    uint4* a4 = reinterpret_cast<uint4*>(smem + L::kA);
+    for (int i = threadIdx.x; i < SA * L::kASlot / 16; i += L::kThreadsTotal) a4[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async();
   }
   tc_fence_before();
   cluster_sync();
@@ -755,11 +898,26 @@ __global__ void __launch_bounds__(64 + 128 * EG + 64, 1) stem_gemm_kernel(const 
   };
 
   constexpr int kFirstBuilderWarp = 2 + 4 * EG;
+  const int Cin = p.stem_cin;
   if (warp == 0) {
-    // ------------------------------------------------------------------ weights: one TMA load for the whole kernel
+    // ------------------------------------------------------------------ TMA: weights once, then one fp32 patch per tile
     if (lane == 0 && first_unit < num_units) {
       if (leader) mbar_arrive_expect_tx(fullB, 2 * L::kBTile);
       tma_load_2d_pair(smem + L::kB, &p.tmapB, mapa_cluster(smem_u32(fullB), 0), 0, (int)rank * 32);
+    }
+    __syncwarp();
+    const uint32_t patch_bytes = (uint32_t)(kStemPatchW * kStemPatchH * 4 * Cin);
+    int sx = 0, px = 0;
+    for (int u = first_unit; u < num_units; u += unit_stride) {
+      int nb, b, w0, h0;
+      decode(u, nb, b, w0, h0);
+      mbar_wait(&emptyX[sx], px ^ 1);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&fullX[sx], patch_bytes);
+        tma_load_4d(smem + L::kX + sx * L::kXSlot, &p.tmapX, &fullX[sx], w0 - 1 - kStemPatchX0, h0 - 1, 0, b);
+      }
+      __syncwarp();
+      if (++sx == SX) { sx = 0; px ^= 1; }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
@@ -786,32 +944,49 @@ __global__ void __launch_bounds__(64 + 128 * EG + 64, 1) stem_gemm_kernel(const 
   } else if (warp >= kFirstBuilderWarp) {
     // ------------------------------------------------------------------ A builders: 64 threads, two pixel rows each
     const int bt = threadIdx.x - kFirstBuilderWarp * 32;     // 0..63
-    const int Cin = p.stem_cin;
-    const float* __restrict__ x = p.stem_x;
-    int st = 0, ph = 0;
+    int st = 0, ph = 0, sx = 0, px = 0;
     for (int u = first_unit; u < num_units; u += unit_stride) {
-      int nb, b, w0, h0;
-      const bool valid = decode(u, nb, b, w0, h0);
+      mbar_wait(&fullX[sx], px);
       mbar_wait(&emptyA[st], ph ^ 1);
+      const float* xs = reinterpret_cast<const float*>(smem + L::kX + sx * L::kXSlot);
       uint8_t* slot = smem + L::kA + st * L::kASlot;
-#pragma unroll 1
+#pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
         const int row = bt + 64 * rr;
-        const int h = h0 + (row >> 3), w = w0 + (row & 7);
-        uint32_t packed[32];                                  // 64 bf16 = k 0..63
-        const bool inside = valid && h < p.H && w < p.W;
-        if (Cin == 3) stem_build_row<3>(x, b, h, w, p.H, p.W, Cin, inside, packed);
-        else stem_build_row<0>(x, b, h, w, p.H, p.W, Cin, inside, packed);
+        const float* xr = xs + (row >> 3) * kStemPatchW + (row & 7) + kStemPatchX0;   // tap (0, 0) of channel 0
         uint8_t* rowp = slot + row * 128;
+        if (Cin == 3) {
+          float v[28];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) =
-              make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+          for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[tap * 3 + c] = xr[(c * kStemPatchH + tap / 3) * kStemPatchW + tap % 3];
+          v[27] = 0.f;
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 14; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+          pk[14] = 0u; pk[15] = 0u;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        } else {
+          // generic 1..7 channels (not the benchmarked configuration): element-wise 2-byte stores
+          const int K = 9 * Cin;
+          for (int k = 0; k < K; ++k) {
+            const int tap = k / Cin, c = k - tap * Cin;
+            const float f = xr[(c * kStemPatchH + tap / 3) * kStemPatchW + tap % 3];
+            *reinterpret_cast<__nv_bfloat16*>(rowp + ((((k >> 3) ^ (row & 7)) << 4) | ((k & 7) << 1))) = __float2bfloat16(f);
+          }
+        }
       }
       fence_proxy_async();                                    // generic-proxy writes -> visible to the tensor core
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster_release(mapa_cluster(smem_u32(&fullA[st]), 0));
+      if (lane == 0) {
+        mbar_arrive(&emptyX[sx]);                             // the fp32 patch may be overwritten
+        mbar_arrive_cluster(mapa_cluster(smem_u32(&fullA[st]), 0));
+      }
       if (++st == SA) { st = 0; ph ^= 1; }
+      if (++sx == SX) { sx = 0; px ^= 1; }
     }
   } else {
     pix_pair_epilogue<BLOCK_N, EG, 1>(p, smem + L::kStage, vec, reinterpret_cast<float*>(smem + L::kRed), tmem_full, tmem_empty,
@@ -826,10 +1001,10 @@ __global__ void __launch_bounds__(64 + 128 * EG + 64, 1) stem_gemm_kernel(const 
 }
 
 static cudaError_t launch_stem_gemm(const PixGemmParams& p, int num_sms, cudaStream_t stream) {
-  constexpr int SA = 4, EG = 2;
-  using L = StemLayout<SA, EG>;
+  constexpr int SA = 4, SX = 4, EG = 2;
+  using L = StemLayout<SA, SX, EG>;
   static_assert(L::kDyn <= 232448, "shared memory budget exceeded");
-  auto kern = stem_gemm_kernel<SA, EG>;
+  auto kern = stem_gemm_kernel<SA, SX, EG>;
   static std::atomic<unsigned long long> attr_done{0};
   {
     cudaError_t ae = ensure_dynamic_smem(kern, L::kDyn, attr_done);
@@ -860,11 +1035,20 @@ static cudaError_t launch_stem_gemm(const PixGemmParams& p, int num_sms, cudaStr
 static cudaError_t launch_conv3_gemm(const PixGemmParams& p, int block_n, int num_sms, cudaStream_t stream) {
   if (p.G != 3 || p.R != 3 || !p.pair) return cudaErrorInvalidValue;
   const bool resident = block_n == 64 && p.n_blocks == 1 && p.kchunks <= 2;
+  if (p.in_scale && p.in_shift) {                            // operand = raw conv output: BN + ReLU applied in shared memory
+    switch (block_n) {
+      case 64: return resident ? launch_conv3<64, 10, 4, 3, 2, 2, true, true>(p, num_sms, stream)
+                               : launch_conv3<64, 10, 4, 3, 2, 2, false, true>(p, num_sms, stream);
+      case 128: return launch_conv3<128, 10, 4, 3, 2, 2, false, true>(p, num_sms, stream);
+      case 256: return launch_conv3<256, 10, 2, 3, 1, 1, false, true>(p, num_sms, stream);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   switch (block_n) {
-    case 64: return resident ? launch_conv3<64, 10, 4, 3, 2, 2, true>(p, num_sms, stream)
-                             : launch_conv3<64, 10, 4, 3, 2, 2, false>(p, num_sms, stream);
-    case 128: return launch_conv3<128, 10, 4, 3, 2, 2, false>(p, num_sms, stream);
-    case 256: return launch_conv3<256, 10, 2, 3, 1, 1, false>(p, num_sms, stream);
+    case 64: return resident ? launch_conv3<64, 10, 4, 3, 2, 2, true, false>(p, num_sms, stream)
+                             : launch_conv3<64, 10, 4, 3, 2, 2, false, false>(p, num_sms, stream);
+    case 128: return launch_conv3<128, 10, 4, 3, 2, 2, false, false>(p, num_sms, stream);
+    case 256: return launch_conv3<256, 10, 2, 3, 1, 1, false, false>(p, num_sms, stream);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -915,27 +1099,31 @@ cudaError_t launch_pix_gemm(const PixGemmParams& p, int block_n, int num_sms, cu
 // =============================================================================================
 //                                   weight-gradient GEMM
 // =============================================================================================
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, bool XF = false>
 struct WgLayout {
   static constexpr int kDY = 2 * 16 * kAtomBytes;                 // two 64-channel blocks of 128 pixels
   static constexpr int kX = (BLOCK_N / 64) * kASlotBytes;         // BLOCK_N/64 blocks of (16+2) rows
   static constexpr int kStageSz = kDY + kX;
   static constexpr int kBar = STAGES * kStageSz;
-  static constexpr int kNumBar = 2 * STAGES + 1;
+  static constexpr int kNumBar = 2 * STAGES + 1 + (XF ? STAGES : 0);
   static constexpr int kTmemPtr = kBar + kNumBar * 8;
   static constexpr int kTotal = kTmemPtr + 16;
   static constexpr int kDyn = kTotal + 1024;
   static constexpr int kTmemCols = 3 * BLOCK_N <= 128 ? 128 : (3 * BLOCK_N <= 256 ? 256 : 512);
 };
 
-template <int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(kThreads, 1) wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
-  using L = WgLayout<BLOCK_N, STAGES>;
+// XF: X is the raw output of the previous convolution; warps 2..5 (idle until the final accumulator drain) apply its
+// BatchNorm + ReLU to the X blocks of every stage in shared memory (bnrelu_patch) between the TMA load and the MMAs.
+static constexpr int kWgXfThreads = kThreads + 128;             // XF: warps 2..9 transform X; warps 2..5 drain the accumulator
+template <int BLOCK_N, int STAGES, bool XF>
+__global__ void __launch_bounds__(XF ? kWgXfThreads : kThreads, 1) wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
+  using L = WgLayout<BLOCK_N, STAGES, XF>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kBar);
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;
+  uint64_t* land = tmem_full + 1;                                  // XF: the stage's TMA loads have landed
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtr);
 
   const int warp = threadIdx.x >> 5;
@@ -955,7 +1143,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_gemm_kernel(const __grid_co
   const int dy_blocks = m_valid > 64 ? 2 : 1;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], XF ? 8 : 1); mbar_init(&empty[i], 1); }
+    if (XF) for (int i = 0; i < STAGES; ++i) mbar_init(&land[i], 1);
     mbar_init(tmem_full, 1);
     fence_barrier_init();
     tma_prefetch_desc(&p.tmapDY[p.dy_map[g]]);
@@ -978,12 +1167,13 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_gemm_kernel(const __grid_co
       mbar_wait(&empty[s], ph ^ 1);
       if (lane == 0) {
         uint8_t* st = smem + s * L::kStageSz;
-        mbar_arrive_expect_tx(&full[s], bytes);
+        uint64_t* bar = XF ? &land[s] : &full[s];
+        mbar_arrive_expect_tx(bar, bytes);
         for (int j = 0; j < dy_blocks; ++j)
-          tma_load_4d(st + j * 16 * kAtomBytes, &p.tmapDY[p.dy_map[g]], &full[s], p.dy_chan0 + mb * 128 + j * 64, w0,
+          tma_load_4d(st + j * 16 * kAtomBytes, &p.tmapDY[p.dy_map[g]], bar, p.dy_chan0 + mb * 128 + j * 64, w0,
                       h0, b);
         for (int j = 0; j < BLOCK_N / 64; ++j)
-          tma_load_4d(st + L::kDY + j * kASlotBytes, &p.tmapX[p.x_map[g]], &full[s],
+          tma_load_4d(st + L::kDY + j * kASlotBytes, &p.tmapX[p.x_map[g]], bar,
                       p.x_chan0 + nb * BLOCK_N + j * 64, w0 + p.x_dw[g], h0 + p.x_dh[g], b);
       }
       __syncwarp();
@@ -1020,6 +1210,25 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_gemm_kernel(const __grid_co
     }
     umma_commit_warp<false>(tmem_full);
   } else {
+    if (XF) {
+      const int tt = threadIdx.x - 64;                               // 0..255
+      int s = 0, ph = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int b = t / per_img, rem = t - b * per_img;
+        const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
+        mbar_wait(&land[s], ph);
+        uint8_t* xs = smem + s * L::kStageSz + L::kDY;
+#pragma unroll 1
+        for (int j = 0; j < BLOCK_N / 64; ++j)
+          bnrelu_patch<8, 256, 144, 4>(xs + j * kASlotBytes, tt, p.x_scale + nb * BLOCK_N + j * 64, p.x_shift + nb * BLOCK_N + j * 64,
+                               th * 16 + p.x_dh[g], tw * 8 + p.x_dw[g], p.H, p.W, true);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[s]);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+    if (warp < 6) {
     const int sub = warp & 3;
     const int row = sub * 32 + lane;
     mbar_wait(tmem_full, 0);
@@ -1047,6 +1256,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_gemm_kernel(const __grid_co
         }
       }
     }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -1056,11 +1266,11 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_gemm_kernel(const __grid_co
   }
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, bool XF>
 static cudaError_t launch_wg(const WgradParams& p, cudaStream_t stream) {
-  using L = WgLayout<BLOCK_N, STAGES>;
+  using L = WgLayout<BLOCK_N, STAGES, XF>;
   static_assert(L::kDyn <= 232448, "shared memory budget exceeded");
-  auto kern = wgrad_gemm_kernel<BLOCK_N, STAGES>;
+  auto kern = wgrad_gemm_kernel<BLOCK_N, STAGES, XF>;
   static std::atomic<unsigned long long> attr_done{0};   // per device: function attributes belong to the context
   {
     cudaError_t ae = ensure_dynamic_smem(kern, L::kDyn, attr_done);
@@ -1068,7 +1278,7 @@ static cudaError_t launch_wg(const WgradParams& p, cudaStream_t stream) {
   }
   const int grid = p.m_blocks * p.n_blocks * p.G * p.splits;
   if (grid <= 0) return cudaSuccess;
-  kern<<<grid, kThreads, L::kDyn, stream>>>(p);
+  kern<<<grid, XF ? kWgXfThreads : kThreads, L::kDyn, stream>>>(p);
   return launched();
 }
 
@@ -1082,28 +1292,29 @@ static cudaError_t launch_wg(const WgradParams& p, cudaStream_t stream) {
 // M = 128 MMA covers two taps (the second 64-row block is the same patch `LBO` bytes further: +128 B = next horizontal tap,
 // +1280 B = next vertical tap), so nine taps are five MMAs per 16-pixel K-step (the last with a duplicated block), N = 64.
 // Per 128-pixel tile: 39 KB of loads for 9 taps x 64 x 64 outputs, instead of 3 x 34 KB.
-template <int STAGES>
+template <int STAGES, bool XF = false>
 struct Wg9Layout {
   static constexpr int kDY = 16 * kAtomBytes;                     // 128 pixels x 64 output channels
   static constexpr int kXPatch = 18 * 10 * 128;
   static constexpr int kX = (kXPatch + 1023) & ~1023;
   static constexpr int kStageSz = kDY + kX;
   static constexpr int kBar = STAGES * kStageSz;
-  static constexpr int kNumBar = 2 * STAGES + 1;
+  static constexpr int kNumBar = 2 * STAGES + 1 + (XF ? STAGES : 0);
   static constexpr int kTmemPtr = kBar + kNumBar * 8;
   static constexpr int kTotal = kTmemPtr + 16;
   static constexpr int kDyn = kTotal + 1024;
   static constexpr int kTmemCols = 512;                           // five 64-column accumulators
 };
 
-template <int STAGES>
-__global__ void __launch_bounds__(kThreads, 1) wgrad9_gemm_kernel(const __grid_constant__ WgradParams p) {
-  using L = Wg9Layout<STAGES>;
+template <int STAGES, bool XF>
+__global__ void __launch_bounds__(XF ? kWgXfThreads : kThreads, 1) wgrad9_gemm_kernel(const __grid_constant__ WgradParams p) {
+  using L = Wg9Layout<STAGES, XF>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kBar);
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;
+  uint64_t* land = tmem_full + 1;                                  // XF: the stage's TMA loads have landed
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtr);
 
   const int warp = threadIdx.x >> 5;
@@ -1118,7 +1329,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad9_gemm_kernel(const __grid_c
   const int per_img = p.tiles_w * p.tiles_h;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], XF ? 8 : 1); mbar_init(&empty[i], 1); }
+    if (XF) for (int i = 0; i < STAGES; ++i) mbar_init(&land[i], 1);
     mbar_init(tmem_full, 1);
     fence_barrier_init();
     tma_prefetch_desc(&p.tmapDY[0]);
@@ -1139,9 +1351,10 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad9_gemm_kernel(const __grid_c
       mbar_wait(&empty[s], ph ^ 1);
       if (lane == 0) {
         uint8_t* st = smem + s * L::kStageSz;
-        mbar_arrive_expect_tx(&full[s], L::kDY + L::kXPatch);
-        tma_load_4d(st, &p.tmapDY[0], &full[s], p.dy_chan0, w0, h0, b);
-        tma_load_4d(st + L::kDY, &p.tmapX9, &full[s], p.x_chan0 + nb * 64, w0 - 1, h0 - 1, b);
+        uint64_t* bar = XF ? &land[s] : &full[s];
+        mbar_arrive_expect_tx(bar, L::kDY + L::kXPatch);
+        tma_load_4d(st, &p.tmapDY[0], bar, p.dy_chan0, w0, h0, b);
+        tma_load_4d(st + L::kDY, &p.tmapX9, bar, p.x_chan0 + nb * 64, w0 - 1, h0 - 1, b);
       }
       __syncwarp();
       if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -1175,6 +1388,22 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad9_gemm_kernel(const __grid_c
     }
     umma_commit_warp<false>(tmem_full);
   } else {
+    if (XF) {
+      const int tt = threadIdx.x - 64;                               // 0..255
+      int s = 0, ph = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        const int b = t / per_img, rem = t - b * per_img;
+        const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
+        mbar_wait(&land[s], ph);
+        bnrelu_patch<10, 256, 180, 5>(smem + s * L::kStageSz + L::kDY, tt, p.x_scale + nb * 64, p.x_shift + nb * 64, th * 16 - 1,
+                              tw * 8 - 1, p.H, p.W, true);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[s]);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+    if (warp < 6) {
     const int sub = warp & 3;
     const int row = sub * 32 + lane;           // accumulator row = (which tap of the pair) * 64 + input channel
     const int half = row >> 6, cin = row & 63;
@@ -1204,6 +1433,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad9_gemm_kernel(const __grid_c
         }
       }
     }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -1213,11 +1443,12 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad9_gemm_kernel(const __grid_c
   }
 }
 
+template <bool XF>
 static cudaError_t launch_wgrad9(const WgradParams& p, cudaStream_t stream) {
   constexpr int STAGES = 5;
-  using L = Wg9Layout<STAGES>;
+  using L = Wg9Layout<STAGES, XF>;
   static_assert(L::kDyn <= 232448, "shared memory budget exceeded");
-  auto kern = wgrad9_gemm_kernel<STAGES>;
+  auto kern = wgrad9_gemm_kernel<STAGES, XF>;
   static std::atomic<unsigned long long> attr_done{0};
   {
     cudaError_t ae = ensure_dynamic_smem(kern, L::kDyn, attr_done);
@@ -1226,15 +1457,17 @@ static cudaError_t launch_wgrad9(const WgradParams& p, cudaStream_t stream) {
   if (p.Mtot != 64 || p.G != 3 || p.R != 3) return cudaErrorInvalidValue;
   const int grid = p.n_blocks * p.splits;
   if (grid <= 0) return cudaSuccess;
-  kern<<<grid, kThreads, L::kDyn, stream>>>(p);
+  kern<<<grid, XF ? kWgXfThreads : kThreads, L::kDyn, stream>>>(p);
   return launched();
 }
 
 cudaError_t launch_wgrad_gemm(const WgradParams& p, int block_n, cudaStream_t stream) {
-  if (p.nine) return launch_wgrad9(p, stream);
+  const bool xf = p.x_scale && p.x_shift;
+  if (xf && (p.R != 3 || p.G != 3)) return cudaErrorInvalidValue;    // the X transform is built for the 3x3 convolutions
+  if (p.nine) return xf ? launch_wgrad9<true>(p, stream) : launch_wgrad9<false>(p, stream);
   switch (block_n) {
-    case 64: return launch_wg<64, 4>(p, stream);
-    case 128: return launch_wg<128, 3>(p, stream);
+    case 64: return xf ? launch_wg<64, 4, true>(p, stream) : launch_wg<64, 4, false>(p, stream);
+    case 128: return xf ? launch_wg<128, 3, true>(p, stream) : launch_wg<128, 3, false>(p, stream);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -1270,6 +1503,18 @@ int make_tmap_4d(CUtensorMap* out, const void* base, const uint64_t dims[4], con
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), d, s, b, e,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
+}
+
+int make_stem_tmap(CUtensorMap* out, const float* x, int B, int C, int H, int W) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -1;
+  cuuint64_t d[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
+  cuuint64_t s[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)C * H * W * 4};
+  cuuint32_t b[4] = {(cuuint32_t)kStemPatchW, (cuuint32_t)kStemPatchH, (cuuint32_t)C, 1};
+  cuuint32_t e[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), d, s, b, e, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
 }
 

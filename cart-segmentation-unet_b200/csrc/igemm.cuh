@@ -48,6 +48,13 @@ struct PixGemmParams {
   // memory from the fp32 NCHW image by two builder warps — no im2col matrix in HBM on the forward path.
   const float* stem_x;  // fp32 NCHW input image (non-null selects stem_gemm_kernel)
   int stem_cin;
+  CUtensorMap tmapX;    // fp32 (W, H, Cin, B) map over stem_x, box (16, 18, Cin, 1): make_stem_tmap
+  // conv3_gemm_kernel only: the A operand is the RAW output of the previous convolution; two transform warps apply that
+  // layer's BatchNorm + ReLU (relu(y * in_scale[c] + in_shift[c]), rounded to bf16 exactly as bn_relu_kernel stores it) to
+  // every patch in shared memory between the TMA load and the MMAs, and zero the pixels outside the image (the padding is
+  // zero AFTER the activation).  Indexed by input channel relative to a_chan0; null = plain operand.
+  const float* in_scale;
+  const float* in_shift;
 };
 
 cudaError_t launch_pix_gemm(const PixGemmParams& p, int block_n, int num_sms, cudaStream_t stream);
@@ -68,11 +75,16 @@ struct WgradParams {
   int Mtot, Ntot;          // Cout-like, Cin-like extents of dW
   int m_blocks, n_blocks;  // ceil(Mtot/128), Ntot/BLOCK_N
   int tiles_w, tiles_h, batch;
+  int H, W;                // image extent (the X transform zeroes the pixels outside it)
   int splits;              // split-K factor over pixel tiles
   float* dw;               // [G*R][Mtot][Ntot] fp32, accumulated atomically
   // wgrad9_gemm_kernel (3x3 convolutions with Cout == 64): all nine taps in one CTA from ONE (8+2) x (16+2) patch of X
   int nine;                // 1: use wgrad9_gemm_kernel with tmapX9
   CUtensorMap tmapX9;      // box (64 ch, 10, 18, 1)
+  // X is the RAW output of the previous convolution: the (otherwise idle) epilogue warps apply its BatchNorm + ReLU to
+  // every X patch in shared memory (see PixGemmParams::in_scale).  Indexed by channel relative to x_chan0; null = plain.
+  const float* x_scale;
+  const float* x_shift;
 };
 
 cudaError_t launch_wgrad_gemm(const WgradParams& p, int block_n, cudaStream_t stream);
@@ -83,5 +95,7 @@ int make_tmap_4d(CUtensorMap* out, const void* base, const uint64_t dims[4], con
                  const uint32_t box[4]);
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
                  uint32_t box_inner, uint32_t box_rows);
+// fp32 NCHW image as (W, H, C, B) with the stem's (16, 18, C, 1) patch box, no swizzle, zero fill outside the image
+int make_stem_tmap(CUtensorMap* out, const float* x, int B, int C, int H, int W);
 
 }  // namespace cs

@@ -71,6 +71,8 @@ struct HeadFwd { const float* w; const float* b; float* logits; int skip_store; 
 // materialises the last layer's activation, which the training path never stores)
 cudaError_t launch_bn_apply_relu(const bf16* y, long long P, int C, const float* scale, const float* shift, bf16* out,
                                  cudaStream_t s);
+// statistics -> (scale, shift, mean, invstd) + running statistics, nothing else (the consumer applies BN + ReLU itself)
+cudaError_t launch_bn_finalize(const BnFinalizeArgs& fin, cudaStream_t s);
 cudaError_t launch_bn_relu(const bf16* y, int B, int H, int W, int C, const BnFinalizeArgs& fin, bf16* out,
                            int out_pitch, int out_c0, bf16* pooled, const HeadFwd& head, cudaStream_t s);
 // relu/bn already applied (eval path): plain 2x2 max-pool of in[p][c0 + c] (pitch in_pitch) -> pooled (pitch C)

@@ -128,6 +128,18 @@ static int wgrad9_enabled() { static const int v = env_int("CARTSEG_WGRAD9", 1);
 // First convolution through stem_gemm_kernel (im2col rows built in shared memory); CARTSEG_STEM=0 restores
 // im2col_first_kernel + the pointwise GEMM on the forward path.
 static int stem_enabled() { static const int v = env_int("CARTSEG_STEM", 1); return v; }
+// CARTSEG_XFORM=1: BatchNorm + ReLU of every convX.0 / dconvX.0 is applied by its consumer convX.3 (transform warps on the
+// forward operand patch and on the weight gradient's X operand, igemm.cu bnrelu_patch) instead of an elementwise pass
+// that writes the activation: 3.1 GB less HBM traffic per K2 step and no activation buffer between the two convolutions
+// of a DoubleConv.  Default OFF — measured on B200 (round 2, K2, same box): 17.02 ms with it (layers with Cout >= 128
+// only: 17.01 ms) against 16.98 ms without.  The 0.74 ms of bn_relu passes it removes come back inside the GEMMs: the
+// transform's shared-memory reads and writes go through the same data pipe as the tensor core's operand fetches (ncu:
+// LSU 32 % + tensor-core 44 % of the pipe in wgrad<128>, the MMA warp waiting for operands a third of the time;
+// conv3<64>, already paced by operand bandwidth, 230 -> 363 us; wgrad<128> +70 us per launch; only the N = 256 layers,
+// which have bandwidth to spare, are unaffected).  More transform warps do not help (the pipe, not instruction issue,
+// is the limit).  Kept as an option with its own parity tests (tests/test_gpu_layers.py, test_gpu_unet_stages.py).
+static int xform_enabled() { static const int v = env_int("CARTSEG_XFORM", 0); return v; }
+static int xform_min_cout() { static const int v = env_int("CARTSEG_XFORM_MIN_COUT", 64); return v; }
 // TMA map over an NHWC buffer with a (64, pw, 18, 1) box: the whole halo patch of an 8 x 16 pixel tile.
 static int nhwc_patch_map(CUtensorMap* m, const bf16* base, int pitch, int B, int H, int W, int pw);
 
@@ -258,6 +270,8 @@ static void wgrad_common(WgradParams& p, int* block_n, int M, int N, int B, int 
   p.tiles_w = (W + 7) / 8;
   p.tiles_h = (H + 15) / 16;
   p.batch = B;
+  p.H = H;
+  p.W = W;
   const int tiles = p.tiles_w * p.tiles_h * B;
   const int base = p.m_blocks * p.n_blocks * G;
   p.splits = choose_wgrad_splits(base, tiles, 148);
@@ -333,6 +347,7 @@ struct ConvL {
   PixGemmParams fp_train, fp_eval, dg;
   WgradParams wg;
   int bn_f, bn_d, bn_w;
+  bool act_fused;                    // training: the activation is never stored; the next conv applies BN + ReLU to y itself
   double flops;                      // algorithmic 2*MACs of one pass (fprop == dgrad == wgrad)
 };
 struct UpL {
@@ -597,9 +612,19 @@ int encode_maps(cs_unet_plan* pl) {
     } else {
       CS_TRY(build_conv3x3(c.fp_eval, &c.bn_f, c.in, c.cin, c.out, c.cout, c.wf, B, c.H, c.W));
       if (train) {
-        CS_TRY(build_conv3x3(c.fp_train, &c.bn_f, c.in, c.cin, y, c.cout, c.wf, B, c.H, c.W));
+        // convX.3 reads the RAW output of convX.0 and applies its BatchNorm + ReLU in shared memory (forward operand and
+        // weight-gradient operand): the activation between the two convolutions of a DoubleConv never exists in HBM
+        ConvL& prev = pl->conv[i - 1];
+        const bool fused_in = (i % 2) == 1 && xform_enabled() && c.fp_eval.conv3 && c.cout >= xform_min_cout();
+        prev.act_fused = fused_in;
+        const View xin = fused_in ? View{prev.y, prev.cout, 0} : c.in;
+        CS_TRY(build_conv3x3(c.fp_train, &c.bn_f, xin, c.cin, y, c.cout, c.wf, B, c.H, c.W));
         CS_TRY(build_conv3x3(c.dg, &c.bn_d, dy, c.cout, c.g_in, c.cin, c.wd, B, c.H, c.W));
-        CS_TRY(build_conv3x3_wgrad(c.wg, &c.bn_w, c.in, c.cin, dy, c.cout, pl->dwp, B, c.H, c.W));
+        CS_TRY(build_conv3x3_wgrad(c.wg, &c.bn_w, xin, c.cin, dy, c.cout, pl->dwp, B, c.H, c.W));
+        if (fused_in) {
+          c.fp_train.in_scale = prev.scale; c.fp_train.in_shift = prev.shift;
+          c.wg.x_scale = prev.scale; c.wg.x_shift = prev.shift;
+        }
       }
     }
     c.fp_train.stat_sum = c.st_sum;
@@ -746,8 +771,13 @@ int cs_unet_forward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* x, 
     // The forward path builds the im2col rows inside stem_gemm_kernel.  The matrix itself is only needed by the first
     // convolution's weight gradient: cs_unet_backward writes it on its side stream, off the critical path — which is why
     // x has to stay valid until then (include/cartseg.h).
-    pl->conv[0].fp_train.stem_x = x; pl->conv[0].fp_train.stem_cin = pl->Cin;
-    pl->conv[0].fp_eval.stem_x = x; pl->conv[0].fp_eval.stem_cin = pl->Cin;
+    PixGemmParams& fp = training ? pl->conv[0].fp_train : pl->conv[0].fp_eval;
+    if (fp.stem_x != x) {                                    // the patch map over the caller's image (re-encoded when x moves)
+      if ((uintptr_t)x & 15) return fail("x must be 16-byte aligned");
+      const int r = make_stem_tmap(&fp.tmapX, x, B, pl->Cin, pl->H, pl->W);
+      if (r != 0) return fail("cuTensorMapEncodeTiled (stem image) failed: %d", r);
+      fp.stem_x = x; fp.stem_cin = pl->Cin;
+    }
     pl->x_keep = training ? x : nullptr;
   }
 
@@ -766,7 +796,8 @@ int cs_unet_forward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* x, 
       // — and does not store them at all: nothing reads the head's input in the training path (the BN backward of this
       // layer recomputes it from y for the head's weight gradient), 0.4 GB less traffic at K2
       const HeadFwd head = (i == 17 && fuse_head()) ? HeadFwd{t->param[80], t->param[81], logits, 1} : HeadFwd{nullptr, nullptr, nullptr, 0};
-      CS_CUDA(launch_bn_relu(c.y, B, c.H, c.W, c.cout, f, c.out.p, c.out.pitch, c.out.c0, c.pooled, head, s));
+      if (c.act_fused) CS_CUDA(launch_bn_finalize(f, s));    // the next convolution applies BN + ReLU to y on the fly
+      else CS_CUDA(launch_bn_relu(c.y, B, c.H, c.W, c.cout, f, c.out.p, c.out.pitch, c.out.c0, c.pooled, head, s));
     } else {
       CS_CUDA(timed(pl, conv_class(c.fp_eval, c.bn_f), c.flops, s, [&] { return launch_pix_gemm(c.fp_eval, c.bn_f, pl->num_sms, s); }));
       if (c.pooled) CS_CUDA(launch_maxpool(c.out.p, c.out.pitch, c.out.c0, B, c.H, c.W, c.cout, c.pooled, s));
@@ -1163,9 +1194,10 @@ int cs_unet_debug_read(cs_unet_plan* pl, int kind, int index, int dims_out[4], f
   if (dims_out) { dims_out[0] = pl->B; dims_out[1] = C; dims_out[2] = H; dims_out[3] = W; }
   if (!dst) return 0;
   if (!v.p) return fail("tensor (kind %d, index %d) does not exist in this plan", kind, index);
-  if (kind == 1 && index == 17 && fuse_head() && !pl->infer && pl->forward_done) {
-    // the training path never stores the last activation: rebuild it from y and the coefficients the forward published
-    const ConvL& c = pl->conv[17];
+  if (kind == 1 && !pl->infer && pl->forward_done && ((index == 17 && fuse_head()) || pl->conv[index].act_fused)) {
+    // the training path never stores this activation (the head / the next convolution consume y directly): rebuild it
+    // from y and the coefficients the forward published
+    const ConvL& c = pl->conv[index];
     CS_CUDA(launch_bn_apply_relu(c.y, c.P, c.cout, c.scale, c.shift, c.out.p, static_cast<cudaStream_t>(stream)));
   }
   if (kind == 3 && index == 17 && fuse_head()) {
@@ -1419,6 +1451,46 @@ int cs_conv3x3_fprop(const void* x, int batch, int height, int width, int cin, c
   p.stat_sum = stat_sum;
   p.stat_sq = stat_sq;
   CS_CUDA(launch_pix_gemm(p, bn, sms, s));
+  return 0;
+}
+
+int cs_conv3x3_fprop_bnrelu(const void* x_raw, const float* in_scale, const float* in_shift, int batch, int height, int width,
+                            int cin, const float* w_oihw, int cout, void* y, double* stat_sum, double* stat_sq, void* scratch,
+                            cs_stream_t stream) {
+  CS_TRY(check_layer(x_raw, y, scratch, batch, height, width, cin, cout));
+  if (!in_scale || !in_shift) return fail("layer op: null pointer");
+  if (((uintptr_t)in_scale | (uintptr_t)in_shift) & 15) return fail("layer op: in_scale / in_shift must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int sms, bn;
+  CS_TRY(layer_sm_count(&sms));
+  LayerScratch ls = carve(scratch, cin, cout);
+  CS_CUDA(launch_pack_pairs(w_oihw, cout, cin, 9, ls.wf, kTapFprop, ls.wd, kTapDgrad, s));
+  PixGemmParams p;
+  CS_TRY(build_conv3x3(p, &bn, View{(bf16*)x_raw, cin, 0}, cin, View{(bf16*)y, cout, 0}, cout, ls.wf, batch, height, width));
+  if (!p.conv3) return fail("layer op: the fused BN + ReLU operand needs conv3_gemm_kernel (CARTSEG_CONV3=0 is set)");
+  p.stat_sum = stat_sum;
+  p.stat_sq = stat_sq;
+  p.in_scale = in_scale;
+  p.in_shift = in_shift;
+  CS_CUDA(launch_pix_gemm(p, bn, sms, s));
+  return 0;
+}
+
+int cs_conv3x3_wgrad_bnrelu(const void* x_raw, const float* x_scale, const float* x_shift, const void* dy, int batch, int height,
+                            int width, int cin, int cout, float* dw_oihw, void* scratch, cs_stream_t stream) {
+  CS_TRY(check_layer(x_raw, dy, scratch, batch, height, width, cin, cout));
+  if (!dw_oihw || !x_scale || !x_shift) return fail("layer op: null pointer");
+  if (((uintptr_t)x_scale | (uintptr_t)x_shift) & 15) return fail("layer op: x_scale / x_shift must be 16-byte aligned");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int bn;
+  LayerScratch ls = carve(scratch, cin, cout);
+  WgradParams p;
+  CS_TRY(build_conv3x3_wgrad(p, &bn, View{(bf16*)x_raw, cin, 0}, cin, View{(bf16*)dy, cout, 0}, cout, ls.dwp, batch, height, width));
+  p.x_scale = x_scale;
+  p.x_shift = x_shift;
+  CS_CUDA(cudaMemsetAsync(ls.dwp, 0, (size_t)9 * cin * cout * sizeof(float), s));
+  CS_CUDA(launch_wgrad_gemm(p, bn, s));
+  CS_CUDA(launch_unpack_pairs(ls.dwp, cout, cin, 9, kTapWgrad, dw_oihw, s));
   return 0;
 }
 

@@ -275,6 +275,16 @@ int cs_conv3x3_fprop(const void* x_nhwc, int batch, int height, int width, int c
                      void* y_nhwc, double* stat_sum, double* stat_sq, void* scratch, cs_stream_t stream);
 int cs_conv3x3_dgrad(const void* dy_nhwc, int batch, int height, int width, int cin, const float* w_oihw, int cout,
                      void* dx_nhwc, void* scratch, cs_stream_t stream);
+/* The same convolution / weight gradient on relu(x_raw * scale[c] + shift[c]) (rounded to bf16), applied to the operand
+ * in shared memory: how convX.3 of a DoubleConv (src/create_testset.py:40-52) consumes the RAW output of convX.0 in
+ * training, so that the BatchNorm + ReLU activation between the two convolutions never exists in HBM.  scale / shift:
+ * fp32 [cin], 16-byte aligned. */
+int cs_conv3x3_fprop_bnrelu(const void* x_raw_nhwc, const float* in_scale, const float* in_shift, int batch, int height,
+                            int width, int cin, const float* w_oihw, int cout, void* y_nhwc, double* stat_sum,
+                            double* stat_sq, void* scratch, cs_stream_t stream);
+int cs_conv3x3_wgrad_bnrelu(const void* x_raw_nhwc, const float* x_scale, const float* x_shift, const void* dy_nhwc,
+                            int batch, int height, int width, int cin, int cout, float* dw_oihw, void* scratch,
+                            cs_stream_t stream);
 int cs_conv3x3_wgrad(const void* x_nhwc, const void* dy_nhwc, int batch, int height, int width, int cin, int cout,
                      float* dw_oihw, void* scratch, cs_stream_t stream);
 int cs_convT2x2_fprop(const void* x_nhwc, int batch, int height, int width, int cin, const float* w_iohw,

@@ -99,6 +99,60 @@ def test_conv3x3_wgrad(B, H, W, Cin, Cout):
     assert rel_l2(got, ref) < 2e-3                        # fp32 accumulate and fp32 output: no bf16 rounding
 
 
+def _bnrelu_operand(B, Cin, H, W, seed):
+    """Raw operand, per-channel affine (both signs of scale, shifts that leave ~half of the values positive) and the
+    activation the kernels must see: relu(fma(x, sc, sh)) rounded to bf16, as bn_relu_kernel stores it."""
+    g = torch.Generator().manual_seed(seed)
+    x = bf16_round(torch.randn(B, Cin, H, W, generator=g))
+    sc = (torch.rand(Cin, generator=g) + 0.5) * torch.where(torch.rand(Cin, generator=g) < 0.25, -1.0, 1.0)
+    sh = torch.randn(Cin, generator=g) * 0.5
+    act = bf16_round(torch.relu(torch.addcmul(sh.view(1, -1, 1, 1).double(), x.double(), sc.view(1, -1, 1, 1).double()).float()))
+    return x, sc, sh, act
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", CONV_SHAPES)
+def test_conv3x3_fprop_with_fused_bn_relu_operand(B, H, W, Cin, Cout):
+    """convX.3 of a DoubleConv reading the RAW output of convX.0 (create_testset.py:40-52): BN + ReLU applied to the
+    operand patch in shared memory, zero padding AFTER the activation (a shift > 0 must not leak into the border)."""
+    L, check = _lib()
+    x, sc, sh, act = _bnrelu_operand(B, Cin, H, W, 21)
+    w = _rand((Cout, Cin, 3, 3), 22, scale=(2.0 / (9 * Cin)) ** 0.5)
+    ref = F.conv2d(act, w, padding=1)
+    xg, wg, scg, shg = to_nhwc_bf16(x), w.cuda(), sc.cuda(), sh.cuda()
+    y = torch.full((B, H, W, Cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+    ssum = torch.zeros(Cout, dtype=torch.float64, device="cuda")
+    ssq = torch.zeros(Cout, dtype=torch.float64, device="cuda")
+    buf, scratch = layer_scratch(Cin, Cout)
+    check(L.cs_conv3x3_fprop_bnrelu(xg.data_ptr(), scg.data_ptr(), shg.data_ptr(), B, H, W, Cin, wg.data_ptr(), Cout,
+                                    y.data_ptr(), ssum.data_ptr(), ssq.data_ptr(), scratch, stream()), "cs_conv3x3_fprop_bnrelu")
+    torch.cuda.synchronize()
+    got = from_nhwc(y)
+    assert torch.isfinite(got).all()
+    assert rel_l2(got, ref) < 1e-2
+    np.testing.assert_allclose(got.numpy(), ref.numpy(), atol=2e-2 * ref.abs().max().item(), rtol=2e-2)
+    np.testing.assert_allclose(ssq.cpu().numpy(), (got.double() ** 2).sum((0, 2, 3)).numpy(), rtol=1e-4)
+    # the raw operand is left untouched in HBM
+    assert torch.equal(from_nhwc(xg), x)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", CONV_SHAPES)
+def test_conv3x3_wgrad_with_fused_bn_relu_operand(B, H, W, Cin, Cout):
+    L, check = _lib()
+    x, sc, sh, act = _bnrelu_operand(B, Cin, H, W, 23)
+    dy = _rand((B, Cout, H, W), 24)
+    wr = torch.zeros(Cout, Cin, 3, 3, requires_grad=True)
+    F.conv2d(act, wr, padding=1).backward(dy)
+    dw = torch.full((Cout, Cin, 3, 3), float("nan"), dtype=torch.float32, device="cuda")
+    buf, scratch = layer_scratch(Cin, Cout)
+    xg, dyg, scg, shg = to_nhwc_bf16(x), to_nhwc_bf16(dy), sc.cuda(), sh.cuda()
+    check(L.cs_conv3x3_wgrad_bnrelu(xg.data_ptr(), scg.data_ptr(), shg.data_ptr(), dyg.data_ptr(), B, H, W, Cin, Cout,
+                                    dw.data_ptr(), scratch, stream()), "cs_conv3x3_wgrad_bnrelu")
+    torch.cuda.synchronize()
+    got = dw.cpu()
+    assert torch.isfinite(got).all()
+    assert rel_l2(got, wr.grad) < 2e-3
+
+
 CONVT_SHAPES = [(2, 8, 8, 128, 64), (1, 14, 14, 256, 128), (2, 7, 7, 1024, 512), (1, 16, 24, 512, 256)]
 
 

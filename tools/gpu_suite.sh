@@ -102,6 +102,16 @@ for part in "$@"; do
                 -k regex:pix_gemm -c 12 -f -o gpurun_out/prof_pix python tools/profile_step.py && \
             run ncu_wgrad 900 ncu --profile-from-start off --set full --clock-control none --import-source on \
                 -k regex:wgrad -c 3 -f -o gpurun_out/prof_wgrad python tools/profile_step.py ;;
+    ncuxf) # ncu --set full of the first launch of each operand-transform (XF) kernel, matched on the demangled name
+            run ncu_xf_wgrad 900 ncu --profile-from-start off --set full --clock-control none --import-source on --kernel-name-base demangled \
+                -k regex:'wgrad_gemm_kernel<.int.128, .int.3, .bool.1>' -c 1 -f -o gpurun_out/prof_xf_wgrad python tools/profile_step.py
+            run ncu_xf_conv64 900 ncu --profile-from-start off --set full --clock-control none --import-source on --kernel-name-base demangled \
+                -k regex:'conv3_gemm_kernel<.int.64,.*bool.1, .bool.1>' -c 1 -f -o gpurun_out/prof_xf_conv64 python tools/profile_step.py ;;
+    ncun64) # ncu --set full of the stem kernel and the first Cout = 64 convolution (conv1.3 fprop, with BN statistics) / its dgrad
+            run ncu_stem 900 ncu --profile-from-start off --set full --clock-control none --import-source on \
+                -k regex:stem_gemm -c 1 -f -o gpurun_out/prof_stem python tools/profile_step.py
+            run ncu_conv64 900 ncu --profile-from-start off --set full --clock-control none --import-source on --kernel-name-base demangled \
+                -k regex:'conv3_gemm_kernel<.int.64,.*bool.1, .bool.0>' -c 1 -f -o gpurun_out/prof_conv64 python tools/profile_step.py ;;
     ncuone) run profile_plain 300 python tools/profile_step.py && \
             run ncu_one 900 ncu --profile-from-start off --set full --clock-control none --import-source on \
                 -k regex:${NCU_KERNEL:-pix_gemm} -s ${NCU_SKIP:-1} -c ${NCU_COUNT:-1} -f -o gpurun_out/${NCU_OUT:-prof_one} python tools/profile_step.py ;;
