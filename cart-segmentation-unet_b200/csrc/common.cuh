@@ -375,4 +375,29 @@ CS_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
 CS_DEVINL float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 CS_DEVINL float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
+// ----------------------------------------------------------------------------- packed fp32 pairs (sm_100: FFMA2)
+// Two fp32 values in one 64-bit register; fma.rn.f32x2 does both lanes in one instruction.  Used where a kernel is
+// paced by instruction issue rather than by memory (operand transforms, statistics epilogue, pooled BN backward).
+CS_DEVINL uint64_t f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+CS_DEVINL uint64_t bf16x2_to_f32x2(uint32_t w) {
+  uint64_t r;
+  asm("{\n\t.reg .b32 a, b;\n\tshl.b32 a, %1, 16;\n\tand.b32 b, %1, 0xffff0000;\n\tmov.b64 %0, {a, b};\n\t}" : "=l"(r) : "r"(w));
+  return r;
+}
+CS_DEVINL uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+CS_DEVINL uint32_t relu_pack_bf16x2(uint64_t v) {
+  uint32_t r;
+  asm("{\n\t.reg .f32 lo, hi;\n\tmov.b64 {lo, hi}, %1;\n\tcvt.rn.relu.bf16x2.f32 %0, hi, lo;\n\t}" : "=r"(r) : "l"(v));
+  return r;
+}
+CS_DEVINL void unpack_f32x2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+
 }  // namespace cs

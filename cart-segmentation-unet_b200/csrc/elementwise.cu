@@ -563,6 +563,72 @@ CS_DEVINL void pooled_unit(const BnBwdArgs& a, const BnCoef& k, int g, long long
   }
 }
 
+// Pooled layers, packed formulation (round 2).  The scalar version above costs ~17 instructions per element and the
+// pooled kernels were paced by instruction issue, not by HBM (B200, K2: reduce 2.9 TB/s, apply 3.4 TB/s, together 1.5 ms
+// of the backward critical path).  Here the two channels of a 32-bit word go through packed fp32 arithmetic
+// (fma.rn.f32x2 for activation and xhat, cvt.rn.relu.bf16x2 for the stored activation) and only the window logic — first
+// maximum of the bf16-rounded activations, exactly as the forward pooled them, and the ReLU mask — stays scalar: ~11
+// instructions per element.  xhat = y * invstd + (-mean * invstd).
+struct PoolCoef { uint64_t sc[4], sh[4], is[4], nm[4]; };
+CS_DEVINL void load_pool_coef(const BnBwdArgs& a, int g, PoolCoef& k) {
+  float sc[8], sh[8], mu[8], is[8];
+  load8(a.scale + g * 8, sc); load8(a.shift + g * 8, sh); load8(a.mean + g * 8, mu); load8(a.invstd + g * 8, is);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    k.sc[j] = f32x2(sc[2 * j], sc[2 * j + 1]);
+    k.sh[j] = f32x2(sh[2 * j], sh[2 * j + 1]);
+    k.is[j] = f32x2(is[2 * j], is[2 * j + 1]);
+    k.nm[j] = f32x2(-mu[2 * j] * is[2 * j], -mu[2 * j + 1] * is[2 * j + 1]);
+  }
+}
+// One channel of a window: a[d] = stored activations, g[d] = incoming gradients; on return g[d] = total gradient w.r.t.
+// the activation of pixel d (pooled gradient added at the FIRST maximum) with the ReLU mask applied.
+CS_DEVINL void pool_route(const float a[4], float g[4], float gp) {
+  const float bv = fmaxf(fmaxf(a[0], a[1]), fmaxf(a[2], a[3]));
+  const bool p0 = a[0] == bv;
+  const bool p1 = !p0 && a[1] == bv;
+  const bool p2 = !p0 && !p1 && a[2] == bv;
+  const bool p3 = !(p0 || p1 || p2);
+  g[0] = a[0] > 0.f ? (p0 ? g[0] + gp : g[0]) : 0.f;
+  g[1] = a[1] > 0.f ? (p1 ? g[1] + gp : g[1]) : 0.f;
+  g[2] = a[2] > 0.f ? (p2 ? g[2] + gp : g[2]) : 0.f;
+  g[3] = a[3] > 0.f ? (p3 ? g[3] + gp : g[3]) : 0.f;
+}
+// f(d, j, gd2, xh2): pixel d of the window, 32-bit word j (channels 2j, 2j+1), packed gradient and xhat.
+template <class F>
+CS_DEVINL void pooled_unit2(const BnBwdArgs& a, const PoolCoef& k, int g, long long unit, long long pix[4], F&& f) {
+  // window -> pixels with ONE 32-bit division: b * H + 2 * h2 == 2 * (unit / W2) because H == 2 * H2 (the 64-bit
+  // div / mod chain of the scalar version was a fifth of its instructions)
+  const unsigned W2 = (unsigned)a.W >> 1;
+  const unsigned row = (unsigned)unit / W2, w2 = (unsigned)unit - row * W2;
+  const long long p0 = (long long)(2u * row) * a.W + 2u * w2;
+  Vec8 yv8[4], gv8[4];
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+    pix[d] = p0 + (d >> 1) * a.W + (d & 1);
+    yv8[d] = ld8_nc(a.y + pix[d] * a.C + g * 8);
+    gv8[d] = ld8_nc(a.g + pix[d] * a.g_pitch + a.g_c0 + g * 8);
+  }
+  const Vec8 gp8 = ld8_nc(a.g_pool + unit * a.C + g * 8);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float alo[4], ahi[4], glo[4], ghi[4];
+    uint64_t xh[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      const uint64_t y2 = bf16x2_to_f32x2(yv8[d].w[j]);
+      const uint32_t aw = relu_pack_bf16x2(fma_f32x2(y2, k.sc[j], k.sh[j]));   // the activation as the forward stored it
+      alo[d] = bf16_lo(aw); ahi[d] = bf16_hi(aw);
+      xh[d] = fma_f32x2(y2, k.is[j], k.nm[j]);
+      glo[d] = bf16_lo(gv8[d].w[j]); ghi[d] = bf16_hi(gv8[d].w[j]);
+    }
+    pool_route(alo, glo, bf16_lo(gp8.w[j]));
+    pool_route(ahi, ghi, bf16_hi(gp8.w[j]));
+#pragma unroll
+    for (int d = 0; d < 4; ++d) f(d, j, f32x2(glo[d], ghi[d]), xh[d]);
+  }
+}
+
 static constexpr int kBnBwdThreads = 256;
 static constexpr int kBnBwdMaxBlocks = 148 * 4;
 
@@ -579,6 +645,11 @@ size_t bn_bwd_scratch_bytes(int maxC) { return (size_t)kBnBwdMaxBlocks * 4 * max
 // Measured alternatives (ncu totals of the 14 non-pooled launches of a k2 step, same box): three blocks per SM with 80
 // registers and 2 units in flight (spills): apply 1.71 / reduce 1.27 ms vs 1.31 / 1.12 ms for this shape; 4 units in
 // flight in the apply kernel (spills at 104 registers): 1.42 ms.
+// CARTSEG_POOL_PACKED=0 selects the scalar pooled kernels (same-box A/B runs).
+static bool pool_packed() {
+  static const bool v = [] { const char* e = getenv("CARTSEG_POOL_PACKED"); return !(e && e[0] == '0'); }();
+  return v;
+}
 static int bn_bwd_grid(const BnBwdArgs& a) {
   const int rpb = kBnBwdThreads / (a.C / 8);
   const long long units = a.g_pool ? (long long)a.B * (a.H / 2) * (a.W / 2) : (long long)a.B * a.H * a.W;
@@ -676,6 +747,93 @@ __global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(REGS) bn_bwd_reduce
   }
 }
 
+template <int REGS>
+__global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(REGS) bn_bwd_pool_reduce_kernel(BnBwdArgs a) {
+  const int cg = a.C >> 3;
+  const int g = threadIdx.x % cg, ri = threadIdx.x / cg, rpb = kBnBwdThreads / cg;
+  const long long units = (long long)a.B * (a.H >> 1) * (a.W >> 1);
+  PoolCoef k;
+  load_pool_coef(a, g, k);
+  uint64_t s1p[4], s2p[4];
+  const uint64_t one2 = f32x2(1.f, 1.f);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) s1p[j] = s2p[j] = 0ull;
+  for (long long u = (long long)blockIdx.x * rpb + ri; u < units; u += (long long)gridDim.x * rpb) {
+    long long pix[4];
+    pooled_unit2(a, k, g, u, pix, [&](int, int j, uint64_t gd2, uint64_t xh2) {
+      s1p[j] = fma_f32x2(gd2, one2, s1p[j]);
+      s2p[j] = fma_f32x2(gd2, xh2, s2p[j]);
+    });
+  }
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { unpack_f32x2(s1p[j], s1[2 * j], s1[2 * j + 1]); unpack_f32x2(s2p[j], s2[2 * j], s2[2 * j + 1]); }
+  // same partial layout as bn_bwd_reduce_kernel (fixed shuffle pattern, one row per row group, channel-major)
+  int rows_per_block, my_row;
+  bool writer;
+  if (cg <= 32) {
+#pragma unroll
+    for (int o = 16; o >= 8; o >>= 1) {
+      if (o >= cg) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
+          s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
+        }
+      }
+    }
+    rows_per_block = kBnBwdThreads / 32;
+    my_row = threadIdx.x >> 5;
+    writer = (threadIdx.x & 31) < cg;
+  } else {
+    rows_per_block = rpb;
+    my_row = ri;
+    writer = true;
+  }
+  if (writer) {
+    const size_t rows_total = (size_t)gridDim.x * rows_per_block;
+    const size_t r = (size_t)blockIdx.x * rows_per_block + my_row;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a.partial[(size_t)(g * 8 + j) * rows_total + r] = s1[j];
+      a.partial[(size_t)(a.C + g * 8 + j) * rows_total + r] = s2[j];
+    }
+  }
+}
+
+template <int REGS>
+__global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(REGS) bn_bwd_pool_apply_kernel(BnBwdArgs a) {
+  const int cg = a.C >> 3;
+  const int g = threadIdx.x % cg, ri = threadIdx.x / cg, rpb = kBnBwdThreads / cg;
+  const long long units = (long long)a.B * (a.H >> 1) * (a.W >> 1);
+  PoolCoef k;
+  load_pool_coef(a, g, k);
+  uint64_t nc1[4], nc2[4];
+  {
+    float c1[8], c2[8];
+    load8(a.c1 + g * 8, c1);
+    load8(a.c2 + g * 8, c2);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { nc1[j] = f32x2(-c1[2 * j], -c1[2 * j + 1]); nc2[j] = f32x2(-c2[2 * j], -c2[2 * j + 1]); }
+  }
+  const uint64_t one2 = f32x2(1.f, 1.f), zero2 = 0ull;
+  for (long long u = (long long)blockIdx.x * rpb + ri; u < units; u += (long long)gridDim.x * rpb) {
+    long long pix[4];
+    Vec8 out[4];
+    pooled_unit2(a, k, g, u, pix, [&](int d, int j, uint64_t gd2, uint64_t xh2) {
+      // dy = scale * (gd - c1 - xhat * c2)
+      uint64_t t = fma_f32x2(xh2, nc2[j], gd2);
+      t = fma_f32x2(t, one2, nc1[j]);
+      t = fma_f32x2(t, k.sc[j], zero2);
+      float lo, hi;
+      unpack_f32x2(t, lo, hi);
+      out[d].w[j] = pack_bf16x2(lo, hi);
+    });
+#pragma unroll
+    for (int d = 0; d < 4; ++d) st8(a.dy + pix[d] * a.C + g * 8, out[d]);
+  }
+}
+
 // s1/s2 totals -> per-channel means c1, c2 and the BN parameter gradients.  One block per channel: thread t sums the
 // partials of rows t, t+256, ... (contiguous in the channel-major layout) in fp64; warps and then the 8 warp sums are
 // combined in a fixed order (deterministic).
@@ -730,7 +888,8 @@ cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t s) {
   const int grid = bn_bwd_grid(a);
   if (a.g_pool) {
     if (a.head_dlogits) return cudaErrorInvalidValue;
-    bn_bwd_reduce_kernel<true, false, 1, 128><<<grid, kBnBwdThreads, 0, s>>>(a);
+    if (pool_packed()) bn_bwd_pool_reduce_kernel<128><<<grid, kBnBwdThreads, 0, s>>>(a);
+    else bn_bwd_reduce_kernel<true, false, 1, 128><<<grid, kBnBwdThreads, 0, s>>>(a);
   } else if (a.head_dlogits) {
     bn_bwd_reduce_kernel<false, true, 5, 128><<<grid, kBnBwdThreads, 0, s>>>(a);
   } else {
@@ -788,7 +947,8 @@ __global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(REGS) bn_bwd_apply_
 }
 cudaError_t launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t s) {
   const int grid = bn_bwd_grid(a);
-  if (a.g_pool) bn_bwd_apply_kernel<true, false, 1, 128><<<grid, kBnBwdThreads, 0, s>>>(a);
+  if (a.g_pool && pool_packed()) bn_bwd_pool_apply_kernel<128><<<grid, kBnBwdThreads, 0, s>>>(a);
+  else if (a.g_pool) bn_bwd_apply_kernel<true, false, 1, 128><<<grid, kBnBwdThreads, 0, s>>>(a);
   else if (a.head_dlogits) bn_bwd_apply_kernel<false, true, 5, 128><<<grid, kBnBwdThreads, 0, s>>>(a);
   else bn_bwd_apply_kernel<false, false, 3, 104><<<grid, kBnBwdThreads, 0, s>>>(a);
   return launched();
@@ -916,6 +1076,20 @@ cudaError_t launch_channel_sum(const bf16* g, int pitch, int c0, long long P, in
   if (e != cudaSuccess) return e;
   const int rpb = 256 / (C / 8);
   channel_sum_kernel<<<grid_for(P, rpb * 8, 148 * 4), 256, C * sizeof(float), s>>>(g, pitch, c0, P, C, out);
+  return launched();
+}
+
+// Conv-transpose bias gradient from the column sums the dgrad epilogue of dconvL.0 left behind (fp64, the statistics
+// machinery of the pixel GEMMs): out[c] = sum[c]; all `n` entries of sum / sq are zeroed again for the next step.
+__global__ void stat_to_bias_kernel(double* __restrict__ sum, double* __restrict__ sq, int n, int C, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (i < C) out[i] = (float)sum[i];
+  sum[i] = 0.0;
+  sq[i] = 0.0;
+}
+cudaError_t launch_stat_to_bias(double* sum, double* sq, int n, int C, float* out, cudaStream_t s) {
+  stat_to_bias_kernel<<<(n + 255) / 256, 256, 0, s>>>(sum, sq, n, C, out);
   return launched();
 }
 

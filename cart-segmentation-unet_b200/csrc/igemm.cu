@@ -49,26 +49,6 @@ CS_DEVINL void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" 
 // Eight channels: two packed fp32 FMAs per 32-bit word pair (fma.rn.f32x2, sm_100) and one cvt.rn.relu.bf16x2.f32 per
 // word — the same values as fmaxf(fmaf(y, sc, sh), 0) rounded to nearest-even.
 struct BnCoef8 { uint64_t sc[4], sh[4]; };                  // (sc[2j], sc[2j+1]) and (sh[2j], sh[2j+1]) as f32x2
-CS_DEVINL uint64_t f32x2(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-CS_DEVINL uint64_t bf16x2_to_f32x2(uint32_t w) {
-  uint64_t r;
-  asm("{\n\t.reg .b32 a, b;\n\tshl.b32 a, %1, 16;\n\tand.b32 b, %1, 0xffff0000;\n\tmov.b64 %0, {a, b};\n\t}" : "=l"(r) : "r"(w));
-  return r;
-}
-CS_DEVINL uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-CS_DEVINL uint32_t relu_pack_bf16x2(uint64_t v) {
-  uint32_t r;
-  asm("{\n\t.reg .f32 lo, hi;\n\tmov.b64 {lo, hi}, %1;\n\tcvt.rn.relu.bf16x2.f32 %0, hi, lo;\n\t}" : "=r"(r) : "l"(v));
-  return r;
-}
 // N vectors (16 bytes = 8 channels each) at p + i * STRIDE: all loads, then all unpacks, all FMAs, all packs, all stores
 // — written stage by stage so that the N x 4 independent word chains are interleaved: the warps that run this have a
 // scheduler to themselves, so every dependent instruction pair costs its full pipeline latency (ncu on the first version,

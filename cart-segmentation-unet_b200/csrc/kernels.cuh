@@ -111,6 +111,9 @@ cudaError_t launch_head_grad_act(const float* dlogits, long long P, int C, const
 // grad_b[c] = sum_p g[p][c0 + c]
 cudaError_t launch_channel_sum(const bf16* g, int pitch, int c0, long long P, int C, float* out, cudaStream_t s);
 
+// the same from per-channel fp64 column sums left by a pixel-GEMM epilogue: out[c] = sum[c] (c < C); sum / sq[0..n) reset to 0
+cudaError_t launch_stat_to_bias(double* sum, double* sq, int n, int C, float* out, cudaStream_t s);
+
 // ---- debug read-back ------------------------------------------------------------------------
 cudaError_t launch_nhwc_to_nchw_f32(const bf16* src, int pitch, int c0, int B, int H, int W, int C, float* dst,
                                     cudaStream_t s);

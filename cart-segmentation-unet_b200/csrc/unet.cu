@@ -139,6 +139,10 @@ static int stem_enabled() { static const int v = env_int("CARTSEG_STEM", 1); ret
 // which have bandwidth to spare, are unaffected).  More transform warps do not help (the pipe, not instruction issue,
 // is the limit).  Kept as an option with its own parity tests (tests/test_gpu_layers.py, test_gpu_unet_stages.py).
 static int xform_enabled() { static const int v = env_int("CARTSEG_XFORM", 0); return v; }
+// Conv-transpose bias gradients (pixel sums of the up-sampled half of the concat gradient) come out of the dgrad epilogue of
+// dconvL.0, which writes that tensor (its BN-statistics path: per-channel column sums of the stored bf16 tile, fp64
+// atomics) instead of a separate pass that re-reads 0.77 GB per K2 step; CARTSEG_UPBIAS_FUSED=0 restores channel_sum_kernel.
+static int upbias_fused() { static const int v = env_int("CARTSEG_UPBIAS_FUSED", 1); return v; }
 static int xform_min_cout() { static const int v = env_int("CARTSEG_XFORM_MIN_COUT", 64); return v; }
 // TMA map over an NHWC buffer with a (64, pw, 18, 1) box: the whole halo patch of an 8 x 16 pixel tile.
 static int nhwc_patch_map(CUtensorMap* m, const bf16* base, int pitch, int B, int H, int W, int pw);
@@ -342,6 +346,7 @@ struct ConvL {
   bf16 *y, *dy, *pooled, *g_pool;
   bf16 *wf, *wd;
   double *st_sum, *st_sq;
+  double *dg_sum, *dg_sq;            // dconvL.0 only: column sums of its dgrad output (the conv-transpose bias gradient)
   float *bc1, *bc2;
   float *scale, *shift, *mean, *invstd;
   PixGemmParams fp_train, fp_eval, dg;
@@ -591,6 +596,11 @@ void layout(cs_unet_plan* pl, uint8_t* base) {
     c.st_sq = c.st_sum + c.cout;
     c.bc1 = a.take<float>(2 * (size_t)c.cout);
     c.bc2 = c.bc1 + c.cout;
+    c.dg_sum = c.dg_sq = nullptr;
+    if (i >= 10 && (i % 2) == 0) {
+      c.dg_sum = a.take<double>(2 * (size_t)c.cin);
+      c.dg_sq = c.dg_sum + c.cin;
+    }
   }
   pl->stats_bytes = a.off - s0;
   pl->ws_bytes = (a.off + 1023) & ~(size_t)1023;
@@ -784,7 +794,7 @@ int cs_unet_forward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* x, 
   auto run_conv = [&](int i) -> int {
     ConvL& c = pl->conv[i];
     if (training) {
-      CS_CUDA(timed(pl, conv_class(c.fp_train, c.bn_f), c.flops, s, [&] { return launch_pix_gemm(c.fp_train, c.bn_f, pl->num_sms, s); }));
+      CS_CUDA(traced(pl, 1000 + i, s, [&] { return timed(pl, conv_class(c.fp_train, c.bn_f), c.flops, s, [&] { return launch_pix_gemm(c.fp_train, c.bn_f, pl->num_sms, s); }); }));
       BnFinalizeArgs f{};
       f.sum = c.st_sum; f.sq = c.st_sq; f.count = (double)c.P;
       f.gamma = t->param[c.pgamma]; f.beta = t->param[c.pbeta]; f.conv_bias = t->param[c.pb];
@@ -797,7 +807,7 @@ int cs_unet_forward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* x, 
       // layer recomputes it from y for the head's weight gradient), 0.4 GB less traffic at K2
       const HeadFwd head = (i == 17 && fuse_head()) ? HeadFwd{t->param[80], t->param[81], logits, 1} : HeadFwd{nullptr, nullptr, nullptr, 0};
       if (c.act_fused) CS_CUDA(launch_bn_finalize(f, s));    // the next convolution applies BN + ReLU to y on the fly
-      else CS_CUDA(launch_bn_relu(c.y, B, c.H, c.W, c.cout, f, c.out.p, c.out.pitch, c.out.c0, c.pooled, head, s));
+      else CS_CUDA(traced(pl, 1100 + i, s, [&] { return launch_bn_relu(c.y, B, c.H, c.W, c.cout, f, c.out.p, c.out.pitch, c.out.c0, c.pooled, head, s); }));
     } else {
       CS_CUDA(timed(pl, conv_class(c.fp_eval, c.bn_f), c.flops, s, [&] { return launch_pix_gemm(c.fp_eval, c.bn_f, pl->num_sms, s); }));
       if (c.pooled) CS_CUDA(launch_maxpool(c.out.p, c.out.pitch, c.out.c0, B, c.H, c.W, c.cout, c.pooled, s));
@@ -808,7 +818,7 @@ int cs_unet_forward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* x, 
   for (int k = 0; k < 4; ++k) {
     UpL& u = pl->up[k];
     u.fp.shift = t->param[u.pb];
-    CS_CUDA(timed(pl, pix_class(u.bn_f), u.flops, s, [&] { return launch_pix_gemm(u.fp, u.bn_f, pl->num_sms, s); }));
+    CS_CUDA(traced(pl, 1200 + k, s, [&] { return timed(pl, pix_class(u.bn_f), u.flops, s, [&] { return launch_pix_gemm(u.fp, u.bn_f, pl->num_sms, s); }); }));
     CS_TRY(run_conv(10 + 2 * k));
     CS_TRY(run_conv(11 + 2 * k));
   }
@@ -916,7 +926,11 @@ static int launch_conv_wgrad(cs_unet_plan* pl, int idx, float* gw, cudaStream_t 
 }
 static int launch_up_wgrad(cs_unet_plan* pl, int idx, float* gw, float* gb, cudaStream_t sw) {
   UpL& u = pl->up[idx];
-  if (gb) CS_CUDA(traced(pl, 900 + idx, sw, [&] { return launch_channel_sum(u.g_out.p, u.g_out.pitch, u.g_out.c0, 4 * u.P, u.cout, gb, sw); }));
+  if (gb) {
+    ConvL& d0 = pl->conv[10 + 2 * idx];                   // dconvL.0, whose dgrad wrote u.g_out
+    if (d0.dg.stat_sum) CS_CUDA(traced(pl, 900 + idx, sw, [&] { return launch_stat_to_bias(d0.dg_sum, d0.dg_sq, d0.cin, u.cout, gb, sw); }));
+    else CS_CUDA(traced(pl, 900 + idx, sw, [&] { return launch_channel_sum(u.g_out.p, u.g_out.pitch, u.g_out.c0, 4 * u.P, u.cout, gb, sw); }));
+  }
   if (gw) {
     CS_CUDA(cudaMemsetAsync(pl->dwp, 0, (size_t)4 * u.cin * u.cout * sizeof(float), sw));
     CS_CUDA(traced(pl, 800 + idx, sw, [&] { return timed(pl, wgrad_class(u.bn_w), u.flops, sw, [&] { return launch_wgrad_gemm(u.wg, u.bn_w, sw); }); }));
@@ -1042,6 +1056,11 @@ int cs_unet_backward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* dl
       }
       // Decoder convs always run their dgrad: it is the only writer of the concat-gradient buffer that the conv-transpose
       // weight / bias gradients read.  An encoder conv needs it only if something below it still trains.
+      if (c.dg_sum) {                                     // dconvL.0: its dgrad also sums the up-sampled half per channel
+        const bool want_bias = upbias_fused() && t->grad[pl->up[(idx - 10) / 2].pb] != nullptr;
+        c.dg.stat_sum = want_bias ? c.dg_sum : nullptr;
+        c.dg.stat_sq = want_bias ? c.dg_sq : nullptr;
+      }
       if (idx >= 10 || (idx > 0 && idx > frozen_encoder_convs))
         CS_CUDA(traced(pl, 300 + idx, s, [&] { return timed(pl, conv_class(c.dg, c.bn_d), c.flops, s, [&] { return launch_pix_gemm(c.dg, c.bn_d, pl->num_sms, s); }); }));
     } else {

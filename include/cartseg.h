@@ -117,8 +117,9 @@ int cs_unet_backward_held_stages(int* flush_stage, int* stages, int capacity);
 #define CS_UNET_NUM_PROFILE_CLASSES 9
 int cs_unet_profile(cs_unet_plan* plan, int enable);
 int cs_unet_profile_read(cs_unet_plan* plan, int n_classes, double* ms, double* flops, long long* launches);
-/* Developer timeline of cs_unet_backward: while enabled, every launch of the backward pass (both internal streams) is
- * bracketed by timing events.  cs_unet_trace_read waits for them and returns, per launch, a label (kind * 100 + layer:
+/* Developer timeline of cs_unet_forward (training mode) / cs_unet_backward: while enabled, the convolution, BatchNorm
+ * and conv-transpose launches of the forward pass (kinds 10 conv, 11 BN + ReLU pass, 12 conv-transpose) and every launch
+ * of the backward pass (both internal streams) are bracketed by timing events.  cs_unet_trace_read waits for them and returns, per launch, a label (kind * 100 + layer:
  * 1 BN-backward reduce, 2 BN-backward apply, 3 conv dgrad, 4 conv wgrad, 5 im2col of the input image, 6 head, 7 conv-transpose dgrad, 8 its wgrad,
  * 9 its bias gradient) and begin / end times in ms relative to the first launch.  Returns the number of entries. */
 int cs_unet_trace(cs_unet_plan* plan, int enable);

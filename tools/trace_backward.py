@@ -46,8 +46,20 @@ N = 512
 lab, t0, t1 = (C.c_int * N)(), (C.c_double * N)(), (C.c_double * N)()
 n = L.cs_unet_trace_read(plan.handle, N, lab, t0, t1)
 L.cs_unet_trace(plan.handle, 0)
-KIND = {1: "bn_reduce", 2: "bn_apply", 3: "dgrad", 4: "wgrad", 5: "im2col", 6: "head_bwd", 7: "up_dgrad", 8: "up_wgrad", 9: "up_bias"}
-rows = sorted((t0[i], t1[i], lab[i]) for i in range(n))
+KIND = {10: "fwd_conv", 11: "fwd_bn", 12: "fwd_up", 1: "bn_reduce", 2: "bn_apply", 3: "dgrad", 4: "wgrad", 5: "im2col", 6: "head_bwd", 7: "up_dgrad", 8: "up_wgrad", 9: "up_bias"}
+fwd = sorted((t0[i], t1[i], lab[i]) for i in range(n) if lab[i] >= 1000)
+if fwd:
+    print(f"# forward timeline (one stream), {len(fwd)} launches, {fwd[-1][1] - fwd[0][0]:.3f} ms from first launch to last completion")
+    print("#   begin     end     dur   gap-before  kernel")
+    prev = fwd[0][0]
+    for b, e, l in fwd:
+        print(f"{b - fwd[0][0]:9.3f} {e - fwd[0][0]:7.3f} {e - b:7.3f}  {b - prev:7.3f}     {KIND.get(l // 100, str(l // 100)):9s} {l % 100:2d}")
+        prev = e
+    print(f"# forward kernel time {sum(e - b for b, e, l in fwd):.3f} ms, gaps (incl. untraced stem / loss kernels) {fwd[-1][1] - fwd[0][0] - sum(e - b for b, e, l in fwd):.3f} ms")
+rows = sorted((t0[i], t1[i], lab[i]) for i in range(n) if lab[i] < 1000)
+base = rows[0][0]
+rows = [(b - base, e - base, l) for b, e, l in rows]
+n = len(rows)
 end = max(r[1] for r in rows)
 print(f"# backward timeline, {n} launches, {end:.3f} ms from first launch to last completion")
 print("#   begin     end     dur  stream  kernel        overlap with the other stream (ms)")
