@@ -645,7 +645,7 @@ size_t bn_bwd_scratch_bytes(int maxC) { return (size_t)kBnBwdMaxBlocks * 4 * max
 // Measured alternatives (ncu totals of the 14 non-pooled launches of a k2 step, same box): three blocks per SM with 80
 // registers and 2 units in flight (spills): apply 1.71 / reduce 1.27 ms vs 1.31 / 1.12 ms for this shape; 4 units in
 // flight in the apply kernel (spills at 104 registers): 1.42 ms.
-// CARTSEG_POOL_PACKED=0 selects the scalar pooled kernels (same-box A/B runs).
+// CARTSEG_POOL_PACKED=0 selects the scalar BN-backward kernels (pooled and plain layers; same-box A/B runs).
 static bool pool_packed() {
   static const bool v = [] { const char* e = getenv("CARTSEG_POOL_PACKED"); return !(e && e[0] == '0'); }();
   return v;
@@ -834,6 +834,132 @@ __global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(REGS) bn_bwd_pool_a
   }
 }
 
+// Plain (no pooling, no head) layers, packed formulation: the ReLU mask is taken from the fp32 pre-activation
+// v = fma(y, scale, shift) — the stored activation bf16(max(v, 0)) is positive exactly when v > 2^-134 (round to nearest
+// even: 2^-134 is the midpoint between 0 and the smallest bf16 subnormal 2^-133) — so the bf16 round trip of the
+// scalar version disappears; activation and xhat are one packed FMA per channel pair.  ~6 instructions per element
+// instead of ~12: these kernels share their SMs with a weight-gradient GEMM and are partly issue-bound.
+static constexpr float kBf16ReluThreshold = 4.591774807899561e-41f;   // 2^-134
+struct PlainUnit2 { Vec8 y, g; };
+CS_DEVINL void plain_load2(const BnBwdArgs& a, int g, long long pix, PlainUnit2& u) {
+  u.y = ld8_nc(a.y + pix * a.C + g * 8);
+  u.g = ld8_nc(a.g + pix * a.g_pitch + a.g_c0 + g * 8);
+}
+CS_DEVINL void plain_compute2(const PoolCoef& k, const PlainUnit2& u, uint64_t gm2[4], uint64_t xh2[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint64_t y2 = bf16x2_to_f32x2(u.y.w[j]);
+    float vlo, vhi;
+    unpack_f32x2(fma_f32x2(y2, k.sc[j], k.sh[j]), vlo, vhi);
+    const float glo = vlo > kBf16ReluThreshold ? bf16_lo(u.g.w[j]) : 0.f;
+    const float ghi = vhi > kBf16ReluThreshold ? bf16_hi(u.g.w[j]) : 0.f;
+    gm2[j] = f32x2(glo, ghi);
+    xh2[j] = fma_f32x2(y2, k.is[j], k.nm[j]);
+  }
+}
+template <int U, int REGS>
+__global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(REGS) bn_bwd_plain_reduce_kernel(BnBwdArgs a) {
+  const int cg = a.C >> 3;
+  const int g = threadIdx.x % cg, ri = threadIdx.x / cg, rpb = kBnBwdThreads / cg;
+  const long long units = (long long)a.B * a.H * a.W;
+  PoolCoef k;
+  load_pool_coef(a, g, k);
+  uint64_t s1p[4], s2p[4];
+  const uint64_t one2 = f32x2(1.f, 1.f);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) s1p[j] = s2p[j] = 0ull;
+  const long long stride = (long long)gridDim.x * rpb;
+  for (long long u0 = (long long)blockIdx.x * rpb + ri; u0 < units; u0 += U * stride) {
+    PlainUnit2 pu[U];
+#pragma unroll
+    for (int i = 0; i < U; ++i)
+      if (u0 + i * stride < units) plain_load2(a, g, u0 + i * stride, pu[i]);
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+      if (u0 + i * stride >= units) break;
+      uint64_t gm2[4], xh2[4];
+      plain_compute2(k, pu[i], gm2, xh2);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s1p[j] = fma_f32x2(gm2[j], one2, s1p[j]); s2p[j] = fma_f32x2(gm2[j], xh2[j], s2p[j]); }
+    }
+  }
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { unpack_f32x2(s1p[j], s1[2 * j], s1[2 * j + 1]); unpack_f32x2(s2p[j], s2[2 * j], s2[2 * j + 1]); }
+  int rows_per_block, my_row;
+  bool writer;
+  if (cg <= 32) {
+#pragma unroll
+    for (int o = 16; o >= 8; o >>= 1) {
+      if (o >= cg) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
+          s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
+        }
+      }
+    }
+    rows_per_block = kBnBwdThreads / 32;
+    my_row = threadIdx.x >> 5;
+    writer = (threadIdx.x & 31) < cg;
+  } else {
+    rows_per_block = rpb;
+    my_row = ri;
+    writer = true;
+  }
+  if (writer) {
+    const size_t rows_total = (size_t)gridDim.x * rows_per_block;
+    const size_t r = (size_t)blockIdx.x * rows_per_block + my_row;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a.partial[(size_t)(g * 8 + j) * rows_total + r] = s1[j];
+      a.partial[(size_t)(a.C + g * 8 + j) * rows_total + r] = s2[j];
+    }
+  }
+}
+template <int U, int REGS>
+__global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(REGS) bn_bwd_plain_apply_kernel(BnBwdArgs a) {
+  const int cg = a.C >> 3;
+  const int g = threadIdx.x % cg, ri = threadIdx.x / cg, rpb = kBnBwdThreads / cg;
+  const long long units = (long long)a.B * a.H * a.W;
+  PoolCoef k;
+  load_pool_coef(a, g, k);
+  uint64_t nc1[4], nc2[4];
+  {
+    float c1[8], c2[8];
+    load8(a.c1 + g * 8, c1);
+    load8(a.c2 + g * 8, c2);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { nc1[j] = f32x2(-c1[2 * j], -c1[2 * j + 1]); nc2[j] = f32x2(-c2[2 * j], -c2[2 * j + 1]); }
+  }
+  const uint64_t one2 = f32x2(1.f, 1.f), zero2 = 0ull;
+  const long long stride = (long long)gridDim.x * rpb;
+  for (long long u0 = (long long)blockIdx.x * rpb + ri; u0 < units; u0 += U * stride) {
+    PlainUnit2 pu[U];
+#pragma unroll
+    for (int i = 0; i < U; ++i)
+      if (u0 + i * stride < units) plain_load2(a, g, u0 + i * stride, pu[i]);
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+      const long long u = u0 + i * stride;
+      if (u >= units) break;
+      uint64_t gm2[4], xh2[4];
+      plain_compute2(k, pu[i], gm2, xh2);
+      Vec8 o;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint64_t t = fma_f32x2(xh2[j], nc2[j], gm2[j]);          // dy = scale * (gm - c1 - xhat * c2)
+        t = fma_f32x2(t, one2, nc1[j]);
+        t = fma_f32x2(t, k.sc[j], zero2);
+        float lo, hi;
+        unpack_f32x2(t, lo, hi);
+        o.w[j] = pack_bf16x2(lo, hi);
+      }
+      st8(a.dy + u * a.C + g * 8, o);
+    }
+  }
+}
+
 // s1/s2 totals -> per-channel means c1, c2 and the BN parameter gradients.  One block per channel: thread t sums the
 // partials of rows t, t+256, ... (contiguous in the channel-major layout) in fp64; warps and then the 8 warp sums are
 // combined in a fixed order (deterministic).
@@ -892,6 +1018,8 @@ cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t s) {
     else bn_bwd_reduce_kernel<true, false, 1, 128><<<grid, kBnBwdThreads, 0, s>>>(a);
   } else if (a.head_dlogits) {
     bn_bwd_reduce_kernel<false, true, 5, 128><<<grid, kBnBwdThreads, 0, s>>>(a);
+  } else if (pool_packed()) {
+    bn_bwd_plain_reduce_kernel<4, 104><<<grid, kBnBwdThreads, 0, s>>>(a);
   } else {
     bn_bwd_reduce_kernel<false, false, 4, 104><<<grid, kBnBwdThreads, 0, s>>>(a);
   }
@@ -950,6 +1078,7 @@ cudaError_t launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t s) {
   if (a.g_pool && pool_packed()) bn_bwd_pool_apply_kernel<128><<<grid, kBnBwdThreads, 0, s>>>(a);
   else if (a.g_pool) bn_bwd_apply_kernel<true, false, 1, 128><<<grid, kBnBwdThreads, 0, s>>>(a);
   else if (a.head_dlogits) bn_bwd_apply_kernel<false, true, 5, 128><<<grid, kBnBwdThreads, 0, s>>>(a);
+  else if (pool_packed()) bn_bwd_plain_apply_kernel<3, 104><<<grid, kBnBwdThreads, 0, s>>>(a);
   else bn_bwd_apply_kernel<false, false, 3, 104><<<grid, kBnBwdThreads, 0, s>>>(a);
   return launched();
 }
