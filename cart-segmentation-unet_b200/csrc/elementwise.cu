@@ -840,52 +840,93 @@ __global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(REGS) bn_bwd_pool_a
 // scalar version disappears; activation and xhat are one packed FMA per channel pair.  ~6 instructions per element
 // instead of ~12: these kernels share their SMs with a weight-gradient GEMM and are partly issue-bound.
 static constexpr float kBf16ReluThreshold = 4.591774807899561e-41f;   // 2^-134
-struct PlainUnit2 { Vec8 y, g; };
-CS_DEVINL void plain_load2(const BnBwdArgs& a, int g, long long pix, PlainUnit2& u) {
+// HEAD (the layer feeding the 1x1 head): the incoming gradient is bf16(dlogits[p] * w[c]) formed on the fly, and the
+// head's parameter gradients (sum dlogits * act, sum dlogits) ride along in the reduction — there the bf16-rounded
+// activation itself is needed, so it is produced with cvt.rn.relu.bf16x2 and the mask taken from it.
+template <bool HEAD> struct PlainUnit2 { Vec8 y, g; };
+template <> struct PlainUnit2<true> { Vec8 y; float dl; };
+template <bool HEAD>
+CS_DEVINL void plain_load2(const BnBwdArgs& a, int g, long long pix, PlainUnit2<HEAD>& u) {
   u.y = ld8_nc(a.y + pix * a.C + g * 8);
-  u.g = ld8_nc(a.g + pix * a.g_pitch + a.g_c0 + g * 8);
+  if constexpr (HEAD) u.dl = __ldg(a.head_dlogits + pix);
+  else u.g = ld8_nc(a.g + pix * a.g_pitch + a.g_c0 + g * 8);
 }
-CS_DEVINL void plain_compute2(const PoolCoef& k, const PlainUnit2& u, uint64_t gm2[4], uint64_t xh2[4]) {
+// gm2 / xh2: masked gradient and xhat per channel pair; act2 (HEAD only): the stored activation as fp32 pairs
+template <bool HEAD>
+CS_DEVINL void plain_compute2(const PoolCoef& k, const uint64_t* hw2, const PlainUnit2<HEAD>& u, uint64_t gm2[4], uint64_t xh2[4],
+                              uint64_t* act2) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const uint64_t y2 = bf16x2_to_f32x2(u.y.w[j]);
-    float vlo, vhi;
-    unpack_f32x2(fma_f32x2(y2, k.sc[j], k.sh[j]), vlo, vhi);
-    const float glo = vlo > kBf16ReluThreshold ? bf16_lo(u.g.w[j]) : 0.f;
-    const float ghi = vhi > kBf16ReluThreshold ? bf16_hi(u.g.w[j]) : 0.f;
-    gm2[j] = f32x2(glo, ghi);
+    const uint64_t v2 = fma_f32x2(y2, k.sc[j], k.sh[j]);
     xh2[j] = fma_f32x2(y2, k.is[j], k.nm[j]);
+    if constexpr (HEAD) {
+      const uint32_t aw = relu_pack_bf16x2(v2);
+      const float alo = bf16_lo(aw), ahi = bf16_hi(aw);
+      float olo, ohi;
+      unpack_f32x2(fma_f32x2(f32x2(u.dl, u.dl), hw2[j], 0ull), olo, ohi);
+      const uint32_t gw = pack_bf16x2(olo, ohi);             // as a stand-alone head backward would store it
+      gm2[j] = f32x2(alo > 0.f ? bf16_lo(gw) : 0.f, ahi > 0.f ? bf16_hi(gw) : 0.f);
+      act2[j] = f32x2(alo, ahi);
+    } else {
+      float vlo, vhi;
+      unpack_f32x2(v2, vlo, vhi);
+      gm2[j] = f32x2(vlo > kBf16ReluThreshold ? bf16_lo(u.g.w[j]) : 0.f, vhi > kBf16ReluThreshold ? bf16_hi(u.g.w[j]) : 0.f);
+    }
   }
 }
-template <int U, int REGS>
+CS_DEVINL void load_head_w2(const BnBwdArgs& a, int g, uint64_t hw2[4]) {
+  float hw[8];
+  load8(a.head_w + g * 8, hw);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) hw2[j] = f32x2(hw[2 * j], hw[2 * j + 1]);
+}
+template <bool HEAD, int U, int REGS>
 __global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(REGS) bn_bwd_plain_reduce_kernel(BnBwdArgs a) {
   const int cg = a.C >> 3;
   const int g = threadIdx.x % cg, ri = threadIdx.x / cg, rpb = kBnBwdThreads / cg;
   const long long units = (long long)a.B * a.H * a.W;
   PoolCoef k;
   load_pool_coef(a, g, k);
-  uint64_t s1p[4], s2p[4];
+  uint64_t hw2[4] = {0ull, 0ull, 0ull, 0ull};
+  if constexpr (HEAD) load_head_w2(a, g, hw2);
+  uint64_t s1p[4], s2p[4], s3p[4];
+  float sb = 0.f;
   const uint64_t one2 = f32x2(1.f, 1.f);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) s1p[j] = s2p[j] = 0ull;
+  for (int j = 0; j < 4; ++j) s1p[j] = s2p[j] = s3p[j] = 0ull;
+  const bool head_grads = HEAD && (a.head_grad_w != nullptr || a.head_grad_b != nullptr);
   const long long stride = (long long)gridDim.x * rpb;
   for (long long u0 = (long long)blockIdx.x * rpb + ri; u0 < units; u0 += U * stride) {
-    PlainUnit2 pu[U];
+    PlainUnit2<HEAD> pu[U];
 #pragma unroll
     for (int i = 0; i < U; ++i)
-      if (u0 + i * stride < units) plain_load2(a, g, u0 + i * stride, pu[i]);
+      if (u0 + i * stride < units) plain_load2<HEAD>(a, g, u0 + i * stride, pu[i]);
 #pragma unroll
     for (int i = 0; i < U; ++i) {
       if (u0 + i * stride >= units) break;
-      uint64_t gm2[4], xh2[4];
-      plain_compute2(k, pu[i], gm2, xh2);
+      uint64_t gm2[4], xh2[4], act2[4];
+      plain_compute2<HEAD>(k, hw2, pu[i], gm2, xh2, act2);
 #pragma unroll
       for (int j = 0; j < 4; ++j) { s1p[j] = fma_f32x2(gm2[j], one2, s1p[j]); s2p[j] = fma_f32x2(gm2[j], xh2[j], s2p[j]); }
+      if constexpr (HEAD) {
+        if (head_grads) {
+          const uint64_t dl2 = f32x2(pu[i].dl, pu[i].dl);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) s3p[j] = fma_f32x2(dl2, act2[j], s3p[j]);
+          sb += pu[i].dl;
+        }
+      }
     }
   }
-  float s1[8], s2[8];
+  float s1[8], s2[8], s3[8];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) { unpack_f32x2(s1p[j], s1[2 * j], s1[2 * j + 1]); unpack_f32x2(s2p[j], s2[2 * j], s2[2 * j + 1]); }
+  for (int j = 0; j < 4; ++j) {
+    unpack_f32x2(s1p[j], s1[2 * j], s1[2 * j + 1]);
+    unpack_f32x2(s2p[j], s2[2 * j], s2[2 * j + 1]);
+    unpack_f32x2(s3p[j], s3[2 * j], s3[2 * j + 1]);
+  }
+  // same partial layout as bn_bwd_reduce_kernel (fixed shuffle pattern, one row per row group, channel-major)
   int rows_per_block, my_row;
   bool writer;
   if (cg <= 32) {
@@ -896,6 +937,11 @@ __global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(REGS) bn_bwd_plain_
         for (int j = 0; j < 8; ++j) {
           s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
           s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
+        }
+        if (head_grads) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s3[j] += __shfl_xor_sync(0xffffffffu, s3[j], o);
+          sb += __shfl_xor_sync(0xffffffffu, sb, o);
         }
       }
     }
@@ -914,16 +960,20 @@ __global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(REGS) bn_bwd_plain_
     for (int j = 0; j < 8; ++j) {
       a.partial[(size_t)(g * 8 + j) * rows_total + r] = s1[j];
       a.partial[(size_t)(a.C + g * 8 + j) * rows_total + r] = s2[j];
+      if (head_grads) a.partial[(size_t)(2 * a.C + g * 8 + j) * rows_total + r] = s3[j];
     }
+    if (head_grads && g == 0) a.partial[(size_t)(3 * a.C) * rows_total + r] = sb;
   }
 }
-template <int U, int REGS>
+template <bool HEAD, int U, int REGS>
 __global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(REGS) bn_bwd_plain_apply_kernel(BnBwdArgs a) {
   const int cg = a.C >> 3;
   const int g = threadIdx.x % cg, ri = threadIdx.x / cg, rpb = kBnBwdThreads / cg;
   const long long units = (long long)a.B * a.H * a.W;
   PoolCoef k;
   load_pool_coef(a, g, k);
+  uint64_t hw2[4] = {0ull, 0ull, 0ull, 0ull};
+  if constexpr (HEAD) load_head_w2(a, g, hw2);
   uint64_t nc1[4], nc2[4];
   {
     float c1[8], c2[8];
@@ -935,16 +985,16 @@ __global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(REGS) bn_bwd_plain_
   const uint64_t one2 = f32x2(1.f, 1.f), zero2 = 0ull;
   const long long stride = (long long)gridDim.x * rpb;
   for (long long u0 = (long long)blockIdx.x * rpb + ri; u0 < units; u0 += U * stride) {
-    PlainUnit2 pu[U];
+    PlainUnit2<HEAD> pu[U];
 #pragma unroll
     for (int i = 0; i < U; ++i)
-      if (u0 + i * stride < units) plain_load2(a, g, u0 + i * stride, pu[i]);
+      if (u0 + i * stride < units) plain_load2<HEAD>(a, g, u0 + i * stride, pu[i]);
 #pragma unroll
     for (int i = 0; i < U; ++i) {
       const long long u = u0 + i * stride;
       if (u >= units) break;
-      uint64_t gm2[4], xh2[4];
-      plain_compute2(k, pu[i], gm2, xh2);
+      uint64_t gm2[4], xh2[4], act2[4];
+      plain_compute2<HEAD>(k, hw2, pu[i], gm2, xh2, act2);
       Vec8 o;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -1017,9 +1067,10 @@ cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t s) {
     if (pool_packed()) bn_bwd_pool_reduce_kernel<128><<<grid, kBnBwdThreads, 0, s>>>(a);
     else bn_bwd_reduce_kernel<true, false, 1, 128><<<grid, kBnBwdThreads, 0, s>>>(a);
   } else if (a.head_dlogits) {
-    bn_bwd_reduce_kernel<false, true, 5, 128><<<grid, kBnBwdThreads, 0, s>>>(a);
+    if (pool_packed()) bn_bwd_plain_reduce_kernel<true, 5, 128><<<grid, kBnBwdThreads, 0, s>>>(a);
+    else bn_bwd_reduce_kernel<false, true, 5, 128><<<grid, kBnBwdThreads, 0, s>>>(a);
   } else if (pool_packed()) {
-    bn_bwd_plain_reduce_kernel<4, 104><<<grid, kBnBwdThreads, 0, s>>>(a);
+    bn_bwd_plain_reduce_kernel<false, 4, 104><<<grid, kBnBwdThreads, 0, s>>>(a);
   } else {
     bn_bwd_reduce_kernel<false, false, 4, 104><<<grid, kBnBwdThreads, 0, s>>>(a);
   }
@@ -1077,8 +1128,9 @@ cudaError_t launch_bn_bwd_apply(const BnBwdArgs& a, cudaStream_t s) {
   const int grid = bn_bwd_grid(a);
   if (a.g_pool && pool_packed()) bn_bwd_pool_apply_kernel<128><<<grid, kBnBwdThreads, 0, s>>>(a);
   else if (a.g_pool) bn_bwd_apply_kernel<true, false, 1, 128><<<grid, kBnBwdThreads, 0, s>>>(a);
+  else if (a.head_dlogits && pool_packed()) bn_bwd_plain_apply_kernel<true, 5, 128><<<grid, kBnBwdThreads, 0, s>>>(a);
   else if (a.head_dlogits) bn_bwd_apply_kernel<false, true, 5, 128><<<grid, kBnBwdThreads, 0, s>>>(a);
-  else if (pool_packed()) bn_bwd_plain_apply_kernel<3, 104><<<grid, kBnBwdThreads, 0, s>>>(a);
+  else if (pool_packed()) bn_bwd_plain_apply_kernel<false, 3, 104><<<grid, kBnBwdThreads, 0, s>>>(a);
   else bn_bwd_apply_kernel<false, false, 3, 104><<<grid, kBnBwdThreads, 0, s>>>(a);
   return launched();
 }

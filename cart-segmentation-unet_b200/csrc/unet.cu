@@ -1007,10 +1007,6 @@ int cs_unet_backward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* dl
       // fly (BnBwdArgs::head_dlogits).  What is left of the head backward only produces parameter gradients, so it
       // goes to the weight-gradient stream, off the critical path.
       if (!t->param[80]) return fail("final_conv.weight is null");
-      // the im2col matrix of the input image, for the first convolution's weight gradient (last kernel of the pass):
-      // written now, on the side stream, while the main stream works on the decoder
-      if (pl->x_keep && frozen_encoder_convs == 0 && t->grad[pl->conv[0].pw])
-        CS_CUDA(traced(pl, 500, sw, [&] { return launch_im2col_first(pl->x_keep, B, pl->Cin, pl->H, pl->W, pl->col, sw); }));
       if (!fuse_head()) {
         CS_CUDA(launch_head_bwd(last.out.p, dlogits, last.P, 64, t->param[80], last.g_out.p, t->grad[80], t->grad[81], s));
         continue;
@@ -1026,6 +1022,12 @@ int cs_unet_backward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* dl
     } else if (kind == 1) {
       ConvL& c = pl->conv[idx];
       if (idx == defer_flush_conv()) CS_TRY(flush_held(pl, s, sw, overlap));
+      // The im2col matrix of the input image, for the first convolution's weight gradient (last kernel of the pass), is
+      // written on the side stream while the main stream is in the bottleneck level: its 0.4 GB of traffic then runs next
+      // to tensor-bound, HBM-light kernels.  (Issued at the start of the pass it took 1.0 ms at low priority next to the
+      // HBM-bound BatchNorm passes of the full-resolution decoder level and slowed those.)
+      if (idx == 9 && pl->x_keep && frozen_encoder_convs == 0 && t->grad[pl->conv[0].pw])
+        CS_CUDA(traced(pl, 500, sw, [&] { return launch_im2col_first(pl->x_keep, B, pl->Cin, pl->H, pl->W, pl->col, sw); }));
       if (idx < frozen_encoder_convs) continue;          // nothing below a frozen prefix needs gradients
       BnBwdArgs a{};
       a.g = c.g_out.p; a.g_pitch = c.g_out.pitch; a.g_c0 = c.g_out.c0;

@@ -240,3 +240,18 @@ def test_forward_and_backward_are_run_to_run_deterministic():
     # the activation-gradient chain has no atomics (fixed-order BN reductions): bit-identical run to run; weight
     # gradients are reduced with fp32 atomic adds across split-K CTAs: identical up to summation order
     assert not bwd_diff and worst[0] < 1e-4
+
+
+def test_stages_with_the_operand_transform_option():
+    """CARTSEG_XFORM=1 (convX.3 applies the BatchNorm + ReLU of convX.0 to its operand patch in shared memory, forward and
+    weight gradient; the activation between the two convolutions is never stored): the same teacher-forced stage checks
+    in a fresh process, because the option is read once per process.  Default is off (measured break-even)."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, CARTSEG_XFORM="1")
+    here = os.path.abspath(__file__)
+    r = subprocess.run([sys.executable, "-m", "pytest", here, "-q", "-x", "-m", "gpu", "--tb=short", "-k",
+                        "teacher_forced and (3-96-80 or 2-224-224)"], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "2 passed" in r.stdout, r.stdout[-2000:]
