@@ -304,7 +304,7 @@ cudaError_t launch_bn_finalize(const BnFinalizeArgs& fin, cudaStream_t s) {
 template <bool POOL>
 __global__ void __launch_bounds__(256, 4) bn_relu_kernel(const bf16* __restrict__ y, int B, int H, int W, int C, const BnFinalizeArgs fin,
                                bf16* __restrict__ out, int out_pitch, int out_c0, bf16* __restrict__ pooled,
-                               const HeadFwd head) {
+                               const HeadFwd head, const int rev) {
   // Fused statistics -> affine step (was a kernel of its own between the convolution and this pass): every block
   // derives (scale, shift) of all C channels into shared memory; block 0 also publishes them for the backward pass
   // and updates the running statistics.
@@ -319,10 +319,13 @@ __global__ void __launch_bounds__(256, 4) bn_relu_kernel(const bf16* __restrict_
   if (!POOL) {
     // The stride of the grid-stride loop is a multiple of the channel-group count (256 % cg == 0): a thread keeps its
     // channel group, so its coefficients live in registers; four 16-byte loads are in flight before the first use.
+    // The tensor is walked from its END to its beginning: the convolution that has just written y finished with the
+    // last tiles (still in the 126 MB L2), and the convolution that reads `out` next starts with the first ones, which
+    // this pass therefore writes last.  CARTSEG_BN_REVERSE=0 (rev == 0) restores the ascending order for A/B runs.
     const long long total = (long long)B * H * W * cg;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const int g = (int)(i0 % cg);
+    const int g = rev ? (int)((total - 1 - i0) % cg) : (int)(i0 % cg);
     float sc[8], sh[8], hw[8];
     *reinterpret_cast<float4*>(sc) = *reinterpret_cast<const float4*>(scale + g * 8);
     *reinterpret_cast<float4*>(sc + 4) = *reinterpret_cast<const float4*>(scale + g * 8 + 4);
@@ -337,12 +340,15 @@ __global__ void __launch_bounds__(256, 4) bn_relu_kernel(const bf16* __restrict_
     for (long long i = i0; i < total; i += U * stride) {
       Vec8 v[U];
 #pragma unroll
-      for (int k = 0; k < U; ++k)
-        if (i + k * stride < total) v[k] = ld8_nc(y + (i + k * stride) * 8);   // dense rows: (i / cg) * C + g * 8 == i * 8
+      for (int k = 0; k < U; ++k) {
+        const long long ik = rev ? total - 1 - (i + k * stride) : i + k * stride;
+        if (i + k * stride < total) v[k] = ld8_nc(y + ik * 8);                 // dense rows: (i / cg) * C + g * 8 == i * 8
+      }
 #pragma unroll
       for (int k = 0; k < U; ++k) {
         if (i + k * stride >= total) break;
-        const long long p = (i + k * stride) >> cg_shift;    // channel counts are powers of two
+        const long long ik = rev ? total - 1 - (i + k * stride) : i + k * stride;
+        const long long p = ik >> cg_shift;                  // channel counts are powers of two
         float f[8];
         unpack8(v[k], f);
 #pragma unroll
@@ -366,8 +372,9 @@ __global__ void __launch_bounds__(256, 4) bn_relu_kernel(const bf16* __restrict_
   } else {
     const int H2 = H >> 1, W2 = W >> 1;
     const long long total = (long long)B * H2 * W2 * cg;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
+    for (long long i_ = blockIdx.x * (long long)blockDim.x + threadIdx.x; i_ < total;
+         i_ += (long long)gridDim.x * blockDim.x) {
+      const long long i = rev ? total - 1 - i_ : i_;
       const int g = (int)(i % cg);
       const long long q = i / cg;                      // pooled pixel index
       const int w2 = (int)(q % W2);
@@ -401,15 +408,16 @@ __global__ void __launch_bounds__(256, 4) bn_relu_kernel(const bf16* __restrict_
 cudaError_t launch_bn_relu(const bf16* y, int B, int H, int W, int C, const BnFinalizeArgs& fin, bf16* out,
                            int out_pitch, int out_c0, bf16* pooled, const HeadFwd& head, cudaStream_t s) {
   const size_t smem = (size_t)2 * C * sizeof(float);
+  static const int rev = [] { const char* e = getenv("CARTSEG_BN_REVERSE"); return (e && e[0] == '0') ? 0 : 1; }();
   if (C < 8 || (C & (C - 1))) return cudaErrorInvalidValue;          // power-of-two channel counts (shift instead of divide)
   if (head.logits && (pooled || C != 64 || ((long long)B * H * W) % 4 != 0)) return cudaErrorInvalidValue;
   if (pooled) {
     bn_relu_kernel<true><<<grid_for((long long)B * (H / 2) * (W / 2) * (C / 8), 256), 256, smem, s>>>(
-        y, B, H, W, C, fin, out, out_pitch, out_c0, pooled, head);
+        y, B, H, W, C, fin, out, out_pitch, out_c0, pooled, head, rev);
   } else {
     // four resident blocks per SM (launch bounds; 64 KB of loads in flight per SM), two full waves
     bn_relu_kernel<false><<<grid_for((long long)B * H * W * (C / 8), 256 * 4, 148 * 8), 256, smem, s>>>(y, B, H, W, C, fin, out,
-                                                                                            out_pitch, out_c0, pooled, head);
+                                                                                            out_pitch, out_c0, pooled, head, rev);
   }
   return launched();
 }
@@ -758,7 +766,9 @@ __global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(REGS) bn_bwd_pool_r
   const uint64_t one2 = f32x2(1.f, 1.f);
 #pragma unroll
   for (int j = 0; j < 4; ++j) s1p[j] = s2p[j] = 0ull;
-  for (long long u = (long long)blockIdx.x * rpb + ri; u < units; u += (long long)gridDim.x * rpb) {
+  // a.reverse: from the last window to the first — the dgrad that produced g wrote its last tiles last (still in L2)
+  for (long long u_ = (long long)blockIdx.x * rpb + ri; u_ < units; u_ += (long long)gridDim.x * rpb) {
+    const long long u = a.reverse ? units - 1 - u_ : u_;
     long long pix[4];
     pooled_unit2(a, k, g, u, pix, [&](int, int j, uint64_t gd2, uint64_t xh2) {
       s1p[j] = fma_f32x2(gd2, one2, s1p[j]);
@@ -900,8 +910,8 @@ __global__ void __launch_bounds__(kBnBwdThreads) __maxnreg__(REGS) bn_bwd_plain_
   for (long long u0 = (long long)blockIdx.x * rpb + ri; u0 < units; u0 += U * stride) {
     PlainUnit2<HEAD> pu[U];
 #pragma unroll
-    for (int i = 0; i < U; ++i)
-      if (u0 + i * stride < units) plain_load2<HEAD>(a, g, u0 + i * stride, pu[i]);
+    for (int i = 0; i < U; ++i)   // a.reverse: from the last pixel to the first (the tail of g is the freshest in L2)
+      if (u0 + i * stride < units) plain_load2<HEAD>(a, g, a.reverse ? units - 1 - (u0 + i * stride) : u0 + i * stride, pu[i]);
 #pragma unroll
     for (int i = 0; i < U; ++i) {
       if (u0 + i * stride >= units) break;
@@ -1058,7 +1068,10 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(BnBwdArgs a, int r
   if (a.grad_conv_bias) a.grad_conv_bias[c] = 0.f;      // exactly zero: BN removes the bias again
 }
 
-cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t s) {
+cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a_in, cudaStream_t s) {
+  static const int rev = [] { const char* e = getenv("CARTSEG_BN_REVERSE_BWD"); return (e && e[0] == '0') ? 0 : 1; }();
+  BnBwdArgs a = a_in;
+  a.reverse = rev;
   const int cg = a.C / 8;
   if (cg > kBnBwdThreads || kBnBwdThreads % cg) return cudaErrorInvalidValue;
   const int grid = bn_bwd_grid(a);

@@ -94,6 +94,7 @@ struct BnBwdArgs {
   bf16* dy;                                // gradient w.r.t. the raw conv output (pitch C)
   float* grad_gamma; float* grad_beta; float* grad_conv_bias;
   int B, H, W, C;
+  int reverse;                             // set by the launchers: the reduction walks the tensor from its end (L2 reuse)
 };
 size_t bn_bwd_scratch_bytes(int maxC);
 cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a, cudaStream_t s);  // + finalize: c1/c2, grad_gamma/beta/bias
