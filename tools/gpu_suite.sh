@@ -61,7 +61,7 @@ for part in "$@"; do
     ncucalib) run cublas_plain 300 python tools/cublas_calib.py
             run ncu_cublas 900 ncu --set full --clock-control none -k regex:'gemm|nvjet|cutlass|sm100|sm90' -s 3 -c 2 -f -o gpurun_out/prof_cublas python tools/cublas_calib.py
             run ncu_conv3 1500 ncu --profile-from-start off --set full --clock-control none --import-source on \
-                -k regex:conv3_gemm -c 22 -f -o gpurun_out/prof_conv3 python tools/profile_step.py ;;
+                -k regex:conv3_gemm -c 8 -f -o gpurun_out/prof_conv3 python tools/profile_step.py ;;
     ncubn)  run ncu_bn 1200 ncu --profile-from-start off --set full --clock-control none --import-source on \
                 -k regex:'bn_bwd_apply_kernel<1|bn_bwd_reduce_kernel<1|bn_relu_kernel|bn_bwd_reduce_kernel<0, 1|bn_bwd_apply_kernel<0, 1' -c 40 -f -o gpurun_out/prof_bn python tools/profile_step.py ;;
     tracedp2) run trace_dp_2gpu 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29551 tools/trace_dp.py ;;

@@ -23,18 +23,30 @@ for i in range(18):
     convs.append((L, cin, cout))
 fc = lambda i: 2 * B * LH[convs[i][0]] ** 2 * convs[i][1] * convs[i][2] * (1 if i == 0 else 9)
 fu = lambda k: 2 * B * LH[5 - k] ** 2 * LC[5 - k] * LC[4 - k] * 4
-order = [("fprop", f"conv{i}", fc(i)) for i in range(10)]
+# Launches are matched per kernel family, in the order each family is issued (the two backward streams interleave in the
+# ncu list, so a single global order does not exist):
+#   conv family (stem / conv3_gemm / pix_gemm2 with CARTSEG_CONV3=0): fprop conv0..9, then per decoder level up-conv is
+#       in the pix family; dgrads conv17..1 in backward order
+#   pix family: conv-transpose fprop up0..3, then their dgrads up3..0
+#   wgrad family (side stream): conv17, conv16, up3, conv15, conv14, up2, conv13, conv12, up1, conv11, conv10, up0, conv9..0
+fam = lambda kn: "wgrad" if "wgrad" in kn else ("pix" if kn.startswith("pix_gemm2") else "conv")
+seq = {"conv": [("fprop", f"conv{i}", fc(i)) for i in range(10)], "pix": [], "wgrad": []}
 for k in range(4):
-    order += [("fprop", f"up{k}", fu(k)), ("fprop", f"conv{10+2*k}", fc(10 + 2 * k)), ("fprop", f"conv{11+2*k}", fc(11 + 2 * k))]
+    seq["pix"].append(("fprop", f"up{k}", fu(k)))
+    seq["conv"] += [("fprop", f"conv{10+2*k}", fc(10 + 2 * k)), ("fprop", f"conv{11+2*k}", fc(11 + 2 * k))]
+for i in range(17, 0, -1):
+    seq["conv"].append(("dgrad", f"conv{i}", fc(i)))
 for k in (3, 2, 1, 0):
-    for i in (11 + 2 * k, 10 + 2 * k):
-        order += [("wgrad", f"conv{i}", fc(i)), ("dgrad", f"conv{i}", fc(i))]
-    order += [("wgrad", f"up{k}", fu(k)), ("dgrad", f"up{k}", fu(k))]
-for i in range(9, -1, -1):
-    order.append(("wgrad", f"conv{i}", fc(i)))
-    if i > 0:
-        order.append(("dgrad", f"conv{i}", fc(i)))
-assert len(order) == len(gem), (len(order), len(gem))
+    seq["pix"].append(("dgrad", f"up{k}", fu(k)))
+    seq["wgrad"] += [("wgrad", f"conv{11+2*k}", fc(11 + 2 * k)), ("wgrad", f"conv{10+2*k}", fc(10 + 2 * k)), ("wgrad", f"up{k}", fu(k))]
+seq["wgrad"] += [("wgrad", f"conv{i}", fc(i)) for i in range(9, -1, -1)]
+pos = {k: 0 for k in seq}
+order = []
+for kn, us in gem:
+    f = fam(kn)
+    assert pos[f] < len(seq[f]), (f, kn)
+    order.append(seq[f][pos[f]]); pos[f] += 1
+assert all(pos[f] == len(seq[f]) for f in seq), pos
 tot_t = tot_f = 0
 for (kind, name, fl), (kn, us) in zip(order, gem):
     if name.startswith("conv"):
