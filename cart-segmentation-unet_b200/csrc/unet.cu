@@ -899,7 +899,7 @@ static int ensure_streams(cs_unet_plan* pl) {
 // do share SMs with a resident wgrad CTA (no shared memory, <= 104 registers) and leave the tensor pipe idle.  So the
 // deep, HBM-light wgrads (levels 3-5: conv 4..13, upconv4/3) CAN be enqueued only when the main stream reaches conv
 // `flush_conv` (CARTSEG_DEFER_WGRAD=1, CARTSEG_DEFER_FLUSH_CONV=n).  Measured on B200 (round 2, k2,
-// profiles/r2_k2_backward_timeline_deferred.txt): the main stream then finishes at 10.1 ms instead of 11.4 ms — every
+// profiles/r2_midround_k2_backward_timeline_deferred.txt): the main stream then finishes at 10.1 ms instead of 11.4 ms — every
 // conv-transpose dgrad runs in 0.07 ms — but the held wgrads run 1.6-2.5x slower next to the BatchNorm passes they were
 // meant to hide under (one issuing warp against 16 memory-bound warps per SM) and nine of them are still queued when the
 // main stream ends: 11.60 ms either way, step 18.08 vs 17.93 ms.  Default OFF.

@@ -73,7 +73,7 @@ def main():
     sync.trace = None
     dist.barrier()
     if rank == 0:
-        KIND = {1: "bn_reduce", 2: "bn_apply", 3: "dgrad", 4: "wgrad", 5: "im2col", 6: "head_bwd", 7: "up_dgrad", 8: "up_wgrad", 9: "up_bias"}
+        KIND = {10: "fwd_conv", 11: "fwd_bn", 12: "fwd_up", 1: "bn_reduce", 2: "bn_apply", 3: "dgrad", 4: "wgrad", 5: "im2col", 6: "head_bwd", 7: "up_dgrad", 8: "up_wgrad", 9: "up_bias"}
         side = {4, 5, 6, 8, 9}
         # the compute trace is relative to its own first launch; `mark` was recorded just before it on the same stream
         first_kernel = min(t0[i] for i in range(n))
