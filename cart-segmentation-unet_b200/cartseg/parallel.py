@@ -19,9 +19,18 @@ import torch
 import torch.distributed as dist
 
 
-# Bucket size of the gradient all-reduce.  Measured on 2 x B200 in one box (k2, ms per step): 16 MB 19.01 / 19.04,
+# Bucket size of the gradient all-reduce.  Measured on 2 x B200 in one box (round 1, k2, ms per step): 16 MB 19.01 / 19.04,
 # 4 MB 19.18 / 19.20, 2 MB 19.50, one bucket after the whole backward (no overlap) 19.52; single GPU 18.8.
+# On 8 x B200 (round 2, k2, one box, tools/dp8_buckets.sh): 16 MB 17.49, 48 MB 17.39, ONE bucket after the backward pass
+# 17.26 ms — with eight ranks every overlapped all-reduce holds SMs that the single-wave persistent GEMM grids then
+# miss (a kernel launched while NCCL is resident runs a second, nearly empty wave), which costs more than the ~0.8 ms the
+# exposed 124 MB all-reduce takes.  Hence: overlapped 16 MB buckets up to 2 ranks, one bucket from 4 ranks on.
 DEFAULT_BUCKET_MB = 16.0
+LARGE_WORLD_BUCKET_MB = 1.0e5
+
+
+def default_bucket_mb(world: int) -> float:
+    return DEFAULT_BUCKET_MB if world <= 2 else LARGE_WORLD_BUCKET_MB
 
 
 def plan_buckets(stage_off: Sequence[int], bucket_elems: int) -> List[Tuple[int, int]]:
@@ -127,7 +136,7 @@ def init_data_parallel(model, group: Optional[dist.ProcessGroup] = None, bucket_
     import os
     from . import ops
     if bucket_mb is None:
-        bucket_mb = float(os.environ.get("CARTSEG_DP_BUCKET_MB", DEFAULT_BUCKET_MB))
+        bucket_mb = float(os.environ.get("CARTSEG_DP_BUCKET_MB", default_bucket_mb(dist.get_world_size(group))))
     if not reserve_sms:
         reserve_sms = int(os.environ.get("CARTSEG_DP_RESERVE_SMS", "0"))
     if wire_dtype is None:
