@@ -255,3 +255,21 @@ def test_stages_with_the_operand_transform_option():
                         "teacher_forced and (3-96-80 or 2-224-224)"], env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "2 passed" in r.stdout, r.stdout[-2000:]
+
+
+def test_stages_with_the_alternative_kernels_selected():
+    """Every same-box A/B knob at its non-default value at once (round-1 pixel GEMM for the 3x3 convolutions, im2col +
+    pointwise stem, wgrad_gemm for Cout = 64, stand-alone head kernels, scalar BN-backward kernels, channel_sum for the
+    conv-transpose bias, ascending BN traversal): the alternatives the measurements in DESIGN.md were taken against stay
+    correct — same teacher-forced stage checks, fresh process (the knobs are read once per process)."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, CARTSEG_CONV3="0", CARTSEG_STEM="0", CARTSEG_WGRAD9="0", CARTSEG_FUSE_HEAD="0",
+               CARTSEG_POOL_PACKED="0", CARTSEG_UPBIAS_FUSED="0", CARTSEG_BN_REVERSE="0", CARTSEG_BN_REVERSE_BWD="0",
+               CARTSEG_WGRAD_AFTER_UP="0")
+    here = os.path.abspath(__file__)
+    r = subprocess.run([sys.executable, "-m", "pytest", here, "-q", "-x", "-m", "gpu", "--tb=short", "-k",
+                        "teacher_forced and 3-96-80"], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "1 passed" in r.stdout, r.stdout[-2000:]
