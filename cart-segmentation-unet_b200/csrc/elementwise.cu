@@ -1072,6 +1072,7 @@ cudaError_t launch_bn_bwd_reduce(const BnBwdArgs& a_in, cudaStream_t s) {
   static const int rev = [] { const char* e = getenv("CARTSEG_BN_REVERSE_BWD"); return (e && e[0] == '0') ? 0 : 1; }();
   BnBwdArgs a = a_in;
   a.reverse = rev;
+  if ((long long)a.B * a.H * a.W >= (1ll << 31)) return cudaErrorInvalidValue;   // the pooled kernels index windows in 32 bits
   const int cg = a.C / 8;
   if (cg > kBnBwdThreads || kBnBwdThreads % cg) return cudaErrorInvalidValue;
   const int grid = bn_bwd_grid(a);
