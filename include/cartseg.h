@@ -91,7 +91,7 @@ int cs_unet_backward(cs_unet_plan* plan, const cs_unet_tensors* t, const float* 
 /* Per-launch timing of the tensor-core kernels (bench.py's roofline): while enabled, every implicit-GEMM launch of
  * cs_unet_forward / cs_unet_backward is bracketed by CUDA events on the launch stream.  cs_unet_profile_read waits for
  * the recorded events and returns, per kernel class, the summed device time (ms), algorithmic FLOPs (2*MACs) and
- * launch count since the last read.  Classes: 0-2 pix_gemm2_kernel N=256 / 128 / 64 (conv-transposes, the stem),
+ * launch count since the last read.  Classes: 0-1 pix_gemm2_kernel N=256 / 128 (conv-transposes), 2 stem_gemm_kernel (first convolution),
  * 3-4 wgrad_gemm_kernel N=128 / 64, 5-7 conv3_gemm_kernel N=256 / 128 / 64 (3x3 convolutions, fprop and dgrad),
  * 8 wgrad9_gemm_kernel (3x3 weight gradients with Cout = 64). */
 /* cs_unet_backward runs the weight-gradient GEMMs on an internal lower-priority stream so that they overlap the
