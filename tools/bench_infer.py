@@ -27,7 +27,7 @@ from bench import synth_batch                   # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--size", type=int, default=224)
 ap.add_argument("--batches", default="1,2,4,8,16,32,64,128,256,512")
-ap.add_argument("--iters", type=int, default=10)
+ap.add_argument("--iters", type=int, default=30)
 ap.add_argument("--graph-max-batch", type=int, default=64)
 args = ap.parse_args()
 GFLOP_FWD = {224: 73.756, 512: 385.339}[args.size]
