@@ -194,6 +194,19 @@ CS_DEVINL void pix_pair_epilogue(const PixGemmParams& p, uint8_t* stage_base, fl
 #pragma unroll
         for (int i = 0; i < 32; ++i) packed[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
       }
+      if (BLOCK_N == 64 && EG == 2 && p.head_logits != nullptr) {
+        // fused 1x1 head (eval): this thread holds all 64 channels of its pixel; the activation tile is not stored
+        const float* hw = vec + 2048;                      // head weights (group 1's statistics slots: unused in eval)
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          acc = fmaf(bf16_lo(packed[i]), hw[2 * i], acc);
+          acc = fmaf(bf16_hi(packed[i]), hw[2 * i + 1], acc);
+        }
+        const int ph = h0 + (row >> 3), pw = w0 + (row & 7);
+        if (valid && ph < p.H && pw < p.W) p.head_logits[((size_t)b * p.H + ph) * p.W + pw] = acc + hw[64];
+        continue;
+      }
       {
         uint8_t* rowp = sbuf + row * 128;
 #pragma unroll
@@ -559,6 +572,11 @@ __global__ void __launch_bounds__(64 + 128 * EG + (XF ? (EG == 2 ? 128 : 64) : 0
       vec[i] = a;                                            // group 0's copy doubles as the scale / shift table
       vec[1024 + i] = b;
       if (EG == 2) { vec[2048 + i] = 0.f; vec[3072 + i] = 0.f; }
+    }
+    if (BLOCK_N == 64 && EG == 2 && p.head_logits != nullptr) {   // eval-mode fused head: weights [0, 64), bias at [64]
+      __syncthreads();
+      if (threadIdx.x < 64) vec[2048 + threadIdx.x] = p.head_w[threadIdx.x];
+      if (threadIdx.x == 64) vec[2048 + 64] = p.head_b ? p.head_b[0] : 0.f;
     }
   }
   tc_fence_before();

@@ -55,6 +55,12 @@ struct PixGemmParams {
   // zero AFTER the activation).  Indexed by input channel relative to a_chan0; null = plain operand.
   const float* in_scale;
   const float* in_shift;
+  // Eval-mode last layer (Cout == 64, one n-block): the 1x1 head is evaluated in the epilogue on the bf16-rounded
+  // activations, logits[pixel] = sum_c act[c] * head_w[c] + head_b, and the activation tile is NOT stored (nothing else
+  // reads it in inference).  head_logits: fp32 [B, H, W]; null = plain epilogue.
+  const float* head_w;
+  const float* head_b;
+  float* head_logits;
 };
 
 cudaError_t launch_pix_gemm(const PixGemmParams& p, int block_n, int num_sms, cudaStream_t stream);

@@ -373,6 +373,7 @@ struct cs_unet_plan {
   size_t ws_bytes;
   uint8_t* ws;
   bool bound, forward_done, infer;
+  bool eval_act17_missing;           // the last eval forward did not store dconv1.3's activation (head fused in its epilogue)
   ConvL conv[18];
   UpL up[4];
   bf16* col;                         // im2col of the input image [P1][64]
@@ -753,6 +754,10 @@ static bool fuse_head() {
   return v;
 }
 
+// Eval mode: the head is evaluated in the epilogue of dconv1.3 when that layer runs on the resident-weights Cout = 64
+// kernel (always, unless CARTSEG_CONV3=0 / CARTSEG_FUSE_HEAD=0 select the stand-alone kernels).
+static bool eval_head_fused(const ConvL& c) { return fuse_head() && c.fp_eval.conv3 && c.bn_f == 64 && c.cin <= 128; }
+
 int cs_unet_forward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* x, int training, float* logits,
                     cs_stream_t stream) {
   if (!pl || !pl->bound) return fail("plan is not bound to a workspace");
@@ -809,6 +814,12 @@ int cs_unet_forward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* x, 
       if (c.act_fused) CS_CUDA(launch_bn_finalize(f, s));    // the next convolution applies BN + ReLU to y on the fly
       else CS_CUDA(traced(pl, 1100 + i, s, [&] { return launch_bn_relu(c.y, B, c.H, c.W, c.cout, f, c.out.p, c.out.pitch, c.out.c0, c.pooled, head, s); }));
     } else {
+      // last layer: the 1x1 head rides in the convolution's epilogue and the activation is never written (nothing reads it
+      // in inference): one launch and 0.8 GB of traffic less at B = 64
+      const bool head_in_epilogue = i == 17 && eval_head_fused(c);
+      c.fp_eval.head_w = head_in_epilogue ? t->param[80] : nullptr;
+      c.fp_eval.head_b = head_in_epilogue ? t->param[81] : nullptr;
+      c.fp_eval.head_logits = head_in_epilogue ? logits : nullptr;
       CS_CUDA(timed(pl, conv_class(c.fp_eval, c.bn_f), c.flops, s, [&] { return launch_pix_gemm(c.fp_eval, c.bn_f, pl->num_sms, s); }));
       if (c.pooled) CS_CUDA(launch_maxpool(c.out.p, c.out.pitch, c.out.c0, B, c.H, c.W, c.cout, c.pooled, s));
     }
@@ -823,7 +834,9 @@ int cs_unet_forward(cs_unet_plan* pl, const cs_unet_tensors* t, const float* x, 
     CS_TRY(run_conv(11 + 2 * k));
   }
   const ConvL& last = pl->conv[17];
-  if (!training || !fuse_head()) CS_CUDA(launch_head_fwd(last.out.p, last.P, 64, t->param[80], t->param[81], logits, s));
+  const bool head_done = training ? fuse_head() : eval_head_fused(last);
+  if (!head_done) CS_CUDA(launch_head_fwd(last.out.p, last.P, 64, t->param[80], t->param[81], logits, s));
+  pl->eval_act17_missing = !training && head_done;
   pl->forward_done = training != 0;
   return 0;
 }
@@ -1214,6 +1227,8 @@ int cs_unet_debug_read(cs_unet_plan* pl, int kind, int index, int dims_out[4], f
   }
   if (dims_out) { dims_out[0] = pl->B; dims_out[1] = C; dims_out[2] = H; dims_out[3] = W; }
   if (!dst) return 0;
+  if (kind == 1 && index == 17 && pl->eval_act17_missing)
+    return fail("the last eval-mode forward did not store dconv1.3's activation (the head runs in that layer's epilogue)");
   if (!v.p) return fail("tensor (kind %d, index %d) does not exist in this plan", kind, index);
   if (kind == 1 && !pl->infer && pl->forward_done && ((index == 17 && fuse_head()) || pl->conv[index].act_fused)) {
     // the training path never stores this activation (the head / the next convolution consume y directly): rebuild it
