@@ -441,35 +441,6 @@ cudaError_t launch_bn_apply_relu(const bf16* y, long long P, int C, const float*
   return launched();
 }
 
-__global__ void maxpool_kernel(const bf16* __restrict__ in, int in_pitch, int in_c0, int B, int H, int W, int C,
-                               bf16* __restrict__ pooled) {
-  const int cg = C >> 3, H2 = H >> 1, W2 = W >> 1;
-  const long long total = (long long)B * H2 * W2 * cg;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % cg);
-    const long long q = i / cg;
-    const int w2 = (int)(q % W2);
-    const int h2 = (int)((q / W2) % H2);
-    const int b = (int)(q / ((long long)W2 * H2));
-    float mx[8];
-#pragma unroll
-    for (int d = 0; d < 4; ++d) {
-      const long long p = ((long long)b * H + 2 * h2 + (d >> 1)) * W + 2 * w2 + (d & 1);
-      float f[8];
-      unpack8(ld8(in + p * in_pitch + in_c0 + g * 8), f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) mx[j] = d == 0 ? f[j] : fmaxf(mx[j], f[j]);
-    }
-    st8(pooled + q * C + g * 8, pack8(mx));
-  }
-}
-cudaError_t launch_maxpool(const bf16* in, int in_pitch, int in_c0, int B, int H, int W, int C, bf16* pooled,
-                           cudaStream_t s) {
-  maxpool_kernel<<<grid_for((long long)B * (H / 2) * (W / 2) * (C / 8), 256), 256, 0, s>>>(in, in_pitch, in_c0, B, H, W,
-                                                                                           C, pooled);
-  return launched();
-}
-
 // ============================================================================ BN + ReLU (+ pool/skip) backward
 // g_total(pixel) = g[pixel] (+ g_pool[window] if the pixel is the first maximum of its 2x2 window).
 // mask = (y*scale + shift > 0), evaluated on the bf16-rounded activation exactly as the forward stored it.

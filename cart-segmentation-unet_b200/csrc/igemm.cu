@@ -221,6 +221,30 @@ CS_DEVINL void pix_pair_epilogue(const PixGemmParams& p, uint8_t* stage_base, fl
         tma_store_4d(&p.tmapO[omap], sbuf, p.o_chan0 + nin, w0, h0, b);
         tma_store_commit();
       }
+      if (p.pool_out != nullptr && valid) {
+        // 2x2 max-pool of the staged 8 x 16 pixel tile: 32 pooled pixels x 8 sixteen-byte chunks, two per thread
+        uint8_t* pool = static_cast<uint8_t*>(p.pool_out);
+        const int H2 = p.H >> 1, W2 = p.W >> 1;
+#pragma unroll
+        for (int q = et; q < 256; q += 128) {
+          const int pp = q >> 3, cj = q & 7, ph = pp >> 2, pw = pp & 3;
+          uint4 m = make_uint4(0u, 0u, 0u, 0u);             // post-ReLU values are >= 0
+#pragma unroll
+          for (int d = 0; d < 4; ++d) {
+            const int r = (2 * ph + (d >> 1)) * 8 + 2 * pw + (d & 1);
+            const uint4 t4 = *reinterpret_cast<const uint4*>(sbuf + r * 128 + ((cj ^ (r & 7)) << 4));
+            asm("max.bf16x2 %0, %0, %1;" : "+r"(m.x) : "r"(t4.x));
+            asm("max.bf16x2 %0, %0, %1;" : "+r"(m.y) : "r"(t4.y));
+            asm("max.bf16x2 %0, %0, %1;" : "+r"(m.z) : "r"(t4.z));
+            asm("max.bf16x2 %0, %0, %1;" : "+r"(m.w) : "r"(t4.w));
+          }
+          const int oh = (h0 >> 1) + ph, ow = (w0 >> 1) + pw;
+          if (oh < H2 && ow < W2) {                          // deep levels have ragged tiles (e.g. 12 x 12, 28 x 28 pixels)
+            const size_t pix = ((size_t)b * H2 + oh) * W2 + ow;
+            *reinterpret_cast<uint4*>(pool + (pix * p.Ntot + col0 + cj * 8) * 2) = m;
+          }
+        }
+      }
       if (want_stats) {
         // Column sums over the staged bf16 tile: this warp covers rows [32*sub, 32*sub+32), lane
         // covers the channel pair (2*lane, 2*lane+1).  Tile rows that lie outside the image hold

@@ -61,6 +61,9 @@ struct PixGemmParams {
   const float* head_w;
   const float* head_b;
   float* head_logits;
+  // Eval-mode skip producers: the 2x2 max-pooled copy of the output tile (NHWC bf16, pitch Ntot, half resolution) is
+  // written from the staged tile in the epilogue — no separate max-pool pass.  H and W must be even.
+  void* pool_out;
 };
 
 cudaError_t launch_pix_gemm(const PixGemmParams& p, int block_n, int num_sms, cudaStream_t stream);

@@ -75,10 +75,6 @@ cudaError_t launch_bn_apply_relu(const bf16* y, long long P, int C, const float*
 cudaError_t launch_bn_finalize(const BnFinalizeArgs& fin, cudaStream_t s);
 cudaError_t launch_bn_relu(const bf16* y, int B, int H, int W, int C, const BnFinalizeArgs& fin, bf16* out,
                            int out_pitch, int out_c0, bf16* pooled, const HeadFwd& head, cudaStream_t s);
-// relu/bn already applied (eval path): plain 2x2 max-pool of in[p][c0 + c] (pitch in_pitch) -> pooled (pitch C)
-cudaError_t launch_maxpool(const bf16* in, int in_pitch, int in_c0, int B, int H, int W, int C, bf16* pooled,
-                           cudaStream_t s);
-
 struct BnBwdArgs {
   const bf16* g; int g_pitch, g_c0;        // gradient w.r.t. the post-ReLU activation
   const float* head_dlogits;               // optional (no pooling): g[p][c] = bf16(head_dlogits[p] * head_w[c]) instead of `g`
