@@ -131,7 +131,10 @@ CS_DEVINL void bnrelu_patch(uint8_t* slot, int t, const float* __restrict__ sc_g
 // Epilogue of the CTA-pair pixel GEMMs (EG groups of 128 threads, warps 2..): TMEM -> registers -> (affine / ReLU) -> bf16 ->
 // 128B-swizzled staging tile -> TMA store; train-mode BN statistics (sum, sum of squares) from the staged bf16 tile.
 // Shared by pix_gemm2_kernel and conv3_gemm_kernel.
-template <int BLOCK_N, int EG, int BPG, class Decode>
+// EVALX: the eval-only extras (fused 1x1 head, 2x2 max-pooled copy) are compiled in.  They are a template parameter, not
+// a run-time branch: carried by the training instantiations they cost 6-9 % of the Cout = 64 / conv-transpose kernels
+// (registers and code in the loop that paces them; measured same-box, 16.2 -> 16.4 ms per K2 step).
+template <int BLOCK_N, int EG, int BPG, bool EVALX, class Decode>
 CS_DEVINL void pix_pair_epilogue(const PixGemmParams& p, uint8_t* stage_base, float* vec, float* red_base, uint64_t* tmem_full,
                                  uint64_t* tmem_empty, uint32_t tmem_base, int warp, int lane, int first_unit, int unit_stride,
                                  int num_units, bool want_stats, Decode&& decode) {
@@ -194,7 +197,7 @@ CS_DEVINL void pix_pair_epilogue(const PixGemmParams& p, uint8_t* stage_base, fl
 #pragma unroll
         for (int i = 0; i < 32; ++i) packed[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
       }
-      if (BLOCK_N == 64 && EG == 2 && p.head_logits != nullptr) {
+      if (EVALX && BLOCK_N == 64 && EG == 2 && p.head_logits != nullptr) {
         // fused 1x1 head (eval): this thread holds all 64 channels of its pixel; the activation tile is not stored
         const float* hw = vec + 2048;                      // head weights (group 1's statistics slots: unused in eval)
         float acc = 0.f;
@@ -221,7 +224,7 @@ CS_DEVINL void pix_pair_epilogue(const PixGemmParams& p, uint8_t* stage_base, fl
         tma_store_4d(&p.tmapO[omap], sbuf, p.o_chan0 + nin, w0, h0, b);
         tma_store_commit();
       }
-      if (p.pool_out != nullptr && valid) {
+      if (EVALX && p.pool_out != nullptr && valid) {
         // 2x2 max-pool of the staged 8 x 16 pixel tile: 32 pooled pixels x 8 sixteen-byte chunks, two per thread
         uint8_t* pool = static_cast<uint8_t*>(p.pool_out);
         const int H2 = p.H >> 1, W2 = p.W >> 1;
@@ -493,8 +496,8 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) pix_gemm2_kernel(const __gri
     }
   } else {
     // ------------------------------------------------------------------ epilogue (EG groups of 128 threads)
-    pix_pair_epilogue<BLOCK_N, EG, BPG>(p, smem + L::kStage, vec, reinterpret_cast<float*>(smem + L::kRed), tmem_full, tmem_empty,
-                                        tmem_base, warp, lane, first_unit, unit_stride, num_units, want_stats, decode);
+    pix_pair_epilogue<BLOCK_N, EG, BPG, false>(p, smem + L::kStage, vec, reinterpret_cast<float*>(smem + L::kRed), tmem_full, tmem_empty,
+                                               tmem_base, warp, lane, first_unit, unit_stride, num_units, want_stats, decode);
   }
   tc_fence_before();
   if (PAIR) cluster_sync();                                  // the peer's smem / TMEM / barriers stay alive until here
@@ -543,7 +546,7 @@ struct Conv3Layout {
   static_assert(RESIDENT || (3 * SA) % SB == 0, "the weight-ring slot of (A slot, tap group) must be a compile-time constant");
 };
 
-template <int BLOCK_N, int PW, int SA, int SB, int NSTG, int EG, bool RESIDENT, bool XF>
+template <int BLOCK_N, int PW, int SA, int SB, int NSTG, int EG, bool RESIDENT, bool XF, bool EVALX>
 __global__ void __launch_bounds__(64 + 128 * EG + (XF ? (EG == 2 ? 128 : 64) : 0), 1) conv3_gemm_kernel(const __grid_constant__ PixGemmParams p) {
   using L = Conv3Layout<BLOCK_N, PW, SA, SB, NSTG, EG, RESIDENT, XF>;
   static_assert(NSTG % EG == 0, "every epilogue group owns NSTG / EG staging buffers");
@@ -597,7 +600,7 @@ __global__ void __launch_bounds__(64 + 128 * EG + (XF ? (EG == 2 ? 128 : 64) : 0
       vec[1024 + i] = b;
       if (EG == 2) { vec[2048 + i] = 0.f; vec[3072 + i] = 0.f; }
     }
-    if (BLOCK_N == 64 && EG == 2 && p.head_logits != nullptr) {   // eval-mode fused head: weights [0, 64), bias at [64]
+    if (EVALX && BLOCK_N == 64 && EG == 2 && p.head_logits != nullptr) {   // eval-mode fused head: weights [0, 64), bias at [64]
       __syncthreads();
       if (threadIdx.x < 64) vec[2048 + threadIdx.x] = p.head_w[threadIdx.x];
       if (threadIdx.x == 64) vec[2048 + 64] = p.head_b ? p.head_b[0] : 0.f;
@@ -762,8 +765,8 @@ __global__ void __launch_bounds__(64 + 128 * EG + (XF ? (EG == 2 ? 128 : 64) : 0
       }
     }
   } else {
-    pix_pair_epilogue<BLOCK_N, EG, BPG>(p, smem + L::kStage, vec, reinterpret_cast<float*>(smem + L::kRed), tmem_full, tmem_empty,
-                                        tmem_base, warp, lane, first_unit, unit_stride, num_units, want_stats, decode);
+    pix_pair_epilogue<BLOCK_N, EG, BPG, EVALX>(p, smem + L::kStage, vec, reinterpret_cast<float*>(smem + L::kRed), tmem_full, tmem_empty,
+                                               tmem_base, warp, lane, first_unit, unit_stride, num_units, want_stats, decode);
   }
   tc_fence_before();
   cluster_sync();                                            // the peer's smem / TMEM / barriers stay alive until here
@@ -773,11 +776,11 @@ __global__ void __launch_bounds__(64 + 128 * EG + (XF ? (EG == 2 ? 128 : 64) : 0
   }
 }
 
-template <int BLOCK_N, int PW, int SA, int SB, int NSTG, int EG, bool RESIDENT, bool XF>
+template <int BLOCK_N, int PW, int SA, int SB, int NSTG, int EG, bool RESIDENT, bool XF, bool EVALX = false>
 static cudaError_t launch_conv3(const PixGemmParams& p, int num_sms, cudaStream_t stream) {
   using L = Conv3Layout<BLOCK_N, PW, SA, SB, NSTG, EG, RESIDENT, XF>;
   static_assert(L::kDyn <= 232448, "shared memory budget exceeded");
-  auto kern = conv3_gemm_kernel<BLOCK_N, PW, SA, SB, NSTG, EG, RESIDENT, XF>;
+  auto kern = conv3_gemm_kernel<BLOCK_N, PW, SA, SB, NSTG, EG, RESIDENT, XF, EVALX>;
   static std::atomic<unsigned long long> attr_done{0};
   {
     cudaError_t ae = ensure_dynamic_smem(kern, L::kDyn, attr_done);
@@ -1011,8 +1014,8 @@ __global__ void __launch_bounds__(64 + 128 * EG + 64, 1) stem_gemm_kernel(const 
       if (++sx == SX) { sx = 0; px ^= 1; }
     }
   } else {
-    pix_pair_epilogue<BLOCK_N, EG, 1>(p, smem + L::kStage, vec, reinterpret_cast<float*>(smem + L::kRed), tmem_full, tmem_empty,
-                                      tmem_base, warp, lane, first_unit, unit_stride, num_units, want_stats, decode);
+    pix_pair_epilogue<BLOCK_N, EG, 1, false>(p, smem + L::kStage, vec, reinterpret_cast<float*>(smem + L::kRed), tmem_full, tmem_empty,
+                                             tmem_base, warp, lane, first_unit, unit_stride, num_units, want_stats, decode);
   }
   tc_fence_before();
   cluster_sync();
@@ -1063,6 +1066,15 @@ static cudaError_t launch_conv3_gemm(const PixGemmParams& p, int block_n, int nu
                                : launch_conv3<64, 10, 4, 3, 2, 2, false, true>(p, num_sms, stream);
       case 128: return launch_conv3<128, 10, 4, 3, 2, 2, false, true>(p, num_sms, stream);
       case 256: return launch_conv3<256, 10, 2, 3, 1, 1, false, true>(p, num_sms, stream);
+      default: return cudaErrorInvalidValue;
+    }
+  }
+  if (p.pool_out != nullptr || p.head_logits != nullptr) {   // eval-mode extras: the instantiations that carry them
+    switch (block_n) {
+      case 64: return resident ? launch_conv3<64, 10, 4, 3, 2, 2, true, false, true>(p, num_sms, stream)
+                               : launch_conv3<64, 10, 4, 3, 2, 2, false, false, true>(p, num_sms, stream);
+      case 128: return launch_conv3<128, 10, 4, 3, 2, 2, false, false, true>(p, num_sms, stream);
+      case 256: return launch_conv3<256, 10, 2, 3, 1, 1, false, false, true>(p, num_sms, stream);
       default: return cudaErrorInvalidValue;
     }
   }
