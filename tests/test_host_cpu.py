@@ -253,3 +253,16 @@ def test_bench_reference_arm_contract():
         r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True,
                            text=True, timeout=600)
         assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_default_bucket_policy_depends_on_world_size():
+    """Overlapped 16 MB buckets up to 2 ranks, one all-reduce after the backward pass from 4 ranks on (measured on
+    8 x B200: cartseg/parallel.py, profiles/r2_bench_k2_8gpu_bucket*mb.json); either way every stage is covered once."""
+    from cartseg import parallel
+    assert parallel.default_bucket_mb(1) == parallel.DEFAULT_BUCKET_MB == parallel.default_bucket_mb(2)
+    assert parallel.default_bucket_mb(4) == parallel.default_bucket_mb(8) == parallel.LARGE_WORLD_BUCKET_MB
+    stage_off = [0, 65, 65 + 36_928, 200_000, 5_000_000, 31_000_000]
+    one = parallel.plan_buckets(stage_off, int(parallel.LARGE_WORLD_BUCKET_MB * (1 << 20) / 4))
+    assert one == [(0, 5)]
+    many = parallel.plan_buckets(stage_off, int(parallel.DEFAULT_BUCKET_MB * (1 << 20) / 4))
+    assert many[0][0] == 0 and many[-1][1] == 5 and all(a[1] == b[0] for a, b in zip(many, many[1:]))
