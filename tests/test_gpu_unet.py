@@ -461,3 +461,36 @@ def test_rejects_cpu_input_and_bad_shapes():
         m(torch.zeros(1, 3, 30, 32, device="cuda"))
     with pytest.raises(Exception):
         m(torch.zeros(1, 4, 32, 32, device="cuda"))
+
+
+@pytest.mark.parametrize("cin", [1, 4, 7])
+def test_other_input_channel_counts(cin):
+    """UNet(in_channels=...) (src/create_testset.py:54): the first convolution's generic path (any 1..7 channels; the
+    benchmarked 3-channel path is a compile-time specialisation) — eval logits and one training step against the oracle."""
+    import cartseg
+    from oracle import unet_oracle as O
+    torch.manual_seed(40 + cin)
+    sd = {k: v.detach().clone() for k, v in cartseg.UNet(in_channels=cin).state_dict().items()}
+    g = torch.Generator().manual_seed(cin)
+    x = torch.randn(2, cin, 48, 32, generator=g)
+    tgt = (torch.rand(2, 1, 48, 32, generator=g) > 0.6).float()
+    with torch.no_grad():
+        ref = O.unet_logits(x, {k: v.clone() for k, v in sd.items()}, training=False)
+    m = _model(sd, in_channels=cin)
+    with torch.no_grad():
+        got = m.eval()(x.cuda()).cpu()
+    assert rel_l2(got, ref) < 2e-2
+    m.train()
+    crit = cartseg.BCEDiceLoss()
+    loss = crit(m(x.cuda()), tgt.cuda())
+    loss.backward()
+    z_ref = O.unet_logits(x, {k: v.clone() for k, v in sd.items()}, training=True)
+    assert abs(loss.item() - float(O.bce_dice_loss(z_ref, tgt))) < 1e-2
+    gw = m.conv1.conv[0].weight.grad
+    assert gw is not None and torch.isfinite(gw).all() and gw.abs().max() > 0 and tuple(gw.shape) == (64, cin, 3, 3)
+    # the first convolution's weight gradient (im2col of the cin-channel image on the side stream): direction against the
+    # fp32 oracle (end-to-end gradients of this ReLU network are ill-conditioned, DESIGN.md section 1: cosine, not rel-L2)
+    g_ref = _oracle_train(O, x, tgt, sd, O.bce_dice_loss)[2]["conv1.conv.0.weight"]
+    cos = float(torch.dot(gw.cpu().double().flatten(), g_ref.double().flatten()) / (gw.cpu().double().norm() * g_ref.double().norm()))
+    print(f"cin={cin}: conv1.conv.0.weight gradient cosine vs fp32 oracle {cos:.4f}")
+    assert cos > 0.9
